@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+For every case it loads the synthetic weights of ``oracle/weights.py`` (strict
+``load_state_dict``) into the reference's own ``Seq2Seq_HighLevel_CMA`` /
+``Seq2Seq_LowLevel`` (imported through ``oracle/ref_loader.py``), feeds the seeded inputs
+of ``weights.make_inputs`` and records the outputs plus the intermediates named in
+SURVEY.md Appendix A (captured with forward hooks -- no reference code is modified).
+The fixtures hold outputs only; weights and inputs are re-generated from their seeds.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import weights as W            # noqa: E402
+from oracle.ref_loader import build_reference_models  # noqa: E402
+
+# name -> kwargs of weights.make_inputs (+ T/N bookkeeping)
+CASES = {
+    # BASELINE.json configs[0]: batch=2, 256x256 RGB-D, 20 tokens (trajectory-shaped T=2,N=1)
+    "cfg1_b2_l20": dict(B=2, L=20, N=1, rgb_hw=256, seed=1, mask_zero_rows=(0,)),
+    # trajectory with an episode reset in the middle, one shared instruction row, PAD tail
+    "traj_t5_reset_pad": dict(B=5, L=12, N=1, rgb_hw=256, seed=2, shared_instruction=True,
+                              pad_tail=4, mask_zero_rows=(0, 3)),
+    # the reference's native 224x224 RGB (adaptive pool 7x7 -> 4x4 with overlapping windows),
+    # single step with mask = 1 so the incoming hidden state is carried
+    "step_rgb224_keep_hidden": dict(B=1, L=8, N=1, rgb_hw=224, seed=3, mask_zero_rows=()),
+}
+
+
+def run_case(hi, lo, kw):
+    inp = W.make_inputs(**kw)
+    cap = {}
+
+    def grab(name, multi=False):
+        def hook(_m, _i, o):
+            o = o[0] if isinstance(o, tuple) else o
+            o = o.last_hidden_state if hasattr(o, "last_hidden_state") else o
+            if multi:
+                cap.setdefault(name, []).append(o.detach().clone())
+            else:
+                cap[name] = o.detach().clone()
+        return hook
+
+    hooks = [
+        hi.depth_encoder.register_forward_hook(grab("hi.depth_embedding")),
+        hi.rgb_encoder.register_forward_hook(grab("hi.rgb_embedding")),
+        hi.embedding_layer.register_forward_hook(grab("hi.bert")),
+        hi.image_cm_encoder.register_forward_hook(grab("hi.vla", multi=True)),
+        hi.state_encoder.register_forward_hook(grab("hi.rnn_out")),
+        lo.depth_encoder.register_forward_hook(grab("lo.depth_embedding")),
+        lo.rgb_encoder.register_forward_hook(grab("lo.rgb_embedding")),
+        lo.state_encoder.register_forward_hook(grab("lo.rnn_out")),
+    ]
+    hi.state_encoder.register_forward_pre_hook(lambda _m, a: cap.__setitem__("hi.rnn_in", a[0].detach().clone()))
+    lo.state_encoder.register_forward_pre_hook(lambda _m, a: cap.__setitem__("lo.rnn_in", a[0].detach().clone()))
+    with torch.no_grad():
+        obs = {"rgb": inp["rgb"], "depth": inp["depth"], "instruction": inp["instruction"].clone()}
+        logits, hid_hi = hi((obs, inp["hidden_hi"], inp["prev_actions"], inp["masks"]))
+        assert "instruction" not in obs          # seq2seq_highlevel_cma.py:196 deletes it
+        obs = {"rgb": inp["rgb"], "depth": inp["depth"]}
+        act, stop, hid_lo = lo((obs, inp["hidden_lo"], inp["prev_actions"], inp["masks"], inp["sub_goal"]))
+    for h in hooks:
+        h.remove()
+    out = {
+        "hi.logits": logits, "hi.hidden": hid_hi,
+        "lo.actions": act, "lo.stop": stop, "lo.hidden": hid_lo,
+        "hi.ins_rgb_att_tokens": cap["hi.vla"][0], "hi.ins_depth_att_tokens": cap["hi.vla"][1],
+    }
+    for k, v in cap.items():
+        if k != "hi.vla":
+            out[k] = v
+    return {k: v.numpy().astype(np.float32) for k, v in out.items()}
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 8)
+    hi, lo = build_reference_models()
+    missing = hi.load_state_dict(W.make_state_dict("hi", 0), strict=True)
+    lo.load_state_dict(W.make_state_dict("lo", 0), strict=True)
+    print("loaded synthetic weights (strict):", missing)
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, kw in CASES.items():
+        res = run_case(hi, lo, kw)
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(path, **res)
+        print(name, {k: (v.shape, float(np.abs(v).max())) for k, v in res.items()})
+        print("  ->", path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

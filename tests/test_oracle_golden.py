@@ -1,0 +1,65 @@
+"""The CPU oracle (oracle/hcm_oracle.py) against fixtures produced by the unmodified
+reference (oracle/make_golden.py).  fp32 CPU vs fp32 CPU: tolerance 2e-4 abs on O(1..4)
+values (different op ordering inside F.* vs nn.Module paths is the only source of drift)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hcm_oracle as O
+from oracle import weights as W
+from oracle.make_golden import CASES
+
+TOL = 2e-4
+
+
+@pytest.fixture(scope="module")
+def sds():
+    return W.make_state_dict("hi", 0), W.make_state_dict("lo", 0)
+
+
+def _close(a, b, name, tol=TOL):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else a
+    err = float(np.abs(a - b).max())
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    assert err <= tol, f"{name}: max abs err {err:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_oracle_matches_reference_golden(case, sds, golden_dir):
+    hi_sd, lo_sd = sds
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
+    kw = CASES[case]
+    inp = W.make_inputs(**kw)
+    with torch.no_grad():
+        logits, hid, it = O.hi_forward(hi_sd, inp["rgb"], inp["depth"], inp["instruction"],
+                                       inp["hidden_hi"], inp["masks"], return_intermediates=True)
+        act, stop, hid_lo, il = O.lo_forward(lo_sd, inp["rgb"], inp["depth"], inp["hidden_lo"],
+                                             inp["masks"], inp["sub_goal"], return_intermediates=True)
+    B = inp["rgb"].shape[0]
+    _close(it["depth_embedding"].view(B, 192, 4, 4), gold["hi.depth_embedding"], "hi.depth_embedding")
+    _close(it["rgb_embedding"].view(B, 2112, 4, 4), gold["hi.rgb_embedding"], "hi.rgb_embedding")
+    _close(it["bert"], gold["hi.bert"], "hi.bert")
+    _close(it["rnn_in"], gold["hi.rnn_in"], "hi.rnn_in")
+    _close(it["rnn_out"], gold["hi.rnn_out"], "hi.rnn_out")
+    _close(it["ins_rgb_att"], gold["hi.ins_rgb_att_tokens"].mean(axis=1), "ins_rgb_att")
+    _close(it["ins_depth_att"], gold["hi.ins_depth_att_tokens"].mean(axis=1), "ins_depth_att")
+    _close(logits, gold["hi.logits"], "hi.logits")
+    _close(hid, gold["hi.hidden"], "hi.hidden")
+    _close(il["depth_embedding"], gold["lo.depth_embedding"], "lo.depth_embedding")
+    _close(il["rgb_embedding"], gold["lo.rgb_embedding"], "lo.rgb_embedding")
+    _close(il["rnn_in"], gold["lo.rnn_in"], "lo.rnn_in")
+    _close(act, gold["lo.actions"], "lo.actions")
+    _close(stop, gold["lo.stop"], "lo.stop")
+    _close(hid_lo, gold["lo.hidden"], "lo.hidden")
+
+
+def test_golden_features_are_nontrivial(golden_dir):
+    """Guards against a degenerate fixture (dead ReLUs / all-zero trunk features)."""
+    g = np.load(os.path.join(golden_dir, "cfg1_b2_l20.npz"))
+    rgb = g["hi.rgb_embedding"][:, :2048]
+    dep = g["hi.depth_embedding"][:, :128]
+    assert (rgb > 0).mean() > 0.2 and rgb.std() > 0.05
+    assert (dep > 0).mean() > 0.2 and dep.std() > 0.05
+    assert np.abs(g["hi.logits"][0] - g["hi.logits"][1]).max() > 1e-3
