@@ -1,0 +1,155 @@
+/*
+ * robovln_b200 -- C ABI of the B200-native HCM policy forward pass.
+ *
+ * The reference (GT-RIPL/robo-vln) has no plugin / FFI layer: its seam for this path is the
+ * Python nn.Module API consumed by robo_vln_baselines/hierarchical_trainer.py:50-51,506,539,
+ * 1096-1100.  The Python classes in robo-vln_b200/ mirror that API and call the functions
+ * below through ctypes; every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are raw addresses in the current CUDA context;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no function synchronises the device or allocates device memory; all scratch lives in
+ *     the caller-provided workspace given to hcm_plan();
+ *   - return value 0 = success, otherwise a cudaError_t or -1; hcm_last_error() returns a
+ *     thread-local message for the last failure;
+ *   - rows of a batch are ordered t-major (row = t*N + n), exactly as
+ *     RNNStateEncoder.seq_forward expects (habitat_baselines/rl/models/rnn_state_encoder.py:85-100).
+ */
+#ifndef ROBOVLN_B200_H_
+#define ROBOVLN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hcm_engine hcm_engine;
+
+enum { HCM_F32 = 0, HCM_BF16 = 1, HCM_I64 = 2 };
+
+/* Shape of one forward call. */
+typedef struct hcm_shape {
+  int32_t B;          /* rows in the batch = T*N                                             */
+  int32_t N;          /* environments (columns of the hidden state [2,N,512])                 */
+  int32_t L;          /* instruction tokens                                                   */
+  int32_t instr_rows; /* 1 (one instruction shared by all rows, expanded like
+                         seq2seq_highlevel_cma.py:189-190) or B                               */
+  int32_t rgb_h, rgb_w;     /* RGB frame size (reference default 224x224; BASELINE 256x256)   */
+  int32_t depth_h, depth_w; /* depth frame size (256x256)                                     */
+} hcm_shape;
+
+const char* hcm_last_error(void);
+const char* hcm_version(void);
+
+/* ---- engine lifetime ------------------------------------------------------------------ */
+int  hcm_create(hcm_engine** out);
+void hcm_destroy(hcm_engine* e);
+
+/* Register a prepared (kernel-layout) weight tensor living in device memory.  The engine keeps
+ * the pointer, not a copy; the Python modules own the storage and re-register after
+ * load_state_dict()/optimizer steps.  Names are listed in robo-vln_b200/weight_prep.py; they
+ * derive from the reference state_dict keys. */
+int hcm_set_tensor(hcm_engine* e, const char* name, const void* dev_ptr, int dtype, int ndim,
+                   const int64_t* shape);
+/* Declare which halves are present: the hi model (Seq2Seq_HighLevel_CMA), the lo model
+ * (Seq2Seq_LowLevel), and whether lo's frozen trunks are bit-identical to hi's so that one
+ * trunk pass serves both (SURVEY.md 7.2 "dedup legality"). */
+int hcm_finalize_weights(hcm_engine* e, int have_hi, int have_lo, int lo_shares_trunks);
+
+/* ---- planning -------------------------------------------------------------------------- */
+size_t hcm_workspace_bytes(hcm_engine* e, const hcm_shape* shape);
+int    hcm_plan(hcm_engine* e, const hcm_shape* shape, void* workspace, size_t workspace_bytes);
+
+/* ---- forward --------------------------------------------------------------------------- */
+/* Seq2Seq_HighLevel_CMA.forward (robo_vln_baselines/models/seq2seq_highlevel_cma.py:170-233).
+ *   rgb [B,rgb_h,rgb_w,3] f32 0..255, depth [B,depth_h,depth_w,1] f32,
+ *   instruction ids as f32 (what the trainer passes) OR i64 (exactly one non-NULL), [instr_rows,L],
+ *   masks: element (row*mask_stride) is masks[row,0]; hc_in/hc_out [2,N,512] f32 (no aliasing),
+ *   logits [B,4] f32. */
+int hcm_forward_hi(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                   const int64_t* instr_i64, const float* masks, int mask_stride, const float* hc_in,
+                   float* logits, float* hc_out, void* stream);
+
+/* Seq2Seq_LowLevel.forward (robo_vln_baselines/models/seq2seq_lowlevel.py:116-162).
+ *   sub_goal i64 [B] in 0..4; actions [B,2], stop_logit [B,1].
+ *   reuse_trunks != 0: take the RGB/depth features computed by the preceding hcm_forward_hi on
+ *   the same observations (only legal when hcm_finalize_weights was told lo_shares_trunks). */
+int hcm_forward_lo(hcm_engine* e, const float* rgb, const float* depth, const float* masks,
+                   int mask_stride, const int64_t* sub_goal, const float* hc_in, float* actions,
+                   float* stop_logit, float* hc_out, int reuse_trunks, void* stream);
+
+/* One rollout step of the hierarchy as hierarchical_trainer.py:1095-1101 runs it:
+ * hi -> argmax over the 4 sub-goal logits -> lo, trunks evaluated once.
+ *   sub_goal_out i64 [B] receives the argmax (may be NULL). */
+int hcm_forward_policy(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                       const int64_t* instr_i64, const float* masks, int mask_stride,
+                       const float* hc_hi_in, const float* hc_lo_in, float* logits, float* actions,
+                       float* stop_logit, float* hc_hi_out, float* hc_lo_out, int64_t* sub_goal_out,
+                       void* stream);
+
+/* Same step with HOST buffers (pinned recommended): H2D of the observations, the forward, and
+ * D2H of the outputs are all enqueued on `stream`; the call returns after synchronising it.
+ * This is the end-to-end entry bench.py times. */
+int hcm_forward_policy_host(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                            const float* masks, const float* hc_hi_in, const float* hc_lo_in,
+                            float* logits, float* actions, float* stop_logit, float* hc_hi_out,
+                            float* hc_lo_out, void* stream);
+
+/* Number of kernels the last forward call launched (for bench.py's gpu_launches). */
+int64_t hcm_last_launch_count(hcm_engine* e);
+
+/* Profiling replay of hcm_forward_policy on ONE stream with a CUDA event between consecutive
+ * launches.  Writes a JSON array [{"name","ms","flops"}...] (flops = algorithmic 2*M*N*K of
+ * tensor-core launches, 0 for the others) into json_out.  Synchronises `stream`. */
+int hcm_profile_policy(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                       const int64_t* instr_i64, const float* masks, int mask_stride,
+                       const float* hc_hi_in, const float* hc_lo_in, float* logits, float* actions,
+                       float* stop_logit, float* hc_hi_out, float* hc_lo_out, char* json_out,
+                       size_t json_cap, void* stream);
+
+/* ---- stage entry points (parity tests, ncu) --------------------------------------------- */
+/* Each runs one stage on the planned shape and leaves its result in an engine buffer that
+ * hcm_get_buffer exposes (name -> device pointer, dtype, shape). */
+int hcm_run_rgb_trunk(hcm_engine* e, const float* rgb, int use_lo_weights, void* stream);
+int hcm_run_depth_trunk(hcm_engine* e, const float* depth, int use_lo_weights, void* stream);
+int hcm_run_bert(hcm_engine* e, const float* instr_f32, const int64_t* instr_i64, void* stream);
+/* cross-modal block on caller tensors: bert [R*L,768] bf16 (R = B or 1 per the plan),
+ * rgb_spatial / depth_spatial [B*16,256] bf16 (outputs of rgb_kv / depth_kv) ->
+ * pooled [B, 512] bf16 (ins_rgb_att | ins_depth_att).  BASELINE.json configs[2]. */
+int hcm_run_cross_modal(hcm_engine* e, const void* bert_bf16, const void* rgb_spatial_bf16,
+                        const void* depth_spatial_bf16, void* pooled_bf16, void* stream);
+int hcm_get_buffer(hcm_engine* e, const char* name, void** dev_ptr, int* dtype, int* ndim,
+                   int64_t* shape /* [>=4] */);
+
+/* Device-to-device copy of a stage buffer into caller memory (bytes must match exactly). */
+int hcm_copy_buffer(hcm_engine* e, const char* name, void* dst_dev, size_t bytes, void* stream);
+
+/* ---- kernel-level entry points (unit parity tests) -------------------------------------- */
+/* Implicit-GEMM convolution / linear layer on NHWC bf16:
+ *   out[m,n] = act(sum A(m,tap,c) W[n,tap*Cin+c] + bias[n] + res[m % res_rows, n]).
+ * impl: 0 = tcgen05 kernel, 1 = CUDA-core validation kernel.  force_bn: 0 or 64/128/256. */
+int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in_pitch,
+                  const void* w_bf16, int Cout, int KH, int KW, int stride, int pad,
+                  const float* bias, const void* res_bf16, int64_t ldr, int res_rows, int act,
+                  void* out, int64_t ldc, int out_f32, int force_bn, int impl, void* stream);
+int rvb_groupnorm(const void* x_bf16, float* stats /* [NB,G,2] zeroed by the call */, const float* gamma,
+                  const float* beta, int NB, int HW, int C, int G, int relu, const void* res_bf16,
+                  void* out_bf16, int64_t out_pitch, void* stream);
+int rvb_layernorm(const float* x, int M, int D, const float* gamma, const float* beta, float eps,
+                  const float* pe, int pe_rows, void* out_bf16, void* stream);
+int rvb_bert_attention(const void* qkv_bf16, void* ctx_bf16, int R, int L, int heads, void* stream);
+int rvb_vla_attention(const void* q_bf16, const void* kv_bf16, void* ctx_bf16, int B, int L, int q_rows,
+                      void* stream);
+int rvb_lstm(const float* gx, const void* whh_bf16, const float* masks, int mask_stride,
+             const float* hc_in, float* hc_out, float* h_scratch, float* y, int T, int N, void* stream);
+int rvb_maxpool3x3s2(const void* in_bf16, void* out_bf16, int NB, int H, int W, int C, void* stream);
+int rvb_rgb_stem_im2col(const float* rgb, void* out_bf16, int NB, int H, int W, int Kpitch, void* stream);
+int rvb_depth_stem(const float* depth, const float* w, void* out_bf16, int NB, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBOVLN_B200_H_ */

@@ -1,0 +1,91 @@
+"""ctypes binding of librobovln_b200.so (C ABI: include/robovln_b200.h).
+
+The product path has no fallback: if the shared library is missing and cannot be built the
+import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librobovln_b200.so")
+
+
+class HcmShape(ctypes.Structure):
+    _fields_ = [
+        ("B", c_int32), ("N", c_int32), ("L", c_int32), ("instr_rows", c_int32),
+        ("rgb_h", c_int32), ("rgb_w", c_int32), ("depth_h", c_int32), ("depth_w", c_int32),
+    ]
+
+
+# name -> (restype, argtypes); the loader checks that every symbol of the header is exported.
+SYMBOLS = {
+    "hcm_last_error": (c_char_p, []),
+    "hcm_version": (c_char_p, []),
+    "hcm_create": (c_int, [POINTER(c_void_p)]),
+    "hcm_destroy": (None, [c_void_p]),
+    "hcm_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),
+    "hcm_finalize_weights": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "hcm_workspace_bytes": (c_size_t, [c_void_p, POINTER(HcmShape)]),
+    "hcm_plan": (c_int, [c_void_p, POINTER(HcmShape), c_void_p, c_size_t]),
+    "hcm_forward_hi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
+    "hcm_forward_lo": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_void_p]),
+    "hcm_forward_policy": (c_int, [c_void_p] + [c_void_p] * 5 + [c_int] + [c_void_p] * 9),
+    "hcm_forward_policy_host": (c_int, [c_void_p] + [c_void_p] * 12),
+    "hcm_last_launch_count": (c_int64, [c_void_p]),
+    "hcm_profile_policy": (c_int, [c_void_p] + [c_void_p] * 5 + [c_int] + [c_void_p] * 7 + [c_char_p, c_size_t, c_void_p]),
+    "hcm_run_rgb_trunk": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "hcm_run_depth_trunk": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "hcm_run_bert": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hcm_run_cross_modal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hcm_get_buffer": (c_int, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
+    "hcm_copy_buffer": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),
+    "rvb_conv_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int,
+                              c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int,
+                              c_void_p]),
+    "rvb_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                              c_void_p, c_int64, c_void_p]),
+    "rvb_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "rvb_bert_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rvb_vla_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rvb_lstm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                         c_void_p]),
+    "rvb_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "rvb_rgb_stem_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "rvb_depth_stem": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise ImportError(f"{LIB_PATH} is missing; run `python robo-vln_b200/build.py`")
+        from .build import build  # needs nvcc; raises if it is absent
+
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a header symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class HcmError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().hcm_last_error()
+        raise HcmError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,251 @@
+// Attention kernels.
+//  * bert_self_attention: softmax(Q K^T / 8) V per (row, head) for BERT-base (12 heads x 64),
+//    all-ones mask because the reference calls BertModel with input_ids only
+//    (seq2seq_highlevel_cma.py:192-195).  L <= 256 keys fit one CTA; scores stay in registers.
+//    L=80 makes each head a 80x80x64 problem (1.7% of BERT's FLOPs), which does not fill a
+//    128-row tcgen05 tile, so this kernel uses warp-level mma.sync m16n8k16 (one 16-query
+//    tile per warp) -- the big BERT contractions go through gemm_tc.cu.
+//  * vla_cross_attention: ScaledDotProductAttention of Visual_Ling_Attn
+//    (transformer.py:81-109) -- 4 heads x 64 over only 16 visual keys; CUDA cores.
+#include "common.cuh"
+#include "rvb.h"
+
+namespace rvb {
+
+namespace {
+
+constexpr int HD = 64;        // head dim
+constexpr int PITCH = HD + 8; // smem row pitch (bf16) -> conflict-free ldmatrix
+
+RVB_DEVICE void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+RVB_DEVICE void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+RVB_DEVICE void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// LKT = number of 16-key tiles (keys padded to 16*LKT)
+template <int LKT>
+__global__ void __launch_bounds__(256) bert_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int L,
+                                                        int heads) {
+  constexpr int LP = LKT * 16;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(sm_raw);
+  bf16* sK = sQ + LP * PITCH;
+  bf16* sV = sK + LP * PITCH;
+  const int head = blockIdx.x;
+  const int row = blockIdx.y;
+  const int H3 = heads * HD * 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  // stage Q, K, V head slices (zero-padded to LP rows)
+  const bf16* src = qkv + static_cast<long long>(row) * L * H3 + head * HD;
+  for (int i = threadIdx.x; i < LP * 8 * 3; i += blockDim.x) {
+    const int which = i / (LP * 8);
+    const int rem = i - which * LP * 8;
+    const int l = rem >> 3, v = rem & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (l < L) val = *reinterpret_cast<const uint4*>(src + static_cast<long long>(l) * H3 + which * heads * HD + v * 8);
+    bf16* dst = (which == 0 ? sQ : (which == 1 ? sK : sV)) + l * PITCH + v * 8;
+    *reinterpret_cast<uint4*>(dst) = val;
+  }
+  __syncthreads();
+
+  const int qtiles = (L + 15) / 16;
+  for (int qt = warp; qt < qtiles; qt += nwarps) {
+    // Q fragments for the 4 k-steps
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r = qt * 16 + (lane & 15);
+      const int c = ks * 16 + (lane >> 4) * 8;
+      ldmatrix_x4(smem_u32(sQ + r * PITCH + c), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+    float s[LKT * 2][4];
+#pragma unroll
+    for (int nt = 0; nt < LKT * 2; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+      const int r = nt * 8 + (lane & 7);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c = half * 32 + (lane >> 3) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(smem_u32(sK + r * PITCH + c), b0, b1, b2, b3);
+        mma_bf16_16816(s[nt], qa[half * 2][0], qa[half * 2][1], qa[half * 2][2], qa[half * 2][3], b0, b1);
+        mma_bf16_16816(s[nt], qa[half * 2 + 1][0], qa[half * 2 + 1][1], qa[half * 2 + 1][2], qa[half * 2 + 1][3], b2, b3);
+      }
+    }
+    // softmax over keys (rows g = lane/4 and g+8), scale 1/sqrt(64)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < LKT * 2; ++nt) {
+      const int key = nt * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = (key + (j & 1)) < L;
+        s[nt][j] = ok ? s[nt][j] * 0.125f : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < LKT * 2; ++nt) {
+      s[nt][0] = __expf(s[nt][0] - mx0);
+      s[nt][1] = __expf(s[nt][1] - mx0);
+      s[nt][2] = __expf(s[nt][2] - mx1);
+      s[nt][3] = __expf(s[nt][3] - mx1);
+      sum0 += s[nt][0] + s[nt][1];
+      sum1 += s[nt][2] + s[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+    // O = P V
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.0f;
+#pragma unroll
+    for (int kt = 0; kt < LKT; ++kt) {
+      const uint32_t a0 = pack_bf16x2(s[2 * kt][0], s[2 * kt][1]);
+      const uint32_t a1 = pack_bf16x2(s[2 * kt][2], s[2 * kt][3]);
+      const uint32_t a2 = pack_bf16x2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+      const uint32_t a3 = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-dim tiles
+        const int r = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = (dp * 2 + (lane >> 4)) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(smem_u32(sV + r * PITCH + c), b0, b1, b2, b3);
+        mma_bf16_16816(o[dp * 2], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    const int q0 = qt * 16 + (lane >> 2), q1 = q0 + 8;
+    bf16* out = ctx + static_cast<long long>(row) * L * heads * HD + head * HD + (lane & 3) * 2;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      if (q0 < L)
+        *reinterpret_cast<uint32_t*>(out + static_cast<long long>(q0) * heads * HD + dt * 8) =
+            pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+      if (q1 < L)
+        *reinterpret_cast<uint32_t*>(out + static_cast<long long>(q1) * heads * HD + dt * 8) =
+            pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+    }
+  }
+}
+
+template <int LKT>
+void launch_bert_attn(const bf16* qkv, bf16* ctx, int R, int L, int heads, cudaStream_t s) {
+  constexpr int LP = LKT * 16;
+  const size_t smem = static_cast<size_t>(3) * LP * PITCH * sizeof(bf16);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    RVB_CUDA(cudaFuncSetAttribute(bert_attn_kernel<LKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = true;
+  }
+  const int qtiles = (L + 15) / 16;
+  const int nwarps = qtiles < 8 ? qtiles : 8;
+  dim3 grid(heads, R);
+  bert_attn_kernel<LKT><<<grid, nwarps * 32, smem, s>>>(qkv, ctx, L, heads);
+  RVB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+// Visual_Ling_Attn cross attention: q [B*L,256] (shared by both modalities),
+// kv [n_mod*B*16, 512] (k | v), ctx [n_mod*B*L, 256].  4 heads x 64, 16 keys.
+// ---------------------------------------------------------------------------------------
+constexpr int VH = 4, VK = 16, VP = HD + 1;
+__global__ void __launch_bounds__(256) vla_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
+                                                       bf16* __restrict__ ctx, int B, int L, int q_shared) {
+  __shared__ float sK[VH * VK * VP];
+  __shared__ float sV[VH * VK * VP];
+  const int b = blockIdx.x, mod = blockIdx.y;
+  const bf16* kvb = kv + (static_cast<long long>(mod) * B + b) * VK * 512;
+  for (int i = threadIdx.x; i < VK * 512; i += blockDim.x) {
+    const int j = i / 512, c = i % 512;
+    const float v = __bfloat162float(kvb[i]);
+    const int cc = c & 255, h = cc >> 6, d = cc & 63;
+    (c < 256 ? sK : sV)[(h * VK + j) * VP + d] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int h = lane >> 3, sub = lane & 7;
+  for (int l = warp; l < L; l += nwarps) {
+    const bf16* qp = q + (static_cast<long long>(q_shared ? 0 : b) * L + l) * 256 + h * HD;
+    float s0 = 0.0f, s1 = 0.0f;
+    const float* k0 = sK + (h * VK + 2 * sub) * VP;
+    const float* k1 = k0 + VP;
+#pragma unroll 8
+    for (int d = 0; d < HD; d += 2) {
+      const float2 qq = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + d));
+      s0 = fmaf(qq.x, k0[d], s0); s0 = fmaf(qq.y, k0[d + 1], s0);
+      s1 = fmaf(qq.x, k1[d], s1); s1 = fmaf(qq.y, k1[d + 1], s1);
+    }
+    s0 *= 0.125f; s1 *= 0.125f;
+    float mx = fmaxf(s0, s1);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    float p0 = __expf(s0 - mx), p1 = __expf(s1 - mx);
+    float sum = p0 + p1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float inv = 1.0f / sum;
+    p0 *= inv; p1 *= inv;
+    float o[8];
+#pragma unroll
+    for (int dd = 0; dd < 8; ++dd) o[dd] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < VK; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, (j & 1) ? p1 : p0, (h << 3) + (j >> 1));
+      const float* vr = sV + (h * VK + j) * VP + sub * 8;
+#pragma unroll
+      for (int dd = 0; dd < 8; ++dd) o[dd] = fmaf(pj, vr[dd], o[dd]);
+    }
+    uint4 u;
+    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(ctx + ((static_cast<long long>(mod) * B + b) * L + l) * 256 + h * HD + sub * 8) = u;
+  }
+}
+
+}  // namespace
+
+void bert_self_attention(const bf16* qkv, bf16* ctx, int R, int L, int heads, cudaStream_t s) {
+  RVB_CHECK(L >= 1 && L <= 256, "bert attention: 1 <= L <= 256 (INSTRUCTION_ENCODER.max_length is 200)");
+  const int lkt = (L + 15) / 16;
+  if (lkt <= 2) launch_bert_attn<2>(qkv, ctx, R, L, heads, s);
+  else if (lkt <= 5) launch_bert_attn<5>(qkv, ctx, R, L, heads, s);
+  else if (lkt <= 8) launch_bert_attn<8>(qkv, ctx, R, L, heads, s);
+  else if (lkt <= 13) launch_bert_attn<13>(qkv, ctx, R, L, heads, s);
+  else launch_bert_attn<16>(qkv, ctx, R, L, heads, s);
+}
+
+void vla_cross_attention(const bf16* q, const bf16* kv, bf16* ctx, int B, int L, int n_mod, int q_shared,
+                         cudaStream_t s) {
+  dim3 grid(B, n_mod);
+  vla_attn_kernel<<<grid, 256, 0, s>>>(q, kv, ctx, B, L, q_shared);
+  RVB_CUDA(cudaGetLastError());
+}
+
+}  // namespace rvb

@@ -1,0 +1,273 @@
+// extern "C" boundary (include/robovln_b200.h): exception -> error code translation only.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.h"
+
+using namespace rvb;
+
+struct hcm_engine {
+  Engine eng;
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code != 0 ? e.code : -1;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return -1;
+  }
+}
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline const bf16* B16(const void* p) { return reinterpret_cast<const bf16*>(p); }
+inline bf16* B16(void* p) { return reinterpret_cast<bf16*>(p); }
+}  // namespace
+
+extern "C" {
+
+const char* hcm_last_error(void) { return g_last_error.c_str(); }
+const char* hcm_version(void) { return "robovln_b200 0.1 (sm_100a: tcgen05/TMEM/TMA)"; }
+
+int hcm_create(hcm_engine** out) {
+  return guarded([&] {
+    RVB_CHECK(out != nullptr, "hcm_create: null out");
+    int dev = 0;
+    RVB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    RVB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    RVB_CHECK(prop.major == 10, std::string("robovln_b200 needs an sm_100 GPU (B200); found sm_") +
+                                    std::to_string(prop.major) + std::to_string(prop.minor));
+    hcm_engine* e = new hcm_engine();
+    const char* ms = std::getenv("ROBOVLN_MULTISTREAM");
+    e->eng.multi_stream_ = (ms == nullptr) ? true : (std::strcmp(ms, "0") != 0);
+    *out = e;
+  });
+}
+
+void hcm_destroy(hcm_engine* e) { delete e; }
+
+int hcm_set_tensor(hcm_engine* e, const char* name, const void* dev_ptr, int dtype, int ndim, const int64_t* shape) {
+  return guarded([&] { e->eng.set_tensor(name, dev_ptr, dtype, ndim, shape); });
+}
+
+int hcm_finalize_weights(hcm_engine* e, int have_hi, int have_lo, int lo_shares_trunks) {
+  return guarded([&] { e->eng.finalize(have_hi, have_lo, lo_shares_trunks); });
+}
+
+size_t hcm_workspace_bytes(hcm_engine* e, const hcm_shape* shape) {
+  size_t n = 0;
+  int rc = guarded([&] { n = e->eng.plan(*shape, nullptr, 0); });
+  return rc == 0 ? n : 0;
+}
+
+int hcm_plan(hcm_engine* e, const hcm_shape* shape, void* workspace, size_t workspace_bytes) {
+  return guarded([&] {
+    RVB_CHECK(workspace != nullptr, "hcm_plan: null workspace");
+    // deterministic contents for padding columns that no kernel writes
+    RVB_CUDA(cudaMemset(workspace, 0, workspace_bytes));
+    e->eng.plan(*shape, workspace, workspace_bytes);
+  });
+}
+
+int hcm_forward_hi(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                   const int64_t* instr_i64, const float* masks, int mask_stride, const float* hc_in, float* logits,
+                   float* hc_out, void* stream) {
+  return guarded([&] {
+    RunArgs a;
+    a.rgb = rgb; a.depth = depth; a.instr_f32 = instr_f32; a.instr_i64 = instr_i64;
+    a.masks = masks; a.mask_stride = mask_stride; a.hc_hi_in = hc_in; a.hc_hi_out = hc_out; a.logits = logits;
+    e->eng.args_ = a;
+    e->eng.forward_hi(S(stream));
+  });
+}
+
+int hcm_forward_lo(hcm_engine* e, const float* rgb, const float* depth, const float* masks, int mask_stride,
+                   const int64_t* sub_goal, const float* hc_in, float* actions, float* stop_logit, float* hc_out,
+                   int reuse_trunks, void* stream) {
+  return guarded([&] {
+    RunArgs a;
+    a.rgb = rgb; a.depth = depth; a.masks = masks; a.mask_stride = mask_stride; a.sub_goal = sub_goal;
+    a.hc_lo_in = hc_in; a.hc_lo_out = hc_out; a.actions = actions; a.stop = stop_logit;
+    e->eng.args_ = a;
+    e->eng.forward_lo(reuse_trunks != 0, S(stream));
+  });
+}
+
+int hcm_forward_policy(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                       const int64_t* instr_i64, const float* masks, int mask_stride, const float* hc_hi_in,
+                       const float* hc_lo_in, float* logits, float* actions, float* stop_logit, float* hc_hi_out,
+                       float* hc_lo_out, int64_t* sub_goal_out, void* stream) {
+  return guarded([&] {
+    RunArgs a;
+    a.rgb = rgb; a.depth = depth; a.instr_f32 = instr_f32; a.instr_i64 = instr_i64;
+    a.masks = masks; a.mask_stride = mask_stride;
+    a.hc_hi_in = hc_hi_in; a.hc_lo_in = hc_lo_in; a.hc_hi_out = hc_hi_out; a.hc_lo_out = hc_lo_out;
+    a.logits = logits; a.actions = actions; a.stop = stop_logit; a.sub_goal_out = sub_goal_out;
+    e->eng.args_ = a;
+    e->eng.forward_policy(S(stream));
+  });
+}
+
+int hcm_forward_policy_host(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                            const float* masks, const float* hc_hi_in, const float* hc_lo_in, float* logits,
+                            float* actions, float* stop_logit, float* hc_hi_out, float* hc_lo_out, void* stream) {
+  return guarded([&] {
+    e->eng.forward_policy_host(rgb, depth, instr_f32, masks, hc_hi_in, hc_lo_in, logits, actions, stop_logit, hc_hi_out,
+                               hc_lo_out, S(stream));
+  });
+}
+
+int64_t hcm_last_launch_count(hcm_engine* e) { return e->eng.launches_; }
+
+int hcm_profile_policy(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                       const int64_t* instr_i64, const float* masks, int mask_stride, const float* hc_hi_in,
+                       const float* hc_lo_in, float* logits, float* actions, float* stop_logit, float* hc_hi_out,
+                       float* hc_lo_out, char* json_out, size_t json_cap, void* stream) {
+  return guarded([&] {
+    RunArgs a;
+    a.rgb = rgb; a.depth = depth; a.instr_f32 = instr_f32; a.instr_i64 = instr_i64;
+    a.masks = masks; a.mask_stride = mask_stride;
+    a.hc_hi_in = hc_hi_in; a.hc_lo_in = hc_lo_in; a.hc_hi_out = hc_hi_out; a.hc_lo_out = hc_lo_out;
+    a.logits = logits; a.actions = actions; a.stop = stop_logit;
+    e->eng.args_ = a;
+    std::vector<OpTiming> t = e->eng.profile_policy(S(stream));
+    std::string js = "[";
+    for (size_t i = 0; i < t.size(); ++i) {
+      char buf[512];
+      snprintf(buf, sizeof(buf), "%s{\"name\":\"%s\",\"ms\":%.6f,\"flops\":%.1f}", i ? "," : "", t[i].name.c_str(),
+               t[i].ms, t[i].flops);
+      js += buf;
+    }
+    js += "]";
+    RVB_CHECK(js.size() + 1 <= json_cap, "hcm_profile_policy: output buffer too small");
+    std::memcpy(json_out, js.c_str(), js.size() + 1);
+  });
+}
+
+int hcm_run_rgb_trunk(hcm_engine* e, const float* rgb, int use_lo_weights, void* stream) {
+  return guarded([&] {
+    RVB_CHECK(e->eng.planned_, "engine not planned");
+    e->eng.args_.rgb = rgb;
+    Stage& st = (use_lo_weights && !e->eng.st_rgb_lo_.empty()) ? e->eng.st_rgb_lo_ : e->eng.st_rgb_;
+    e->eng.launches_ = e->eng.run(e->eng.st_pre_, S(stream));
+    e->eng.launches_ += e->eng.run(st, S(stream));
+  });
+}
+
+int hcm_run_depth_trunk(hcm_engine* e, const float* depth, int use_lo_weights, void* stream) {
+  return guarded([&] {
+    RVB_CHECK(e->eng.planned_, "engine not planned");
+    e->eng.args_.depth = depth;
+    Stage& st = (use_lo_weights && !e->eng.st_depth_lo_.empty()) ? e->eng.st_depth_lo_ : e->eng.st_depth_;
+    e->eng.launches_ = e->eng.run(e->eng.st_pre_, S(stream));
+    e->eng.launches_ += e->eng.run(st, S(stream));
+  });
+}
+
+int hcm_run_bert(hcm_engine* e, const float* instr_f32, const int64_t* instr_i64, void* stream) {
+  return guarded([&] {
+    RVB_CHECK(e->eng.planned_ && e->eng.have_hi_, "engine not planned");
+    e->eng.args_.instr_f32 = instr_f32;
+    e->eng.args_.instr_i64 = instr_i64;
+    e->eng.launches_ = e->eng.run(e->eng.st_bert_, S(stream));
+  });
+}
+
+int hcm_run_cross_modal(hcm_engine* e, const void* bert_bf16, const void* rgb_spatial_bf16,
+                        const void* depth_spatial_bf16, void* pooled_bf16, void* stream) {
+  return guarded([&] { e->eng.run_cross_modal(bert_bf16, rgb_spatial_bf16, depth_spatial_bf16, pooled_bf16, S(stream)); });
+}
+
+int hcm_get_buffer(hcm_engine* e, const char* name, void** dev_ptr, int* dtype, int* ndim, int64_t* shape) {
+  return guarded([&] {
+    std::vector<int64_t> shp;
+    RVB_CHECK(e->eng.get_buffer(name, dev_ptr, dtype, &shp), std::string("unknown buffer '") + name + "'");
+    *ndim = static_cast<int>(shp.size());
+    for (size_t i = 0; i < shp.size(); ++i) shape[i] = shp[i];
+  });
+}
+
+int hcm_copy_buffer(hcm_engine* e, const char* name, void* dst_dev, size_t bytes, void* stream) {
+  return guarded([&] {
+    std::vector<int64_t> shp;
+    void* src = nullptr;
+    int dtype = 0;
+    RVB_CHECK(e->eng.get_buffer(name, &src, &dtype, &shp), std::string("unknown buffer '") + name + "'");
+    size_t n = dtype == 0 ? 4 : (dtype == 1 ? 2 : 8);
+    for (auto v : shp) n *= static_cast<size_t>(v);
+    RVB_CHECK(bytes == n, "hcm_copy_buffer: size mismatch");
+    RVB_CUDA(cudaMemcpyAsync(dst_dev, src, n, cudaMemcpyDeviceToDevice, S(stream)));
+  });
+}
+
+// ---- kernel-level entry points -------------------------------------------------------------
+int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in_pitch, const void* w_bf16, int Cout,
+                  int KH, int KW, int stride, int pad, const float* bias, const void* res_bf16, int64_t ldr,
+                  int res_rows, int act, void* out, int64_t ldc, int out_f32, int force_bn, int impl, void* stream) {
+  return guarded([&] {
+    ConvGemm g;
+    g.in = B16(in_bf16); g.NB = NB; g.H = H; g.W = W; g.Cin = Cin; g.in_pitch = in_pitch;
+    g.w = B16(w_bf16); g.Cout = Cout; g.KH = KH; g.KW = KW; g.stride = stride; g.pad = pad;
+    g.bias = bias; g.res = B16(res_bf16); g.ldr = ldr; g.res_rows = res_rows; g.act = act;
+    g.out = out; g.ldc = ldc; g.out_f32 = out_f32;
+    if (impl == 1) {
+      gemm_simt_launch(g, S(stream));
+    } else {
+      GemmTcPlan plan;
+      gemm_tc_make_plan(g, &plan, force_bn);
+      gemm_tc_launch(plan, S(stream));
+    }
+  });
+}
+
+int rvb_groupnorm(const void* x_bf16, float* stats, const float* gamma, const float* beta, int NB, int HW, int C, int G,
+                  int relu, const void* res_bf16, void* out_bf16, int64_t out_pitch, void* stream) {
+  return guarded([&] {
+    RVB_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(NB) * G * 2 * sizeof(float), S(stream)));
+    gn_stats(B16(x_bf16), stats, NB, HW, C, G, S(stream));
+    GnApply a{B16(x_bf16), stats, gamma, beta, NB, HW, C, G, relu, res_bf16 != nullptr ? 1 : 0, B16(res_bf16),
+              nullptr, nullptr, nullptr, B16(out_bf16), out_pitch};
+    gn_apply(a, S(stream));
+  });
+}
+
+int rvb_layernorm(const float* x, int M, int D, const float* gamma, const float* beta, float eps, const float* pe,
+                  int pe_rows, void* out_bf16, void* stream) {
+  return guarded([&] { layernorm_rows(x, M, D, gamma, beta, eps, pe, pe_rows > 0 ? pe_rows : 1, B16(out_bf16), S(stream)); });
+}
+
+int rvb_bert_attention(const void* qkv_bf16, void* ctx_bf16, int R, int L, int heads, void* stream) {
+  return guarded([&] { bert_self_attention(B16(qkv_bf16), B16(ctx_bf16), R, L, heads, S(stream)); });
+}
+
+int rvb_vla_attention(const void* q_bf16, const void* kv_bf16, void* ctx_bf16, int B, int L, int q_rows, void* stream) {
+  return guarded([&] { vla_cross_attention(B16(q_bf16), B16(kv_bf16), B16(ctx_bf16), B, L, 1, q_rows == L ? 1 : 0, S(stream)); });
+}
+
+int rvb_lstm(const float* gx, const void* whh_bf16, const float* masks, int mask_stride, const float* hc_in,
+             float* hc_out, float* h_scratch, float* y, int T, int N, void* stream) {
+  return guarded([&] { lstm_forward(gx, B16(whh_bf16), masks, mask_stride, hc_in, hc_out, h_scratch, y, T, N, S(stream)); });
+}
+
+int rvb_maxpool3x3s2(const void* in_bf16, void* out_bf16, int NB, int H, int W, int C, void* stream) {
+  return guarded([&] { maxpool3x3s2(B16(in_bf16), B16(out_bf16), NB, H, W, C, S(stream)); });
+}
+
+int rvb_rgb_stem_im2col(const float* rgb, void* out_bf16, int NB, int H, int W, int Kpitch, void* stream) {
+  return guarded([&] { rgb_stem_im2col(rgb, B16(out_bf16), NB, H, W, Kpitch, S(stream)); });
+}
+
+int rvb_depth_stem(const float* depth, const float* w, void* out_bf16, int NB, int H, int W, void* stream) {
+  return guarded([&] { depth_stem_conv(depth, w, B16(out_bf16), NB, H, W, S(stream)); });
+}
+
+}  // extern "C"

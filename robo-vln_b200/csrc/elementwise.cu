@@ -1,0 +1,611 @@
+// Bandwidth-bound kernels around the tensor-core contractions: stems, pooling, GroupNorm,
+// LayerNorm, embeddings, small heads.  All activations are NHWC / row-major bf16 with fp32
+// statistics; every kernel moves 16-byte vectors along the contiguous (channel) dimension.
+#include "common.cuh"
+#include "rvb.h"
+
+#include <algorithm>
+
+namespace rvb {
+
+namespace {
+
+RVB_DEVICE void load8(const bf16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+RVB_DEVICE void store8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ---------------------------------------------------------------------------------------
+// RGB stem: [NB,H,W,3] fp32 0..255 -> im2col rows [NB*Ho*Wo, Kpitch] bf16 for the 7x7 s2 p3
+// conv (k = r*21 + s*3 + c), with the reference's /255 (resnet_encoders.py:213) folded in.
+// ---------------------------------------------------------------------------------------
+constexpr int STEM_PIX = 32;
+__global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __restrict__ rgb, bf16* __restrict__ out,
+                                                              int NB, int H, int W, int Ho, int Wo, int Kpitch) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  bf16* tile = reinterpret_cast<bf16*>(sm_raw);  // [STEM_PIX][Kpitch]
+  const long long M = static_cast<long long>(NB) * Ho * Wo;
+  const long long m0 = static_cast<long long>(blockIdx.x) * STEM_PIX;
+  const int total = STEM_PIX * Kpitch;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int px = e / Kpitch;
+    const int k = e - px * Kpitch;
+    float v = 0.0f;
+    const long long m = m0 + px;
+    if (k < 147 && m < M) {
+      const int wo = static_cast<int>(m % Wo);
+      const int ho = static_cast<int>((m / Wo) % Ho);
+      const int img = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+      const int r = k / 21;
+      const int rem = k - r * 21;
+      const int s = rem / 3;
+      const int c = rem - s * 3;
+      const int h = 2 * ho + r - 3;
+      const int w = 2 * wo + s - 3;
+      if (h >= 0 && h < H && w >= 0 && w < W)
+        v = __ldg(rgb + ((static_cast<long long>(img) * H + h) * W + w) * 3 + c) / 255.0f;
+    }
+    tile[e] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const long long rows = std::min<long long>(STEM_PIX, M - m0);
+  const int nvec = static_cast<int>(rows * Kpitch / 8);
+  uint4* dst = reinterpret_cast<uint4*>(out + m0 * Kpitch);
+  const uint4* src = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// 3x3 stride-2 pad-1 max pooling, NHWC bf16
+// ---------------------------------------------------------------------------------------
+__global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int NB, int H, int W, int C,
+                                    int Ho, int Wo) {
+  const int cv = C / 8;
+  const long long total = static_cast<long long>(NB) * Ho * Wo * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    const long long pix = i / cv;
+    const int wo = static_cast<int>(pix % Wo);
+    const int ho = static_cast<int>((pix / Wo) % Ho);
+    const int img = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ho + r - 1;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * wo + s - 1;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        load8(in + ((static_cast<long long>(img) * H + h) * W + w) * C + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      }
+    }
+    store8(out + pix * C + v * 8, m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Depth stem: [NB,H,W,1] fp32 -> avg_pool2d(2) -> conv7x7 s2 p3 (1->32, no bias) -> raw bf16
+// [NB,Ho,Wo,32]  (resnet_policy.py:184-186, resnet.py:185-196).  fp32 math on CUDA cores:
+// 12.8 MFLOP per image.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) depth_stem_kernel(const float* __restrict__ depth, const float* __restrict__ w,
+                                                         bf16* __restrict__ out, int H, int W, int Hp, int Wp, int Ho,
+                                                         int Wo) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* ws = reinterpret_cast<float*>(sm_raw);  // [49][32]
+  float* rows = ws + 49 * 32;                    // [7][Wp + 6]
+  const int img = blockIdx.y;
+  const int ho = blockIdx.x;
+  const int RW = Wp + 6;
+  for (int i = threadIdx.x; i < 49 * 32; i += blockDim.x) {
+    const int k = i / 32, ch = i % 32;
+    ws[i] = w[ch * 49 + k];
+  }
+  const float* base = depth + static_cast<long long>(img) * H * W;
+  for (int i = threadIdx.x; i < 7 * RW; i += blockDim.x) {
+    const int r = i / RW;
+    const int x = i - r * RW - 3;
+    const int hp = 2 * ho + r - 3;
+    float v = 0.0f;
+    if (hp >= 0 && hp < Hp && x >= 0 && x < Wp) {
+      const float* q = base + static_cast<long long>(2 * hp) * W + 2 * x;
+      v = 0.25f * (q[0] + q[1] + q[W] + q[W + 1]);
+    }
+    rows[i] = v;
+  }
+  __syncthreads();
+  const int ch = threadIdx.x & 31;
+  for (int wo = threadIdx.x >> 5; wo < Wo; wo += blockDim.x >> 5) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+#pragma unroll
+      for (int s = 0; s < 7; ++s) acc = fmaf(rows[r * RW + 2 * wo + s], ws[(r * 7 + s) * 32 + ch], acc);
+    }
+    out[((static_cast<long long>(img) * Ho + ho) * Wo + wo) * 32 + ch] = __float2bfloat16_rn(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[img][g] = (sum, sumsq) over HW x (C/G) elements (fp32 atomics
+// on a pre-zeroed buffer).  Thread t owns the 8-channel slot t % (C/8).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int HW,
+                                                       int C, int G) {
+  __shared__ float sg[64], qg[64];
+  const int img = blockIdx.y;
+  const int cv = C / 8;
+  const int slot = threadIdx.x % cv;
+  const int prow = threadIdx.x / cv;
+  const int rows_per_iter = blockDim.x / cv;
+  const int cpg = C / G;
+  if (threadIdx.x < 64) {
+    sg[threadIdx.x] = 0.0f;
+    qg[threadIdx.x] = 0.0f;
+  }
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0f;
+  const bf16* base = x + static_cast<long long>(img) * HW * C + slot * 8;
+  for (int p = blockIdx.x * rows_per_iter + prow; p < HW; p += gridDim.x * rows_per_iter) {
+    float f[8];
+    load8(base + static_cast<long long>(p) * C, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      q[j] = fmaf(f[j], f[j], q[j]);
+    }
+  }
+  if (cpg >= 8) {
+    float ss = 0.0f, qq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ss += s[j];
+      qq += q[j];
+    }
+    const int g = (slot * 8) / cpg;
+    atomicAdd(&sg[g], ss);
+    atomicAdd(&qg[g], qq);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (slot * 8 + j) / cpg;
+      atomicAdd(&sg[g], s[j]);
+      atomicAdd(&qg[g], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(&stats[(static_cast<long long>(img) * G + threadIdx.x) * 2 + 0], sg[threadIdx.x]);
+    atomicAdd(&stats[(static_cast<long long>(img) * G + threadIdx.x) * 2 + 1], qg[threadIdx.x]);
+  }
+}
+
+struct GnApplyDev {
+  const bf16* x; const float* stats; const float* gamma; const float* beta;
+  int NB, HW, C, G, relu, res_mode;
+  const bf16* res; const float* res_stats; const float* res_gamma; const float* res_beta;
+  bf16* out; long long out_pitch;
+};
+
+RVB_DEVICE void gn_scale_shift(const float* stats, int img, int G, int g, float cnt, float gamma, float beta,
+                               float& sc, float& sh) {
+  const float sum = stats[(static_cast<long long>(img) * G + g) * 2 + 0];
+  const float sq = stats[(static_cast<long long>(img) * G + g) * 2 + 1];
+  const float mean = sum / cnt;
+  const float var = fmaxf(sq / cnt - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  sc = rstd * gamma;
+  sh = beta - mean * sc;
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
+  const int cv = a.C / 8;
+  const int cpg = a.C / a.G;
+  const float cnt = static_cast<float>(a.HW) * static_cast<float>(cpg);
+  const long long total = static_cast<long long>(a.NB) * a.HW * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    const long long pix = i / cv;
+    const int img = static_cast<int>(pix / a.HW);
+    const int c0 = v * 8;
+    float f[8];
+    load8(a.x + pix * a.C + c0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sc, sh;
+      gn_scale_shift(a.stats, img, a.G, (c0 + j) / cpg, cnt, __ldg(a.gamma + c0 + j), __ldg(a.beta + c0 + j), sc, sh);
+      f[j] = fmaf(f[j], sc, sh);
+    }
+    if (a.res_mode == 1) {
+      float r[8];
+      load8(a.res + pix * a.C + c0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    } else if (a.res_mode == 2) {
+      float r[8];
+      load8(a.res + pix * a.C + c0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float sc, sh;
+        gn_scale_shift(a.res_stats, img, a.G, (c0 + j) / cpg, cnt, __ldg(a.res_gamma + c0 + j),
+                       __ldg(a.res_beta + c0 + j), sc, sh);
+        f[j] += fmaf(r[j], sc, sh);
+      }
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+    store8(a.out + pix * a.out_pitch + c0, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// RGB head pooling: layer4 output [NB,H,W,C] ->
+//   tokens[img][cell][0..C)  = adaptive_avg_pool2d(4,4)   (resnet_encoders.py:162-166)
+//   cellmean[img][0..C)      = mean over the 16 cells     (rgb_linear's AdaptiveAvgPool1d(1))
+//   gmean[img][0..C)         = global mean                (torchvision avgpool, lo path)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rgb_pool_kernel(const bf16* __restrict__ feat, int H, int W, int C,
+                                                       bf16* __restrict__ tokens, long long tok_pitch,
+                                                       bf16* __restrict__ cellmean, long long cm_pitch,
+                                                       bf16* __restrict__ gmean) {
+  const int img = blockIdx.x;
+  const bf16* base = feat + static_cast<long long>(img) * H * W * C;
+  for (int v = threadIdx.x; v < C / 8; v += blockDim.x) {
+    float cm[8], gm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cm[j] = gm[j] = 0.0f;
+    for (int ch = 0; ch < 4; ++ch) {
+      const int h0 = (ch * H) / 4, h1 = ((ch + 1) * H + 3) / 4;
+      for (int cw = 0; cw < 4; ++cw) {
+        const int w0 = (cw * W) / 4, w1 = ((cw + 1) * W + 3) / 4;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+        for (int h = h0; h < h1; ++h)
+          for (int w = w0; w < w1; ++w) {
+            float f[8];
+            load8(base + (static_cast<long long>(h) * W + w) * C + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          }
+        const float inv = 1.0f / static_cast<float>((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] *= inv;
+          cm[j] += acc[j];
+        }
+        store8(tokens + (static_cast<long long>(img) * 16 + ch * 4 + cw) * tok_pitch + v * 8, acc);
+      }
+    }
+    for (int p = 0; p < H * W; ++p) {
+      float f[8];
+      load8(base + static_cast<long long>(p) * C + v * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gm[j] += f[j];
+    }
+    const float invp = 1.0f / static_cast<float>(H * W);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cm[j] *= (1.0f / 16.0f);
+      gm[j] *= invp;
+    }
+    store8(cellmean + static_cast<long long>(img) * cm_pitch + v * 8, cm);
+    store8(gmean + static_cast<long long>(img) * C + v * 8, gm);
+  }
+}
+
+// Spatial-embedding channels: the reference views the [16,64] table as [64,4,4]
+// (resnet_encoders.py:91-102): channel c of cell k reads flat[c*16 + k].
+__global__ void fill_spatial_embedding_kernel(const float* __restrict__ flat, bf16* __restrict__ tokens, int NB,
+                                              long long tok_pitch, int col0, bf16* __restrict__ cellmean,
+                                              long long cm_pitch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NB * 64) return;
+  const int img = i / 64, c = i % 64;
+  float m = 0.0f;
+  for (int k = 0; k < 16; ++k) {
+    const float v = flat[c * 16 + k];
+    m += v;
+    tokens[(static_cast<long long>(img) * 16 + k) * tok_pitch + col0 + c] = __float2bfloat16_rn(v);
+  }
+  if (cellmean != nullptr) cellmean[static_cast<long long>(img) * cm_pitch + col0 + c] = __float2bfloat16_rn(m / 16.0f);
+}
+
+// ---------------------------------------------------------------------------------------
+// BERT embeddings + LayerNorm(eps 1e-12): one warp per token, D = 768.
+// ---------------------------------------------------------------------------------------
+template <int NV>  // float4 per lane: D = NV * 128
+__global__ void __launch_bounds__(256) bert_embed_ln_kernel(const long long* __restrict__ ids_i64,
+                                                            const float* __restrict__ ids_f32, int id_rows, int R,
+                                                            int L, const float* __restrict__ word,
+                                                            const float* __restrict__ pos,
+                                                            const float* __restrict__ type0,
+                                                            const float* __restrict__ g, const float* __restrict__ b,
+                                                            bf16* __restrict__ out) {
+  constexpr int D = NV * 128;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= R * L) return;
+  const int row = warp / L, l = warp - row * L;
+  const int src_row = (id_rows == 1) ? 0 : row;
+  long long id = ids_i64 != nullptr ? ids_i64[static_cast<long long>(src_row) * L + l]
+                                    : static_cast<long long>(ids_f32[static_cast<long long>(src_row) * L + l]);
+  float4 v[NV];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(word + id * D + c));
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(l) * D + c));
+    const float4 t = __ldg(reinterpret_cast<const float4*>(type0 + c));
+    v[i] = make_float4(a.x + t.x + p4.x, a.y + t.y + p4.y, a.z + t.z + p4.z, a.w + t.w + p4.w);
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(sum) / D;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    sq += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / D + 1e-12f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    uint2 o;
+    o.x = pack_bf16x2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+    o.y = pack_bf16x2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+    *reinterpret_cast<uint2*>(out + static_cast<long long>(warp) * D + c) = o;
+  }
+}
+
+// LayerNorm over fp32 rows (the producing GEMM already added bias and residual), optional
+// additive table (sinusoid PE, transformer.py:271-274) AFTER the norm; bf16 out.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int M,
+                                                             const float* __restrict__ g,
+                                                             const float* __restrict__ b, float eps,
+                                                             const float* __restrict__ pe, int pe_rows,
+                                                             bf16* __restrict__ out) {
+  constexpr int D = NV * 128;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float4 v[NV];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D + (i * 32 + lane) * 4);
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(sum) / D;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    sq += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / D + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    float4 y = make_float4((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+                           (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+    if (pe != nullptr) {
+      const float4 pp = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(row % pe_rows) * D + c));
+      y.x += pp.x; y.y += pp.y; y.z += pp.z; y.w += pp.w;
+    }
+    uint2 o;
+    o.x = pack_bf16x2(y.x, y.y);
+    o.y = pack_bf16x2(y.z, y.w);
+    *reinterpret_cast<uint2*>(out + static_cast<long long>(row) * D + c) = o;
+  }
+}
+
+// mean over the L tokens of each (modality, batch row) group: x [n_mod*B*L, D] ->
+// out[b*out_pitch + mod*mod_stride + d]   (cross_pooler, seq2seq_highlevel_cma.py:114-115,209-210)
+__global__ void token_mean_kernel(const bf16* __restrict__ x, int B, int L, int D, bf16* __restrict__ out,
+                                  long long out_pitch, long long mod_stride) {
+  const int g = blockIdx.x;
+  const int mod = g / B, b = g % B;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.0f;
+    const bf16* p = x + static_cast<long long>(g) * L * D + d;
+    for (int l = 0; l < L; ++l) acc += __bfloat162float(p[static_cast<long long>(l) * D]);
+    out[b * out_pitch + mod * mod_stride + d] = __float2bfloat16_rn(acc / static_cast<float>(L));
+  }
+}
+
+__global__ void sub_task_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ table, int B,
+                                      bf16* __restrict__ out, long long out_pitch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 32) return;
+  const int b = i / 32, c = i % 32;
+  long long id = ids[b];
+  id = id < 0 ? 0 : (id > 4 ? 4 : id);
+  out[b * out_pitch + c] = __float2bfloat16_rn(table[id * 32 + c]);
+}
+
+// out[m][o] = dot(y[m], w[o]) + b[o], one warp per output (tiny heads: 512 -> 4 / 2 / 1)
+__global__ void heads_linear_kernel(const float* __restrict__ y, int M, int K, const float* __restrict__ w,
+                                    const float* __restrict__ b, int n_out, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M * n_out) return;
+  const int m = warp / n_out, o = warp % n_out;
+  float acc = 0.0f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(y[static_cast<long long>(m) * K + k], w[static_cast<long long>(o) * K + k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[static_cast<long long>(m) * n_out + o] = acc + b[o];
+}
+
+__global__ void argmax_rows_kernel(const float* __restrict__ x, int M, int n, long long* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int best = 0;
+  float bv = x[static_cast<long long>(m) * n];
+  for (int j = 1; j < n; ++j) {
+    const float v = x[static_cast<long long>(m) * n + j];
+    if (v > bv) {
+      bv = v;
+      best = j;
+    }
+  }
+  out[m] = best;
+}
+
+// PE[p,2i] = sin(p / 10000^(2i/D)), PE[p,2i+1] = cos(same)   (common/utils.py:167-185)
+__global__ void sinusoid_table_kernel(float* __restrict__ pe, int L, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * (D / 2)) return;
+  const int p = i / (D / 2), k = i % (D / 2);
+  const float denom = powf(10000.0f, 2.0f * static_cast<float>(k) / static_cast<float>(D));
+  const float ang = static_cast<float>(p) / denom;
+  pe[static_cast<long long>(p) * D + 2 * k] = sinf(ang);
+  pe[static_cast<long long>(p) * D + 2 * k + 1] = cosf(ang);
+}
+
+int grid_for(long long total, int block, int max_blocks) {
+  const long long g = (total + block - 1) / block;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(g, max_blocks)));
+}
+
+}  // namespace
+
+void rgb_stem_im2col(const float* rgb, bf16* out, int NB, int H, int W, int Kpitch, cudaStream_t s) {
+  RVB_CHECK(Kpitch >= 147 && Kpitch % 8 == 0, "stem: bad K pitch");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long M = static_cast<long long>(NB) * Ho * Wo;
+  const int blocks = static_cast<int>((M + STEM_PIX - 1) / STEM_PIX);
+  rgb_stem_im2col_kernel<<<blocks, 256, STEM_PIX * Kpitch * 2, s>>>(rgb, out, NB, H, W, Ho, Wo, Kpitch);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void maxpool3x3s2(const bf16* in, bf16* out, int NB, int H, int W, int C, cudaStream_t s) {
+  RVB_CHECK(C % 8 == 0, "maxpool: C % 8");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(NB) * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(in, out, NB, H, W, C, Ho, Wo);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void depth_stem_conv(const float* depth, const float* w, bf16* out, int NB, int H, int W, cudaStream_t s) {
+  const int Hp = H / 2, Wp = W / 2;
+  const int Ho = (Hp + 6 - 7) / 2 + 1, Wo = (Wp + 6 - 7) / 2 + 1;
+  const size_t smem = (49 * 32 + 7 * (Wp + 6)) * sizeof(float);
+  dim3 grid(Ho, NB);
+  depth_stem_kernel<<<grid, 256, smem, s>>>(depth, w, out, H, W, Hp, Wp, Ho, Wo);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void gn_stats(const bf16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s) {
+  const int cv = C / 8;
+  RVB_CHECK(C % 8 == 0 && cv <= 256 && 256 % cv == 0 && G <= 64 && C % G == 0, "gn_stats: unsupported C/G");
+  const int rows_per_iter = 256 / cv;
+  int gx = (HW + rows_per_iter * 4 - 1) / (rows_per_iter * 4);
+  gx = std::max(1, std::min(gx, 64));
+  dim3 grid(gx, NB);
+  gn_stats_kernel<<<grid, 256, 0, s>>>(x, stats, HW, C, G);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void gn_apply(const GnApply& a, cudaStream_t s) {
+  RVB_CHECK(a.C % 8 == 0 && a.C % a.G == 0 && a.out_pitch % 8 == 0, "gn_apply: bad shape");
+  GnApplyDev d;
+  d.x = a.x; d.stats = a.stats; d.gamma = a.gamma; d.beta = a.beta;
+  d.NB = a.NB; d.HW = a.HW; d.C = a.C; d.G = a.G; d.relu = a.relu; d.res_mode = a.res_mode;
+  d.res = a.res; d.res_stats = a.res_stats; d.res_gamma = a.res_gamma; d.res_beta = a.res_beta;
+  d.out = a.out; d.out_pitch = a.out_pitch;
+  const long long total = static_cast<long long>(a.NB) * a.HW * (a.C / 8);
+  gn_apply_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(d);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void rgb_pool(const bf16* feat, int NB, int H, int W, int C, bf16* tokens, int64_t tok_pitch, bf16* cellmean,
+              int64_t cm_pitch, bf16* gmean, cudaStream_t s) {
+  RVB_CHECK(C % 8 == 0 && H >= 4 && W >= 4, "rgb_pool: bad shape");
+  rgb_pool_kernel<<<NB, 256, 0, s>>>(feat, H, W, C, tokens, tok_pitch, cellmean, cm_pitch, gmean);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void fill_spatial_embedding(const float* emb_flat, bf16* tokens, int NB, int64_t tok_pitch, int col0, bf16* cellmean,
+                            int64_t cm_pitch, cudaStream_t s) {
+  fill_spatial_embedding_kernel<<<(NB * 64 + 127) / 128, 128, 0, s>>>(emb_flat, tokens, NB, tok_pitch, col0, cellmean,
+                                                                      cm_pitch);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, int R, int L, const float* word,
+                   const float* pos, const float* type0, const float* g, const float* b, bf16* out, cudaStream_t s) {
+  const long long warps = static_cast<long long>(R) * L;
+  bert_embed_ln_kernel<6><<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(
+      reinterpret_cast<const long long*>(ids_i64), ids_f32, id_rows, R, L, word, pos, type0, g, b, out);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void layernorm_rows(const float* x, int M, int D, const float* g, const float* b, float eps, const float* pe,
+                    int pe_rows, bf16* out, cudaStream_t s) {
+  const int blocks = static_cast<int>((static_cast<long long>(M) * 32 + 255) / 256);
+  if (D == 768) layernorm_rows_kernel<6><<<blocks, 256, 0, s>>>(x, M, g, b, eps, pe, pe_rows, out);
+  else if (D == 256) layernorm_rows_kernel<2><<<blocks, 256, 0, s>>>(x, M, g, b, eps, pe, pe_rows, out);
+  else RVB_CHECK(false, "layernorm: D must be 256 or 768");
+  RVB_CUDA(cudaGetLastError());
+}
+
+void token_mean(const bf16* x, int n_mod, int B, int L, int D, bf16* out, int64_t out_pitch, int64_t mod_stride,
+                cudaStream_t s) {
+  token_mean_kernel<<<n_mod * B, 256, 0, s>>>(x, B, L, D, out, out_pitch, mod_stride);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void sub_task_embed(const int64_t* ids, const float* table, int B, bf16* out, int64_t out_pitch, cudaStream_t s) {
+  sub_task_embed_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(reinterpret_cast<const long long*>(ids), table, B, out,
+                                                             out_pitch);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void heads_linear(const float* y, int M, int K, const float* w, const float* b, int n_out, float* out,
+                  cudaStream_t s) {
+  const long long warps = static_cast<long long>(M) * n_out;
+  heads_linear_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(y, M, K, w, b, n_out, out);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void argmax_rows(const float* x, int M, int n, int64_t* out, cudaStream_t s) {
+  argmax_rows_kernel<<<(M + 127) / 128, 128, 0, s>>>(x, M, n, reinterpret_cast<long long*>(out));
+  RVB_CUDA(cudaGetLastError());
+}
+
+void sinusoid_table(float* pe, int L, int D, cudaStream_t s) {
+  const int total = L * (D / 2);
+  sinusoid_table_kernel<<<(total + 255) / 256, 256, 0, s>>>(pe, L, D);
+  RVB_CUDA(cudaGetLastError());
+}
+
+}  // namespace rvb

@@ -1,0 +1,752 @@
+// HcmEngine: the planned, launch-only forward pass of robo-vln's hierarchical policy
+// (Seq2Seq_HighLevel_CMA + Seq2Seq_LowLevel) on one B200.
+//
+// hcm_plan() carves every intermediate out of one caller-provided workspace, encodes all TMA
+// tensor maps once, and records each stage as a list of launch closures; the forward calls
+// only replay those lists on the caller's stream (no allocation, no synchronisation), which
+// also makes them CUDA-graph capturable.  The RGB trunk, the depth trunk and BERT are
+// independent until the cross-modal block, so the engine forks them onto three streams and
+// joins with events.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace rvb {
+
+// ---------------------------------------------------------------------------------------
+// weights registry
+// ---------------------------------------------------------------------------------------
+void Engine::set_tensor(const std::string& name, const void* ptr, int dtype, int ndim, const int64_t* shape) {
+  RVB_CHECK(ptr != nullptr, "set_tensor(" + name + "): null pointer");
+  RVB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "set_tensor(" + name + "): pointer must be 16-byte aligned");
+  WTensor t;
+  t.ptr = ptr;
+  t.dtype = dtype;
+  t.shape.assign(shape, shape + ndim);
+  weights_[name] = t;
+  planned_ = false;  // plans capture weight pointers
+}
+
+const WTensor& Engine::W(const std::string& name, int dtype, std::initializer_list<int64_t> shape) const {
+  auto it = weights_.find(name);
+  RVB_CHECK(it != weights_.end(), "missing weight tensor '" + name + "'");
+  const WTensor& t = it->second;
+  RVB_CHECK(t.dtype == dtype, "weight '" + name + "' has the wrong dtype");
+  if (shape.size() > 0) {
+    std::vector<int64_t> want(shape);
+    if (t.shape != want) {
+      std::string got, exp;
+      for (auto v : t.shape) got += std::to_string(v) + ",";
+      for (auto v : want) exp += std::to_string(v) + ",";
+      RVB_CHECK(false, "weight '" + name + "' has shape [" + got + "] expected [" + exp + "]");
+    }
+  }
+  return t;
+}
+const bf16* Engine::Wb(const std::string& n, std::initializer_list<int64_t> s) const {
+  return reinterpret_cast<const bf16*>(W(n, 1, s).ptr);
+}
+const float* Engine::Wf(const std::string& n, std::initializer_list<int64_t> s) const {
+  return reinterpret_cast<const float*>(W(n, 0, s).ptr);
+}
+
+void Engine::finalize(int have_hi, int have_lo, int lo_shares) {
+  have_hi_ = have_hi != 0;
+  have_lo_ = have_lo != 0;
+  lo_shares_trunks_ = lo_shares != 0;
+  RVB_CHECK(have_hi_ || have_lo_, "finalize: neither hi nor lo weights present");
+  RVB_CHECK(!lo_shares_trunks_ || (have_hi_ && have_lo_), "lo_shares_trunks needs both models");
+  finalized_ = true;
+  planned_ = false;
+}
+
+// ---------------------------------------------------------------------------------------
+// planning helpers
+// ---------------------------------------------------------------------------------------
+void* Engine::alloc(size_t bytes) {
+  const size_t off = (arena_off_ + 1023) & ~size_t(1023);
+  arena_off_ = off + bytes;
+  if (!dry_) RVB_CHECK(arena_off_ <= arena_cap_, "workspace too small");
+  return arena_base_ + off;
+}
+
+void Engine::add_gemm(Stage& st, const ConvGemm& g, int force_bn) {
+  if (dry_) return;
+  gemms_.emplace_back(new GemmTcPlan());
+  GemmTcPlan* plan = gemms_.back().get();
+  gemm_tc_make_plan(g, plan, force_bn);
+  Op op([plan](cudaStream_t s) { gemm_tc_launch(*plan, s); return 1; });
+  const double K = static_cast<double>(g.KH) * g.KW * g.Cin;
+  op.flops = 2.0 * static_cast<double>(g.M()) * g.Cout * K;
+  op.name = "gemm_tc<" + std::to_string(plan->BN) + "> M=" + std::to_string(g.M()) + " N=" + std::to_string(g.Cout) +
+            " K=" + std::to_string(static_cast<long long>(K)) + (g.plain() ? " plain" : (" conv" + std::to_string(g.KH) +
+            "x" + std::to_string(g.KW) + "s" + std::to_string(g.stride))) + " tiles=" +
+            std::to_string(plan->p.m_tiles * plan->p.n_tiles);
+  st.push_back(std::move(op));
+}
+
+void Engine::label(Stage& st, const std::string& prefix) {
+  int i = 0;
+  for (auto& op : st) {
+    if (op.name.empty()) op.name = prefix + ".aux" + std::to_string(i);
+    else if (op.name.rfind("gemm_tc", 0) == 0) op.name = prefix + ":" + op.name;
+    ++i;
+  }
+}
+
+ConvGemm Engine::linear(const bf16* in, int64_t M, int K, int64_t lda, const bf16* w, int N, const float* bias,
+                        int act, void* out, int64_t ldc, int out_f32, const bf16* res, int64_t ldr, int res_rows) {
+  ConvGemm g;
+  g.in = in; g.NB = 1; g.H = 1; g.W = static_cast<int>(M); g.Cin = K; g.in_pitch = lda;
+  g.w = w; g.Cout = N; g.KH = g.KW = 1; g.stride = 1; g.pad = 0;
+  g.bias = bias; g.res = res; g.ldr = ldr; g.res_rows = res_rows; g.act = act;
+  g.out = out; g.ldc = ldc; g.out_f32 = out_f32;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------
+// RGB trunk: torchvision ResNet-50 v1.5, eval-mode BN folded into the conv weights + bias
+// ---------------------------------------------------------------------------------------
+void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
+  const int B = shp_.B, H = shp_.rgb_h, W = shp_.rgb_w;
+  const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;   // conv1 7x7 s2 p3
+  const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1; // maxpool 3x3 s2 p1
+  constexpr int KP = 160;
+  bf16* im2col = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * KP * 2));
+  bf16* stem = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 64 * 2));
+  bf16* x = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 64 * 2));
+  if (!dry_) {
+    st.push_back([this, im2col, B, H, W](cudaStream_t s) { rgb_stem_im2col(args_.rgb, im2col, B, H, W, KP, s); return 1; });
+    add_gemm(st, linear(im2col, static_cast<int64_t>(B) * H1 * W1, KP, KP, Wb(ns + ".rgb.stem.w", {64, KP}), 64,
+                        Wf(ns + ".rgb.stem.b", {64}), ACT_RELU, stem, 64, 0));
+    st.push_back([stem, x, B, H1, W1](cudaStream_t s) { maxpool3x3s2(stem, x, B, H1, W1, 64, s); return 1; });
+  }
+  int h = H2, w = W2, cin = 64;
+  const int nblocks[4] = {3, 4, 6, 3};
+  for (int li = 0; li < 4; ++li) {
+    const int mid = 64 << li, cout = mid * 4;
+    for (int b = 0; b < nblocks[li]; ++b) {
+      const int stride = (b == 0 && li > 0) ? 2 : 1;
+      const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+      const std::string p = ns + ".rgb.l" + std::to_string(li + 1) + "." + std::to_string(b);
+      bf16* t1 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
+      bf16* t2 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
+      bf16* out = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+      const bf16* idt = x;
+      if (b == 0) {
+        bf16* ds = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+        if (!dry_) {
+          ConvGemm g;
+          g.in = x; g.NB = B; g.H = h; g.W = w; g.Cin = cin; g.in_pitch = cin;
+          g.w = Wb(p + ".ds.w", {cout, cin}); g.Cout = cout; g.KH = g.KW = 1; g.stride = stride; g.pad = 0;
+          g.bias = Wf(p + ".ds.b", {cout}); g.act = ACT_NONE; g.out = ds; g.ldc = cout;
+          add_gemm(st, g);
+        }
+        idt = ds;
+      }
+      if (!dry_) {
+        add_gemm(st, linear(x, static_cast<int64_t>(B) * h * w, cin, cin, Wb(p + ".c1.w", {mid, cin}), mid,
+                            Wf(p + ".c1.b", {mid}), ACT_RELU, t1, mid, 0));
+        ConvGemm g;
+        g.in = t1; g.NB = B; g.H = h; g.W = w; g.Cin = mid; g.in_pitch = mid;
+        g.w = Wb(p + ".c2.w", {mid, 9 * mid}); g.Cout = mid; g.KH = g.KW = 3; g.stride = stride; g.pad = 1;
+        g.bias = Wf(p + ".c2.b", {mid}); g.act = ACT_RELU; g.out = t2; g.ldc = mid;
+        add_gemm(st, g);
+        add_gemm(st, linear(t2, static_cast<int64_t>(B) * ho * wo, mid, mid, Wb(p + ".c3.w", {cout, mid}), cout,
+                            Wf(p + ".c3.b", {cout}), ACT_RELU, out, cout, 0, idt, cout, 0));
+      }
+      x = out; h = ho; w = wo; cin = cout;
+    }
+  }
+  rgb_feat_ = x; rgb_fh_ = h; rgb_fw_ = w;
+  if (!dry_) {
+    bf16* feat = x;
+    const int fh = h, fw = w;
+    st.push_back([this, feat, B, fh, fw](cudaStream_t s) {
+      rgb_pool(feat, B, fh, fw, 2048, tokens_r_, 2112, cellmean_r_, 2112, gmean_r_, s);
+      return 1;
+    });
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Depth trunk: DDPPO ResNet-50 (base 32, GroupNorm 16) + compression conv + GroupNorm(1)
+// ---------------------------------------------------------------------------------------
+float* Engine::new_stats(int G) {
+  float* p = gn_stats_arena_ + gn_stats_used_;
+  gn_stats_used_ += static_cast<size_t>(shp_.B) * G * 2;
+  if (!dry_) RVB_CHECK(gn_stats_used_ <= gn_stats_cap_, "GroupNorm stats arena overflow");
+  return p;
+}
+
+void Engine::plan_depth_trunk(const std::string& ns, Stage& st) {
+  const int B = shp_.B, H = shp_.depth_h, W = shp_.depth_w;
+  const int Hp = H / 2, Wp = W / 2;
+  const int H1 = (Hp + 6 - 7) / 2 + 1, W1 = (Wp + 6 - 7) / 2 + 1;
+  const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1;
+  constexpr int G = 16;
+  gn_stats_used_ = 0;
+  if (!dry_) {
+    float* arena = gn_stats_arena_;
+    const size_t bytes = gn_stats_cap_ * sizeof(float);
+    st.push_back([arena, bytes](cudaStream_t s) { RVB_CUDA(cudaMemsetAsync(arena, 0, bytes, s)); return 1; });
+  }
+  bf16* raw0 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
+  bf16* a0 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
+  bf16* x = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 32 * 2));
+  {
+    float* st0 = new_stats(G);
+    if (!dry_) {
+      const float* w = Wf(ns + ".depth.stem.w", {32, 49});
+      const float* gw = Wf(ns + ".depth.stem.gn.w", {32});
+      const float* gb = Wf(ns + ".depth.stem.gn.b", {32});
+      st.push_back([this, w, raw0, B, H, W](cudaStream_t s) { depth_stem_conv(args_.depth, w, raw0, B, H, W, s); return 1; });
+      st.push_back([raw0, st0, B, H1, W1](cudaStream_t s) { gn_stats(raw0, st0, B, H1 * W1, 32, G, s); return 1; });
+      GnApply a{raw0, st0, gw, gb, B, H1 * W1, 32, G, 1, 0, nullptr, nullptr, nullptr, nullptr, a0, 32};
+      st.push_back([a](cudaStream_t s) { gn_apply(a, s); return 1; });
+      st.push_back([a0, x, B, H1, W1](cudaStream_t s) { maxpool3x3s2(a0, x, B, H1, W1, 32, s); return 1; });
+    }
+  }
+  int h = H2, w = W2, cin = 32;
+  const int nblocks[4] = {3, 4, 6, 3};
+  auto conv_gn = [&](const bf16* in, int ih, int iw, int ci, const std::string& wname, int co, int k, int stride,
+                     bf16* raw, float* stats) {
+    if (dry_) return;
+    ConvGemm g;
+    g.in = in; g.NB = B; g.H = ih; g.W = iw; g.Cin = ci; g.in_pitch = ci;
+    g.w = Wb(wname, {co, k * k * ci}); g.Cout = co; g.KH = g.KW = k; g.stride = stride; g.pad = (k == 3) ? 1 : 0;
+    g.act = ACT_NONE; g.out = raw; g.ldc = co;
+    add_gemm(st, g);
+    const int oh = g.Ho(), ow = g.Wo();
+    st.push_back([raw, stats, B, oh, ow, co](cudaStream_t s) { gn_stats(raw, stats, B, oh * ow, co, G, s); return 1; });
+  };
+  for (int li = 0; li < 4; ++li) {
+    const int mid = 32 << li, cout = mid * 4;
+    for (int b = 0; b < nblocks[li]; ++b) {
+      const int stride = (b == 0 && li > 0) ? 2 : 1;
+      const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+      const std::string p = ns + ".depth.l" + std::to_string(li + 1) + "." + std::to_string(b);
+      bf16* r1 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
+      bf16* t1 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
+      bf16* r2 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
+      bf16* t2 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
+      bf16* r3 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+      bf16* out = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+      float* s1 = new_stats(G);
+      float* s2 = new_stats(G);
+      float* s3 = new_stats(G);
+      bf16* rds = nullptr;
+      float* sds = nullptr;
+      if (b == 0) {
+        rds = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+        sds = new_stats(G);
+      }
+      if (dry_) { x = out; h = ho; w = wo; cin = cout; continue; }
+      conv_gn(x, h, w, cin, p + ".c1.w", mid, 1, 1, r1, s1);
+      {
+        GnApply a{r1, s1, Wf(p + ".gn1.w", {mid}), Wf(p + ".gn1.b", {mid}), B, h * w, mid, G, 1, 0,
+                  nullptr, nullptr, nullptr, nullptr, t1, mid};
+        st.push_back([a](cudaStream_t s) { gn_apply(a, s); return 1; });
+      }
+      conv_gn(t1, h, w, mid, p + ".c2.w", mid, 3, stride, r2, s2);
+      {
+        GnApply a{r2, s2, Wf(p + ".gn2.w", {mid}), Wf(p + ".gn2.b", {mid}), B, ho * wo, mid, G, 1, 0,
+                  nullptr, nullptr, nullptr, nullptr, t2, mid};
+        st.push_back([a](cudaStream_t s) { gn_apply(a, s); return 1; });
+      }
+      conv_gn(t2, ho, wo, mid, p + ".c3.w", cout, 1, 1, r3, s3);
+      if (b == 0) conv_gn(x, h, w, cin, p + ".ds.w", cout, 1, stride, rds, sds);
+      {
+        GnApply a{r3, s3, Wf(p + ".gn3.w", {cout}), Wf(p + ".gn3.b", {cout}), B, ho * wo, cout, G, 1,
+                  b == 0 ? 2 : 1, b == 0 ? rds : x, sds,
+                  b == 0 ? Wf(p + ".dsgn.w", {cout}) : nullptr, b == 0 ? Wf(p + ".dsgn.b", {cout}) : nullptr,
+                  out, cout};
+        st.push_back([a](cudaStream_t s) { gn_apply(a, s); return 1; });
+      }
+      x = out; h = ho; w = wo; cin = cout;
+    }
+  }
+  RVB_CHECK(h == 4 && w == 4, "depth trunk must end at 4x4 (depth frames must be 256x256)");
+  // compression conv3x3 1024->128 + GroupNorm(1,128) + ReLU -> tokens_d[:, :, 0:128]
+  bf16* rc = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 16 * 128 * 2));
+  float* sc = new_stats(1);
+  if (!dry_) {
+    ConvGemm g;
+    g.in = x; g.NB = B; g.H = 4; g.W = 4; g.Cin = 1024; g.in_pitch = 1024;
+    g.w = Wb(ns + ".depth.comp.w", {128, 9 * 1024}); g.Cout = 128; g.KH = g.KW = 3; g.stride = 1; g.pad = 1;
+    g.act = ACT_NONE; g.out = rc; g.ldc = 128;
+    add_gemm(st, g);
+    st.push_back([rc, sc, B](cudaStream_t s) { gn_stats(rc, sc, B, 16, 128, 1, s); return 1; });
+    GnApply a{rc, sc, Wf(ns + ".depth.comp.gn.w", {128}), Wf(ns + ".depth.comp.gn.b", {128}), B, 16, 128, 1, 1, 0,
+              nullptr, nullptr, nullptr, nullptr, tokens_d_, 192};
+    st.push_back([a](cudaStream_t s) { gn_apply(a, s); return 1; });
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// BERT-base encoder
+// ---------------------------------------------------------------------------------------
+void Engine::plan_bert(Stage& st) {
+  const int L = shp_.L;
+  const int R = (shp_.instr_rows == 1) ? 1 : shp_.B;   // one BERT pass per DISTINCT instruction row
+  const int64_t M = static_cast<int64_t>(R) * L;
+  bf16* xa = reinterpret_cast<bf16*>(alloc(M * 768 * 2));
+  bf16* xb = reinterpret_cast<bf16*>(alloc(M * 768 * 2));
+  bf16* qkv = reinterpret_cast<bf16*>(alloc(M * 2304 * 2));
+  bf16* ctx = reinterpret_cast<bf16*>(alloc(M * 768 * 2));
+  float* y = reinterpret_cast<float*>(alloc(M * 768 * 4));
+  bf16* hbuf = reinterpret_cast<bf16*>(alloc(M * 3072 * 2));
+  bert_out_ = xa;
+  if (dry_) return;
+  {
+    const float* word = Wf("hi.bert.word", {});
+    const float* pos = Wf("hi.bert.pos", {});
+    const float* type0 = Wf("hi.bert.type0", {768});
+    const float* g = Wf("hi.bert.emb_ln.w", {768});
+    const float* b = Wf("hi.bert.emb_ln.b", {768});
+    RVB_CHECK(weights_.at("hi.bert.pos").shape[0] >= L, "instruction longer than BERT's position table");
+    const int id_rows = shp_.instr_rows;
+    st.push_back([this, id_rows, R, L, word, pos, type0, g, b, xa](cudaStream_t s) {
+      bert_embed_ln(args_.instr_i64, args_.instr_f32, id_rows == 1 ? 1 : R, R, L, word, pos, type0, g, b, xa, s);
+      return 1;
+    });
+  }
+  for (int i = 0; i < 12; ++i) {
+    const std::string p = "hi.bert." + std::to_string(i);
+    add_gemm(st, linear(xa, M, 768, 768, Wb(p + ".qkv.w", {2304, 768}), 2304, Wf(p + ".qkv.b", {2304}), ACT_NONE, qkv,
+                        2304, 0));
+    st.push_back([qkv, ctx, R, L](cudaStream_t s) { bert_self_attention(qkv, ctx, R, L, 12, s); return 1; });
+    add_gemm(st, linear(ctx, M, 768, 768, Wb(p + ".ao.w", {768, 768}), 768, Wf(p + ".ao.b", {768}), ACT_NONE, y, 768, 1,
+                        xa, 768, 0));
+    {
+      const float* g = Wf(p + ".ln1.w", {768});
+      const float* b = Wf(p + ".ln1.b", {768});
+      st.push_back([y, M, g, b, xb](cudaStream_t s) {
+        layernorm_rows(y, static_cast<int>(M), 768, g, b, 1e-12f, nullptr, 1, xb, s);
+        return 1;
+      });
+    }
+    add_gemm(st, linear(xb, M, 768, 768, Wb(p + ".ff1.w", {3072, 768}), 3072, Wf(p + ".ff1.b", {3072}), ACT_GELU, hbuf,
+                        3072, 0));
+    add_gemm(st, linear(hbuf, M, 3072, 3072, Wb(p + ".ff2.w", {768, 3072}), 768, Wf(p + ".ff2.b", {768}), ACT_NONE, y,
+                        768, 1, xb, 768, 0));
+    {
+      const float* g = Wf(p + ".ln2.w", {768});
+      const float* b = Wf(p + ".ln2.b", {768});
+      st.push_back([y, M, g, b, xa](cudaStream_t s) {
+        layernorm_rows(y, static_cast<int>(M), 768, g, b, 1e-12f, nullptr, 1, xa, s);
+        return 1;
+      });
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Visual_Ling_Attn for both modalities at once + token mean-pool
+//   bert: [R*L,768] bf16; kvin: [2*B*16,256] bf16 (rgb rows then depth rows);
+//   pooled -> out[b*out_pitch + mod*256 + d]
+// ---------------------------------------------------------------------------------------
+void Engine::plan_cross_modal(Stage& st, const bf16* bert, const bf16* kvin, bf16* out, int64_t out_pitch) {
+  const int B = shp_.B, L = shp_.L;
+  const int R = (shp_.instr_rows == 1) ? 1 : B;
+  const int64_t MQ = static_cast<int64_t>(R) * L, MV = 2ll * B * 16, MX = 2ll * B * L;
+  float* f32a = reinterpret_cast<float*>(alloc(std::max<int64_t>(MX, MV) * 256 * 4));
+  bf16* Q0 = reinterpret_cast<bf16*>(alloc(MQ * 256 * 2));
+  bf16* qq = reinterpret_cast<bf16*>(alloc(MQ * 256 * 2));
+  bf16* vis = reinterpret_cast<bf16*>(alloc(MV * 256 * 2));
+  bf16* kv = reinterpret_cast<bf16*>(alloc(MV * 512 * 2));
+  bf16* ctx = reinterpret_cast<bf16*>(alloc(MX * 256 * 2));
+  bf16* X = reinterpret_cast<bf16*>(alloc(MX * 256 * 2));
+  bf16* hff = reinterpret_cast<bf16*>(alloc(MX * 1024 * 2));
+  bf16* Y = reinterpret_cast<bf16*>(alloc(MX * 256 * 2));
+  float* pe = reinterpret_cast<float*>(alloc(static_cast<size_t>(L) * 256 * 4));
+  if (dry_) return;
+  const std::string p = "hi.vla";
+  const float* ln0w = Wf(p + ".ln0.w", {256});
+  const float* ln0b = Wf(p + ".ln0.b", {256});
+  st.push_back([pe, L](cudaStream_t s) { sinusoid_table(pe, L, 256, s); return 1; });
+  // query side (shared by both modalities)
+  add_gemm(st, linear(bert, MQ, 768, 768, Wb(p + ".ins_fc.w", {256, 768}), 256, Wf(p + ".ins_fc.b", {256}), ACT_RELU,
+                      f32a, 256, 1));
+  st.push_back([f32a, MQ, ln0w, ln0b, pe, L, Q0](cudaStream_t s) {
+    layernorm_rows(f32a, static_cast<int>(MQ), 256, ln0w, ln0b, 1e-5f, pe, L, Q0, s);
+    return 1;
+  });
+  add_gemm(st, linear(Q0, MQ, 256, 256, Wb(p + ".fc_q.w", {256, 256}), 256, Wf(p + ".fc_q.b", {256}), ACT_NONE, qq, 256, 0));
+  // key/value side
+  add_gemm(st, linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
+                      f32a, 256, 1));
+  st.push_back([f32a, MV, ln0w, ln0b, vis](cudaStream_t s) {
+    layernorm_rows(f32a, static_cast<int>(MV), 256, ln0w, ln0b, 1e-5f, nullptr, 1, vis, s);
+    return 1;
+  });
+  add_gemm(st, linear(vis, MV, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}), ACT_NONE, kv, 512, 0));
+  const int q_shared = (R == 1) ? 1 : 0;
+  st.push_back([qq, kv, ctx, B, L, q_shared](cudaStream_t s) { vla_cross_attention(qq, kv, ctx, B, L, 2, q_shared, s); return 1; });
+  add_gemm(st, linear(ctx, MX, 256, 256, Wb(p + ".fc_o.w", {256, 256}), 256, Wf(p + ".fc_o.b", {256}), ACT_NONE, f32a, 256,
+                      1, Q0, 256, static_cast<int>(MQ)));
+  {
+    const float* g = Wf(p + ".ln1.w", {256});
+    const float* b = Wf(p + ".ln1.b", {256});
+    st.push_back([f32a, MX, g, b, X](cudaStream_t s) {
+      layernorm_rows(f32a, static_cast<int>(MX), 256, g, b, 1e-5f, nullptr, 1, X, s);
+      return 1;
+    });
+  }
+  add_gemm(st, linear(X, MX, 256, 256, Wb(p + ".fc1.w", {1024, 256}), 1024, Wf(p + ".fc1.b", {1024}), ACT_RELU, hff, 1024, 0));
+  add_gemm(st, linear(hff, MX, 1024, 1024, Wb(p + ".fc2.w", {256, 1024}), 256, Wf(p + ".fc2.b", {256}), ACT_NONE, f32a,
+                      256, 1, X, 256, 0));
+  {
+    const float* g = Wf(p + ".ln2.w", {256});
+    const float* b = Wf(p + ".ln2.b", {256});
+    st.push_back([f32a, MX, g, b, Y](cudaStream_t s) {
+      layernorm_rows(f32a, static_cast<int>(MX), 256, g, b, 1e-5f, nullptr, 1, Y, s);
+      return 1;
+    });
+  }
+  vla_tokens_ = Y;
+  st.push_back([Y, B, L, out, out_pitch](cudaStream_t s) { token_mean(Y, 2, B, L, 256, out, out_pitch, 256, s); return 1; });
+}
+
+// ---------------------------------------------------------------------------------------
+// hi / lo tails
+// ---------------------------------------------------------------------------------------
+void Engine::plan_hi_tail(Stage& pre, Stage& st) {
+  const int B = shp_.B, N = shp_.N, T = B / N;
+  kvin_ = reinterpret_cast<bf16*>(alloc(2ull * B * 16 * 256 * 2));
+  concat_hi_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 896 * 2));
+  gx_hi_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 2048 * 4));
+  y_hi_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 512 * 4));
+  hscr_hi_ = reinterpret_cast<float*>(alloc(2ull * N * 512 * 4));
+  logits_buf_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 4 * 4));
+  hc_hi_buf_ = reinterpret_cast<float*>(alloc(2ull * N * 512 * 4));
+  subgoal_buf_ = reinterpret_cast<int64_t*>(alloc(static_cast<size_t>(B) * 8));
+  if (!dry_) {
+    const float* er = Wf("hi.rgb_emb", {16, 64});
+    const float* ed = Wf("hi.depth_emb", {16, 64});
+    // spatial-embedding channels are input independent; written once per forward (cheap) so
+    // that a weight update is always reflected
+    pre.push_back([this, er, B](cudaStream_t s) { fill_spatial_embedding(er, tokens_r_, B, 2112, 2048, cellmean_r_, 2112, s); return 1; });
+    pre.push_back([this, ed, B](cudaStream_t s) { fill_spatial_embedding(ed, tokens_d_, B, 192, 128, nullptr, 0, s); return 1; });
+    // rgb_kv / depth_kv: Conv1d(k=1) == per-cell linear (seq2seq_highlevel_cma.py:102-112,198-199)
+    add_gemm(st, linear(tokens_r_, static_cast<int64_t>(B) * 16, 2112, 2112, Wb("hi.rgb_kv.w", {256, 2112}), 256,
+                        Wf("hi.rgb_kv.b", {256}), ACT_NONE, kvin_, 256, 0));
+    add_gemm(st, linear(tokens_d_, static_cast<int64_t>(B) * 16, 192, 192, Wb("hi.depth_kv.w", {256, 192}), 256,
+                        Wf("hi.depth_kv.b", {256}), ACT_NONE, kvin_ + static_cast<size_t>(B) * 16 * 256, 256, 0));
+  }
+  plan_cross_modal(st, bert_out_, kvin_, concat_hi_ + 384, 896);
+  if (dry_) return;
+  // rgb_linear (mean over cells -> Linear -> ReLU), depth_linear (Flatten -> Linear -> ReLU)
+  add_gemm(st, linear(cellmean_r_, B, 2112, 2112, Wb("hi.rgb_linear.w", {256, 2112}), 256, Wf("hi.rgb_linear.b", {256}),
+                      ACT_RELU, concat_hi_, 896, 0));
+  add_gemm(st, linear(tokens_d_, B, 3072, 3072, Wb("hi.depth_linear.w", {128, 3072}), 128, Wf("hi.depth_linear.b", {128}),
+                      ACT_RELU, concat_hi_ + 256, 896, 0));
+  add_gemm(st, linear(concat_hi_, B, 896, 896, Wb("hi.lstm.wih", {2048, 896}), 2048, Wf("hi.lstm.b", {2048}), ACT_NONE,
+                      gx_hi_, 2048, 1));
+  {
+    const bf16* whh = Wb("hi.lstm.whh", {2048, 512});
+    st.push_back([this, whh, T, N](cudaStream_t s) {
+      lstm_forward(gx_hi_, whh, args_.masks, args_.mask_stride, args_.hc_hi_in, args_.hc_hi_out, hscr_hi_, y_hi_, T, N, s);
+      return T;
+    });
+    const float* lw = Wf("hi.linear.w", {4, 512});
+    const float* lb = Wf("hi.linear.b", {4});
+    st.push_back([this, lw, lb, B](cudaStream_t s) { heads_linear(y_hi_, B, 512, lw, lb, 4, args_.logits, s); return 1; });
+  }
+}
+
+void Engine::plan_lo_tail(Stage& st) {
+  const int B = shp_.B, N = shp_.N, T = B / N;
+  lo_in_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 416 * 2));
+  gx_lo_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 2048 * 4));
+  y_lo_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 512 * 4));
+  hscr_lo_ = reinterpret_cast<float*>(alloc(2ull * N * 512 * 4));
+  act_buf_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 2 * 4));
+  stop_buf_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 4));
+  hc_lo_buf_ = reinterpret_cast<float*>(alloc(2ull * N * 512 * 4));
+  if (dry_) return;
+  add_gemm(st, linear(tokens_d_, B, 3072, 3072, Wb("lo.depth_fc.w", {128, 3072}), 128, Wf("lo.depth_fc.b", {128}),
+                      ACT_RELU, lo_in_, 416, 0));
+  add_gemm(st, linear(gmean_r_, B, 2048, 2048, Wb("lo.rgb_fc.w", {256, 2048}), 256, Wf("lo.rgb_fc.b", {256}), ACT_RELU,
+                      lo_in_ + 128, 416, 0));
+  {
+    const float* tbl = Wf("lo.sub_emb", {5, 32});
+    st.push_back([this, tbl, B](cudaStream_t s) { sub_task_embed(args_.sub_goal, tbl, B, lo_in_ + 384, 416, s); return 1; });
+  }
+  add_gemm(st, linear(lo_in_, B, 416, 416, Wb("lo.lstm.wih", {2048, 416}), 2048, Wf("lo.lstm.b", {2048}), ACT_NONE, gx_lo_,
+                      2048, 1));
+  const bf16* whh = Wb("lo.lstm.whh", {2048, 512});
+  st.push_back([this, whh, T, N](cudaStream_t s) {
+    lstm_forward(gx_lo_, whh, args_.masks, args_.mask_stride, args_.hc_lo_in, args_.hc_lo_out, hscr_lo_, y_lo_, T, N, s);
+    return T;
+  });
+  const float* lw = Wf("lo.linear.w", {2, 512});
+  const float* lb = Wf("lo.linear.b", {2});
+  const float* sw = Wf("lo.stop.w", {1, 512});
+  const float* sb = Wf("lo.stop.b", {1});
+  st.push_back([this, lw, lb, B](cudaStream_t s) { heads_linear(y_lo_, B, 512, lw, lb, 2, args_.actions, s); return 1; });
+  st.push_back([this, sw, sb, B](cudaStream_t s) { heads_linear(y_lo_, B, 512, sw, sb, 1, args_.stop, s); return 1; });
+}
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
+  RVB_CHECK(finalized_, "hcm_finalize_weights must be called before planning");
+  RVB_CHECK(shp.B >= 1 && shp.N >= 1 && shp.B % shp.N == 0, "B must be a positive multiple of N");
+  RVB_CHECK(shp.L >= 1 && shp.L <= 256, "1 <= L <= 256");
+  RVB_CHECK(shp.instr_rows == 1 || shp.instr_rows == shp.B, "instr_rows must be 1 or B");
+  RVB_CHECK(shp.rgb_h >= 128 && shp.rgb_w >= 128 && shp.rgb_h % 32 == 0 && shp.rgb_w % 32 == 0,
+            "RGB frames must be multiples of 32 and at least 128x128");
+  RVB_CHECK(shp.depth_h == 256 && shp.depth_w == 256, "depth frames must be 256x256 (DDPPO encoder geometry)");
+  dry_ = (workspace == nullptr);
+  shp_ = shp;
+  arena_base_ = dry_ ? reinterpret_cast<uint8_t*>(uintptr_t(1) << 40) : reinterpret_cast<uint8_t*>(workspace);
+  RVB_CHECK(dry_ || (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+  arena_off_ = 0;
+  arena_cap_ = bytes;
+  gemms_.clear();
+  for (Stage* s : {&st_rgb_, &st_depth_, &st_rgb_lo_, &st_depth_lo_, &st_bert_, &st_pre_, &st_hi_tail_, &st_lo_tail_,
+                   &st_cm_only_})
+    s->clear();
+  planned_ = false;
+
+  const int B = shp.B;
+  // feature buffers shared by hi and lo
+  tokens_r_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 16 * 2112 * 2));
+  cellmean_r_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 2112 * 2));
+  gmean_r_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 2048 * 2));
+  tokens_d_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 16 * 192 * 2));
+  gn_stats_cap_ = static_cast<size_t>(B) * 16 * 2 * 64;   // 54 GroupNorm layers + compression
+  gn_stats_arena_ = reinterpret_cast<float*>(alloc(gn_stats_cap_ * sizeof(float)));
+  // host-call staging (hcm_forward_policy_host)
+  stage_rgb_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * shp.rgb_h * shp.rgb_w * 3 * 4));
+  stage_depth_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * shp.depth_h * shp.depth_w * 4));
+  stage_instr_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(shp.instr_rows) * shp.L * 4));
+  stage_masks_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 2 * 4));
+  stage_hc_hi_ = reinterpret_cast<float*>(alloc(2ull * shp.N * 512 * 4));
+  stage_hc_lo_ = reinterpret_cast<float*>(alloc(2ull * shp.N * 512 * 4));
+
+  const std::string trunk_ns = have_hi_ ? "hi" : "lo";
+  plan_rgb_trunk(trunk_ns, st_rgb_);
+  plan_depth_trunk(trunk_ns, st_depth_);
+  if (have_hi_ && have_lo_ && !lo_shares_trunks_) {
+    // lo has its own (different) frozen trunks: a second pair of trunk stages writing the same
+    // feature buffers, used only by hcm_forward_lo(reuse_trunks = 0)
+    plan_rgb_trunk("lo", st_rgb_lo_);
+    plan_depth_trunk("lo", st_depth_lo_);
+  }
+  if (have_hi_) {
+    plan_bert(st_bert_);
+    plan_hi_tail(st_pre_, st_hi_tail_);
+    // stand-alone cross-modal stage on caller tensors (BASELINE.json configs[2])
+    cm_bert_in_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(shp.instr_rows == 1 ? 1 : B) * shp.L * 768 * 2));
+    cm_kv_in_ = reinterpret_cast<bf16*>(alloc(2ull * B * 16 * 256 * 2));
+    cm_out_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 512 * 2));
+    plan_cross_modal(st_cm_only_, cm_bert_in_, cm_kv_in_, cm_out_, 512);
+  }
+  if (have_lo_) plan_lo_tail(st_lo_tail_);
+  label(st_rgb_, "rgb"); label(st_depth_, "depth"); label(st_rgb_lo_, "rgb_lo"); label(st_depth_lo_, "depth_lo");
+  label(st_bert_, "bert"); label(st_pre_, "pre"); label(st_hi_tail_, "hi_tail"); label(st_lo_tail_, "lo_tail");
+  label(st_cm_only_, "cross_modal");
+
+  const size_t need = arena_off_ + 1024;
+  if (!dry_) {
+    if (!streams_ready_) {
+      RVB_CUDA(cudaStreamCreateWithFlags(&side_[0], cudaStreamNonBlocking));
+      RVB_CUDA(cudaStreamCreateWithFlags(&side_[1], cudaStreamNonBlocking));
+      for (auto& ev : events_) RVB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      streams_ready_ = true;
+    }
+    planned_ = true;
+    trunks_valid_ = false;
+  }
+  return need;
+}
+
+// ---------------------------------------------------------------------------------------
+// run
+// ---------------------------------------------------------------------------------------
+int Engine::run(const Stage& st, cudaStream_t s) {
+  int n = 0;
+  for (const auto& op : st) n += op(s);
+  return n;
+}
+
+// trunks (RGB on the caller's stream, depth and BERT on side streams), joined before the tail
+void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s) {
+  const bool multi = multi_stream_;
+  Stage& rgb = (lo_weights && !st_rgb_lo_.empty()) ? st_rgb_lo_ : st_rgb_;
+  Stage& dep = (lo_weights && !st_depth_lo_.empty()) ? st_depth_lo_ : st_depth_;
+  if (!multi) {
+    launches_ += run(rgb, s);
+    launches_ += run(dep, s);
+    if (with_bert) launches_ += run(st_bert_, s);
+    return;
+  }
+  RVB_CUDA(cudaEventRecord(events_[0], s));
+  RVB_CUDA(cudaStreamWaitEvent(side_[0], events_[0], 0));
+  launches_ += run(dep, side_[0]);
+  RVB_CUDA(cudaEventRecord(events_[1], side_[0]));
+  if (with_bert) {
+    RVB_CUDA(cudaStreamWaitEvent(side_[1], events_[0], 0));
+    launches_ += run(st_bert_, side_[1]);
+    RVB_CUDA(cudaEventRecord(events_[2], side_[1]));
+  }
+  launches_ += run(rgb, s);
+  RVB_CUDA(cudaStreamWaitEvent(s, events_[1], 0));
+  if (with_bert) RVB_CUDA(cudaStreamWaitEvent(s, events_[2], 0));
+}
+
+void Engine::forward_hi(cudaStream_t s) {
+  RVB_CHECK(planned_ && have_hi_, "forward_hi: engine not planned or hi weights missing");
+  RVB_CHECK(args_.rgb && args_.depth && (args_.instr_f32 || args_.instr_i64) && args_.masks && args_.hc_hi_in &&
+                args_.hc_hi_out && args_.logits, "forward_hi: null argument");
+  launches_ = 0;
+  launches_ += run(st_pre_, s);
+  run_encoders(true, false, s);
+  launches_ += run(st_hi_tail_, s);
+  trunks_valid_ = true;
+}
+
+void Engine::forward_lo(bool reuse_trunks, cudaStream_t s) {
+  RVB_CHECK(planned_ && have_lo_, "forward_lo: engine not planned or lo weights missing");
+  RVB_CHECK(args_.masks && args_.sub_goal && args_.hc_lo_in && args_.hc_lo_out && args_.actions && args_.stop,
+            "forward_lo: null argument");
+  launches_ = 0;
+  if (reuse_trunks) {
+    RVB_CHECK(trunks_valid_ && (lo_shares_trunks_ || !have_hi_), "forward_lo: no reusable trunk features");
+  } else {
+    RVB_CHECK(args_.rgb && args_.depth, "forward_lo: null observation");
+    run_encoders(false, true, s);
+    trunks_valid_ = !have_hi_ || lo_shares_trunks_;
+  }
+  launches_ += run(st_lo_tail_, s);
+}
+
+void Engine::forward_policy(cudaStream_t s) {
+  RVB_CHECK(planned_ && have_hi_ && have_lo_, "forward_policy needs both models");
+  RVB_CHECK(lo_shares_trunks_, "forward_policy requires lo to share hi's frozen trunks");
+  int64_t* sg = args_.sub_goal_out != nullptr ? args_.sub_goal_out : subgoal_buf_;
+  forward_hi(s);
+  const int n_hi = launches_;
+  const int B = shp_.B;
+  const float* logits = args_.logits;
+  argmax_rows(logits, B, 4, sg, s);
+  args_.sub_goal = sg;
+  forward_lo(true, s);
+  launches_ += n_hi + 1;
+}
+
+std::vector<OpTiming> Engine::profile_policy(cudaStream_t s) {
+  RVB_CHECK(planned_ && have_hi_ && have_lo_ && lo_shares_trunks_, "profile_policy needs a planned hi+lo engine");
+  int64_t* sg = args_.sub_goal_out != nullptr ? args_.sub_goal_out : subgoal_buf_;
+  std::vector<const Stage*> order = {&st_pre_, &st_rgb_, &st_depth_, &st_bert_, &st_hi_tail_};
+  std::vector<OpTiming> out;
+  size_t nops = 2;
+  for (auto* st : order) nops += st->size();
+  nops += st_lo_tail_.size();
+  while (prof_events_.size() < nops + 1) {
+    cudaEvent_t ev;
+    RVB_CUDA(cudaEventCreate(&ev));
+    prof_events_.push_back(ev);
+  }
+  size_t ei = 0;
+  RVB_CUDA(cudaEventRecord(prof_events_[ei++], s));
+  auto run_timed = [&](const Stage& st) {
+    for (const auto& op : st) {
+      op(s);
+      RVB_CUDA(cudaEventRecord(prof_events_[ei++], s));
+      out.push_back({op.name, 0.0, op.flops});
+    }
+  };
+  for (auto* st : order) run_timed(*st);
+  argmax_rows(args_.logits, shp_.B, 4, sg, s);
+  RVB_CUDA(cudaEventRecord(prof_events_[ei++], s));
+  out.push_back({"argmax", 0.0, 0.0});
+  args_.sub_goal = sg;
+  run_timed(st_lo_tail_);
+  RVB_CUDA(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < out.size(); ++i) {
+    float ms = 0.f;
+    RVB_CUDA(cudaEventElapsedTime(&ms, prof_events_[i], prof_events_[i + 1]));
+    out[i].ms = ms;
+  }
+  trunks_valid_ = true;
+  return out;
+}
+
+void Engine::forward_policy_host(const float* rgb, const float* depth, const float* instr, const float* masks,
+                                 const float* hc_hi_in, const float* hc_lo_in, float* logits, float* actions,
+                                 float* stop, float* hc_hi_out, float* hc_lo_out, cudaStream_t s) {
+  RVB_CHECK(planned_, "engine not planned");
+  const int B = shp_.B, N = shp_.N;
+  const size_t rgb_b = static_cast<size_t>(B) * shp_.rgb_h * shp_.rgb_w * 3 * 4;
+  const size_t dep_b = static_cast<size_t>(B) * shp_.depth_h * shp_.depth_w * 4;
+  const size_t ins_b = static_cast<size_t>(shp_.instr_rows) * shp_.L * 4;
+  const size_t hc_b = 2ull * N * 512 * 4;
+  RVB_CUDA(cudaMemcpyAsync(stage_rgb_, rgb, rgb_b, cudaMemcpyHostToDevice, s));
+  RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, s));
+  RVB_CUDA(cudaMemcpyAsync(stage_instr_, instr, ins_b, cudaMemcpyHostToDevice, s));
+  RVB_CUDA(cudaMemcpyAsync(stage_masks_, masks, static_cast<size_t>(B) * 2 * 4, cudaMemcpyHostToDevice, s));
+  RVB_CUDA(cudaMemcpyAsync(stage_hc_hi_, hc_hi_in, hc_b, cudaMemcpyHostToDevice, s));
+  RVB_CUDA(cudaMemcpyAsync(stage_hc_lo_, hc_lo_in, hc_b, cudaMemcpyHostToDevice, s));
+  RunArgs a;
+  a.rgb = stage_rgb_; a.depth = stage_depth_; a.instr_f32 = stage_instr_; a.instr_i64 = nullptr;
+  a.masks = stage_masks_; a.mask_stride = 2;
+  a.hc_hi_in = stage_hc_hi_; a.hc_lo_in = stage_hc_lo_;
+  a.hc_hi_out = hc_hi_buf_; a.hc_lo_out = hc_lo_buf_;
+  a.logits = logits_buf_; a.actions = act_buf_; a.stop = stop_buf_;
+  a.sub_goal_out = nullptr;
+  args_ = a;
+  forward_policy(s);
+  RVB_CUDA(cudaMemcpyAsync(logits, logits_buf_, static_cast<size_t>(B) * 4 * 4, cudaMemcpyDeviceToHost, s));
+  RVB_CUDA(cudaMemcpyAsync(actions, act_buf_, static_cast<size_t>(B) * 2 * 4, cudaMemcpyDeviceToHost, s));
+  RVB_CUDA(cudaMemcpyAsync(stop, stop_buf_, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
+  RVB_CUDA(cudaMemcpyAsync(hc_hi_out, hc_hi_buf_, hc_b, cudaMemcpyDeviceToHost, s));
+  RVB_CUDA(cudaMemcpyAsync(hc_lo_out, hc_lo_buf_, hc_b, cudaMemcpyDeviceToHost, s));
+  RVB_CUDA(cudaStreamSynchronize(s));
+}
+
+void Engine::run_cross_modal(const void* bert, const void* rgb_sp, const void* depth_sp, void* pooled, cudaStream_t s) {
+  RVB_CHECK(planned_ && have_hi_, "run_cross_modal: engine not planned");
+  const int B = shp_.B, L = shp_.L;
+  const int R = shp_.instr_rows == 1 ? 1 : B;
+  launches_ = 0;
+  RVB_CUDA(cudaMemcpyAsync(cm_bert_in_, bert, static_cast<size_t>(R) * L * 768 * 2, cudaMemcpyDeviceToDevice, s));
+  RVB_CUDA(cudaMemcpyAsync(cm_kv_in_, rgb_sp, static_cast<size_t>(B) * 16 * 256 * 2, cudaMemcpyDeviceToDevice, s));
+  RVB_CUDA(cudaMemcpyAsync(cm_kv_in_ + static_cast<size_t>(B) * 16 * 256, depth_sp, static_cast<size_t>(B) * 16 * 256 * 2,
+                           cudaMemcpyDeviceToDevice, s));
+  launches_ += run(st_cm_only_, s);
+  RVB_CUDA(cudaMemcpyAsync(pooled, cm_out_, static_cast<size_t>(B) * 512 * 2, cudaMemcpyDeviceToDevice, s));
+}
+
+bool Engine::get_buffer(const std::string& name, void** ptr, int* dtype, std::vector<int64_t>* shape) const {
+  if (!planned_) return false;
+  const int B = shp_.B, L = shp_.L;
+  const int R = shp_.instr_rows == 1 ? 1 : B;
+  if (name == "rgb_tokens") { *ptr = tokens_r_; *dtype = 1; *shape = {B, 16, 2112}; return true; }
+  if (name == "rgb_cellmean") { *ptr = cellmean_r_; *dtype = 1; *shape = {B, 2112}; return true; }
+  if (name == "rgb_gmean") { *ptr = gmean_r_; *dtype = 1; *shape = {B, 2048}; return true; }
+  if (name == "rgb_layer4") { *ptr = rgb_feat_; *dtype = 1; *shape = {B, rgb_fh_, rgb_fw_, 2048}; return true; }
+  if (name == "depth_tokens") { *ptr = tokens_d_; *dtype = 1; *shape = {B, 16, 192}; return true; }
+  if (name == "bert") { *ptr = bert_out_; *dtype = 1; *shape = {R, L, 768}; return true; }
+  if (name == "vla_tokens") { *ptr = vla_tokens_; *dtype = 1; *shape = {2, B, L, 256}; return true; }
+  if (name == "kv_in") { *ptr = kvin_; *dtype = 1; *shape = {2, B * 16, 256}; return true; }
+  if (name == "hi_rnn_in") { *ptr = concat_hi_; *dtype = 1; *shape = {B, 896}; return true; }
+  if (name == "hi_rnn_out") { *ptr = y_hi_; *dtype = 0; *shape = {B, 512}; return true; }
+  if (name == "lo_rnn_in") { *ptr = lo_in_; *dtype = 1; *shape = {B, 416}; return true; }
+  if (name == "lo_rnn_out") { *ptr = y_lo_; *dtype = 0; *shape = {B, 512}; return true; }
+  return false;
+}
+
+Engine::~Engine() {
+  if (streams_ready_) {
+    cudaStreamDestroy(side_[0]);
+    cudaStreamDestroy(side_[1]);
+    for (auto& ev : events_) cudaEventDestroy(ev);
+  }
+}
+
+}  // namespace rvb

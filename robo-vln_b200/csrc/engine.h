@@ -1,0 +1,136 @@
+// Engine class behind the opaque hcm_engine handle of include/robovln_b200.h.
+#pragma once
+
+#include <functional>
+#include <initializer_list>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/robovln_b200.h"
+#include "rvb.h"
+
+namespace rvb {
+
+struct WTensor {
+  const void* ptr = nullptr;
+  int dtype = 0;  // HCM_F32 / HCM_BF16 / HCM_I64
+  std::vector<int64_t> shape;
+};
+
+// Pointers that change from call to call; the planned closures read them at launch time.
+struct RunArgs {
+  const float* rgb = nullptr;
+  const float* depth = nullptr;
+  const float* instr_f32 = nullptr;
+  const int64_t* instr_i64 = nullptr;
+  const float* masks = nullptr;
+  int mask_stride = 2;
+  const int64_t* sub_goal = nullptr;
+  const float* hc_hi_in = nullptr;
+  const float* hc_lo_in = nullptr;
+  float* hc_hi_out = nullptr;
+  float* hc_lo_out = nullptr;
+  float* logits = nullptr;
+  float* actions = nullptr;
+  float* stop = nullptr;
+  int64_t* sub_goal_out = nullptr;
+};
+
+// One planned launch (or a short fixed sequence of launches); fn returns the kernel count.
+struct Op {
+  std::function<int(cudaStream_t)> fn;
+  std::string name;     // filled for the profile listing
+  double flops = 0.0;   // algorithmic FLOPs (2*M*N*K) for tensor-core ops, 0 otherwise
+  Op() = default;
+  template <class F, class = typename std::enable_if<!std::is_same<typename std::decay<F>::type, Op>::value>::type>
+  Op(F&& f) : fn(std::forward<F>(f)) {}
+  int operator()(cudaStream_t s) const { return fn(s); }
+};
+using Stage = std::vector<Op>;
+
+struct OpTiming {
+  std::string name;
+  double ms = 0.0;
+  double flops = 0.0;
+};
+
+class Engine {
+ public:
+  Engine() = default;
+  ~Engine();
+
+  void set_tensor(const std::string& name, const void* ptr, int dtype, int ndim, const int64_t* shape);
+  void finalize(int have_hi, int have_lo, int lo_shares_trunks);
+  // workspace == nullptr: dry run, returns the bytes needed
+  size_t plan(const hcm_shape& shp, void* workspace, size_t bytes);
+
+  void forward_hi(cudaStream_t s);
+  void forward_lo(bool reuse_trunks, cudaStream_t s);
+  void forward_policy(cudaStream_t s);
+  void forward_policy_host(const float* rgb, const float* depth, const float* instr, const float* masks,
+                           const float* hc_hi_in, const float* hc_lo_in, float* logits, float* actions, float* stop,
+                           float* hc_hi_out, float* hc_lo_out, cudaStream_t s);
+  void run_cross_modal(const void* bert, const void* rgb_sp, const void* depth_sp, void* pooled, cudaStream_t s);
+  void run_encoders(bool with_bert, bool lo_weights, cudaStream_t s);
+  // single-stream replay of forward_policy with a CUDA event between every op
+  std::vector<OpTiming> profile_policy(cudaStream_t s);
+  int run(const Stage& st, cudaStream_t s);
+  bool get_buffer(const std::string& name, void** ptr, int* dtype, std::vector<int64_t>* shape) const;
+
+  RunArgs args_;
+  int64_t launches_ = 0;
+  bool multi_stream_ = false;
+  bool planned_ = false;
+  bool have_hi_ = false, have_lo_ = false, lo_shares_trunks_ = false;
+  hcm_shape shp_{};
+  Stage st_rgb_, st_depth_, st_rgb_lo_, st_depth_lo_, st_bert_, st_pre_, st_hi_tail_, st_lo_tail_, st_cm_only_;
+
+ private:
+  const WTensor& W(const std::string& name, int dtype, std::initializer_list<int64_t> shape) const;
+  const bf16* Wb(const std::string& n, std::initializer_list<int64_t> s) const;
+  const float* Wf(const std::string& n, std::initializer_list<int64_t> s) const;
+  void* alloc(size_t bytes);
+  float* new_stats(int G);
+  void add_gemm(Stage& st, const ConvGemm& g, int force_bn = 0);
+  static void label(Stage& st, const std::string& prefix);
+  static ConvGemm linear(const bf16* in, int64_t M, int K, int64_t lda, const bf16* w, int N, const float* bias, int act,
+                         void* out, int64_t ldc, int out_f32, const bf16* res = nullptr, int64_t ldr = 0,
+                         int res_rows = 0);
+  void plan_rgb_trunk(const std::string& ns, Stage& st);
+  void plan_depth_trunk(const std::string& ns, Stage& st);
+  void plan_bert(Stage& st);
+  void plan_cross_modal(Stage& st, const bf16* bert, const bf16* kvin, bf16* out, int64_t out_pitch);
+  void plan_hi_tail(Stage& pre, Stage& st);
+  void plan_lo_tail(Stage& st);
+
+  std::unordered_map<std::string, WTensor> weights_;
+  bool finalized_ = false;
+  bool dry_ = true;
+  uint8_t* arena_base_ = nullptr;
+  size_t arena_off_ = 0, arena_cap_ = 0;
+  std::vector<std::unique_ptr<GemmTcPlan>> gemms_;
+
+  // planned buffers
+  bf16 *tokens_r_ = nullptr, *cellmean_r_ = nullptr, *gmean_r_ = nullptr, *tokens_d_ = nullptr;
+  bf16* rgb_feat_ = nullptr;
+  int rgb_fh_ = 0, rgb_fw_ = 0;
+  float* gn_stats_arena_ = nullptr;
+  size_t gn_stats_cap_ = 0, gn_stats_used_ = 0;
+  bf16 *bert_out_ = nullptr, *kvin_ = nullptr, *concat_hi_ = nullptr, *lo_in_ = nullptr, *vla_tokens_ = nullptr;
+  float *gx_hi_ = nullptr, *y_hi_ = nullptr, *hscr_hi_ = nullptr, *gx_lo_ = nullptr, *y_lo_ = nullptr, *hscr_lo_ = nullptr;
+  float *logits_buf_ = nullptr, *act_buf_ = nullptr, *stop_buf_ = nullptr, *hc_hi_buf_ = nullptr, *hc_lo_buf_ = nullptr;
+  int64_t* subgoal_buf_ = nullptr;
+  bf16 *cm_bert_in_ = nullptr, *cm_kv_in_ = nullptr, *cm_out_ = nullptr;
+  float *stage_rgb_ = nullptr, *stage_depth_ = nullptr, *stage_instr_ = nullptr, *stage_masks_ = nullptr,
+        *stage_hc_hi_ = nullptr, *stage_hc_lo_ = nullptr;
+
+  bool trunks_valid_ = false;
+  bool streams_ready_ = false;
+  cudaStream_t side_[2] = {nullptr, nullptr};
+  cudaEvent_t events_[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> prof_events_;
+};
+
+}  // namespace rvb

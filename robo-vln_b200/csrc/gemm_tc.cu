@@ -1,0 +1,479 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernel for sm_100a.
+//
+// One persistent, warp-specialised kernel covers every dense contraction of the HCM policy
+// forward (reference call sites: torchvision ResNet-50 convs behind
+// robo_vln_baselines/models/encoders/resnet_encoders.py:189-237, the DDPPO GroupNorm ResNet
+// convs of habitat_baselines/rl/ddppo/policy/resnet.py:65-77, every nn.Linear of BERT and of
+// robo_vln_baselines/models/transformer/transformer.py, the kv/linear heads of
+// seq2seq_highlevel_cma.py:83-115 and the LSTM input projections):
+//
+//   out[m, n] = act( sum_{tap, c} A(m, tap, c) * W[n, tap*Cin + c] + bias[n] + res[m, n] )
+//
+// * A operand: NHWC bf16 activations read straight from the tensor by TMA -- no im2col
+//   buffer.  For a KHxKW filter the K loop walks (tap, 64-channel block); each step is one
+//   4-D box load (64 ch, Wo, th, nb) whose start coordinate is shifted by the tap offset,
+//   with TMA out-of-bounds zero fill providing the padding and elementStrides providing the
+//   convolution stride.  Because an M tile is a set of full output rows, the box lands in
+//   shared memory exactly as the 128-row, K-major, 128B-swizzled tile UMMA expects.
+// * B operand: weights [Cout, KH*KW*Cin] bf16, K-major, 2-D TMA boxes (64, BN).
+// * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16, fp32 accumulators in TMEM,
+//   double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 =
+//   epilogue (tcgen05.ld -> bias / residual / ReLU|GELU -> bf16|fp32 global store).
+#include "common.cuh"
+#include "rvb.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace rvb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: powers of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmTcParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles;
+        const int nt = tile - mt * p.n_tiles;
+        int img = 0, h0 = 0;
+        if (!p.plain) {
+          if (p.nb == 1) {
+            img = mt / p.tiles_per_img;
+            h0 = (mt - img * p.tiles_per_img) * p.th;
+          } else {
+            img = mt * p.nb;
+          }
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + C::B_STAGE_BYTES);
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
+          if (p.plain) {
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, mt * BLOCK_M, 0, 0);
+          } else {
+            const int r = tap / p.KW;
+            const int s = tap - r * p.KW;
+            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, s - p.pad, h0 * p.stride + r - p.pad, img);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cb * BLOCK_K, nt * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                      static_cast<uint32_t>((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ---------------------
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
+      const int nt = tile - mt * p.n_tiles;
+      const int row_in_tile = quad * 32 + lane;
+      const long long m = static_cast<long long>(mt) * p.tile_rows + row_in_tile;
+      const bool row_ok = (row_in_tile < p.tile_rows) && (m < p.M);
+      const int n0 = nt * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+      const bf16* res_row = nullptr;
+      if (p.res != nullptr && row_ok) {
+        const long long rr = (p.res_rows > 0) ? (m % p.res_rows) : m;
+        res_row = p.res + rr * p.ldr;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated body below
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        const int n = n0 + c0;
+        if (row_ok && n < p.N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+        }
+        if (res_row != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (n + j < p.N) {
+              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res_row + n + j));
+              float2 t;
+              t = unpack_bf16x2(r4.x); f[j] += t.x; f[j + 1] += t.y;
+              t = unpack_bf16x2(r4.y); f[j + 2] += t.x; f[j + 3] += t.y;
+              t = unpack_bf16x2(r4.z); f[j + 4] += t.x; f[j + 5] += t.y;
+              t = unpack_bf16x2(r4.w); f[j + 6] += t.x; f[j + 7] += t.y;
+            }
+          }
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        } else if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + m * p.ldc + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (n + j < p.N) {
+              uint4 q;
+              q.x = pack_bf16x2(f[j], f[j + 1]);
+              q.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              q.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              q.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = q;
+            }
+          }
+        }
+        }  // row_ok
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  RVB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  return fn;
+}
+
+void encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, const uint32_t* estr) {
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = estr[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                                 const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string msg = "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ") dims=";
+    for (int i = 0; i < rank; ++i) msg += std::to_string(dims[i]) + (i + 1 < rank ? "x" : "");
+    msg += " box=";
+    for (int i = 0; i < rank; ++i) msg += std::to_string(box[i]) + (i + 1 < rank ? "x" : "");
+    throw Error(static_cast<int>(r), msg);
+  }
+}
+
+template <int BN>
+void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN><<<plan.grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(plan.tmA, plan.tmB, plan.p);
+  RVB_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    RVB_CUDA(cudaGetDevice(&dev));
+    RVB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return sms;
+}
+
+bool use_simt_gemm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_GEMM");
+    v = (e != nullptr && std::strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
+  RVB_CHECK(g.in != nullptr && g.w != nullptr && g.out != nullptr, "gemm: null operand");
+  RVB_CHECK(g.Cin % 8 == 0 && g.in_pitch % 8 == 0 && g.in_pitch >= g.Cin, "gemm: Cin / pitch must be multiples of 8");
+  RVB_CHECK((reinterpret_cast<uintptr_t>(g.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
+            "gemm: operands must be 16-byte aligned");
+  RVB_CHECK(g.Cout % 8 == 0, "gemm: Cout must be a multiple of 8");
+  RVB_CHECK(g.ldc % (g.out_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0,
+            "gemm: output pitch/alignment");
+  if (g.res != nullptr)
+    RVB_CHECK(g.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g.res) & 15) == 0, "gemm: residual pitch/alignment");
+  if (g.bias != nullptr) RVB_CHECK((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias alignment");
+
+  plan->desc = g;
+  GemmTcParams& p = plan->p;
+  std::memset(&p, 0, sizeof(p));
+  const int Ho = g.Ho(), Wo = g.Wo();
+  const long long M = g.M();
+  RVB_CHECK(M > 0 && M < (1ll << 31), "gemm: M out of range");
+  p.M = static_cast<int>(M);
+  p.N = g.Cout;
+  p.Cin = g.Cin;
+  p.KW = g.KW;
+  p.cblocks = (g.Cin + BLOCK_K - 1) / BLOCK_K;
+  p.num_kb = g.KH * g.KW * p.cblocks;
+  p.stride = g.stride;
+  p.pad = g.pad;
+  p.plain = g.plain() ? 1 : 0;
+  p.bias = g.bias;
+  p.res = g.res;
+  p.ldr = g.ldr;
+  p.res_rows = g.res_rows;
+  p.act = g.act;
+  p.out = g.out;
+  p.ldc = g.ldc;
+  p.out_f32 = g.out_f32;
+
+  const uint64_t pitchB = static_cast<uint64_t>(g.in_pitch) * 2;
+  if (p.plain) {
+    p.tile_rows = BLOCK_M;
+    p.th = 1;
+    p.nb = 1;
+    p.tiles_per_img = 1;
+    p.m_tiles = static_cast<int>((M + BLOCK_M - 1) / BLOCK_M);
+    const uint64_t dims[4] = {static_cast<uint64_t>(g.Cin), static_cast<uint64_t>(M), 1, 1};
+    const uint64_t strides[3] = {pitchB, pitchB * static_cast<uint64_t>(M), pitchB * static_cast<uint64_t>(M)};
+    const uint32_t box[4] = {BLOCK_K, BLOCK_M, 1, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    encode_map(&plan->tmA, g.in, 4, dims, strides, box, es);
+  } else {
+    RVB_CHECK(Wo <= BLOCK_M, "conv: output width > 128 is not supported by the full-row tiling");
+    RVB_CHECK(Wo * g.stride <= 256, "conv: box width exceeds the TMA limit");
+    const int P = Ho * Wo;
+    if (P >= BLOCK_M) {
+      int th = 1;
+      for (int t = 1; t <= Ho; ++t)
+        if (Ho % t == 0 && t * Wo <= BLOCK_M && t * g.stride <= 256) th = t;
+      p.th = th;
+      p.nb = 1;
+      p.tiles_per_img = Ho / th;
+      p.tile_rows = th * Wo;
+      p.m_tiles = g.NB * p.tiles_per_img;
+    } else {
+      p.th = Ho;
+      p.nb = BLOCK_M / P;
+      p.tiles_per_img = 1;
+      p.tile_rows = p.nb * P;
+      p.m_tiles = (g.NB + p.nb - 1) / p.nb;
+    }
+    const uint64_t dims[4] = {static_cast<uint64_t>(g.Cin), static_cast<uint64_t>(g.W), static_cast<uint64_t>(g.H),
+                              static_cast<uint64_t>(g.NB)};
+    const uint64_t strides[3] = {pitchB, pitchB * g.W, pitchB * g.W * g.H};
+    const uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(Wo * g.stride), static_cast<uint32_t>(p.th * g.stride),
+                             static_cast<uint32_t>(p.nb)};
+    const uint32_t es[4] = {1, static_cast<uint32_t>(g.stride), static_cast<uint32_t>(g.stride), 1};
+    encode_map(&plan->tmA, g.in, 4, dims, strides, box, es);
+  }
+  p.a_bytes = static_cast<uint32_t>(p.tile_rows) * BLOCK_K * 2;
+
+  // N tile: prefer the candidate with the best wave efficiency on this device; ties -> larger BN.
+  const int sms = device_sm_count();
+  int best_bn = 0;
+  double best_score = -1.0;
+  const int cands[3] = {256, 128, 64};
+  for (int bn : cands) {
+    if (force_bn != 0 && bn != force_bn) continue;
+    if (force_bn == 0 && bn > 64 && g.Cout <= bn / 2) continue;  // more than half the tile would be padding
+    const int nt = (g.Cout + bn - 1) / bn;
+    const long long tiles = static_cast<long long>(p.m_tiles) * nt;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double eff = static_cast<double>(tiles) / static_cast<double>(waves * sms);
+    const double fill = static_cast<double>(g.Cout) / static_cast<double>(nt * bn);
+    const double score = eff * fill * (bn == 64 ? 0.85 : 1.0);  // BN=64 runs the tensor pipe at lower efficiency
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best_bn = bn;
+    }
+  }
+  RVB_CHECK(best_bn != 0, "gemm: no tile configuration");
+  plan->BN = best_bn;
+  p.n_tiles = (g.Cout + best_bn - 1) / best_bn;
+
+  const uint64_t Ktot = static_cast<uint64_t>(g.KH) * g.KW * g.Cin;
+  const uint64_t bdims[2] = {Ktot, static_cast<uint64_t>(g.Cout)};
+  const uint64_t bstrides[1] = {Ktot * 2};
+  const uint32_t bbox[2] = {BLOCK_K, static_cast<uint32_t>(best_bn)};
+  const uint32_t bes[2] = {1, 1};
+  RVB_CHECK((Ktot * 2) % 16 == 0, "gemm: weight row pitch must be a multiple of 16 bytes");
+  encode_map(&plan->tmB, g.w, 2, bdims, bstrides, bbox, bes);
+
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  plan->grid = static_cast<int>(std::min<long long>(tiles, sms));
+  plan->valid = true;
+}
+
+void gemm_tc_launch(const GemmTcPlan& plan, cudaStream_t stream) {
+  RVB_CHECK(plan.valid, "gemm: plan not built");
+  if (use_simt_gemm()) {
+    gemm_simt_launch(plan.desc, stream);
+    return;
+  }
+  switch (plan.BN) {
+    case 64: launch_bn<64>(plan, stream); break;
+    case 128: launch_bn<128>(plan, stream); break;
+    case 256: launch_bn<256>(plan, stream); break;
+    default: RVB_CHECK(false, "gemm: bad BN");
+  }
+}
+
+}  // namespace rvb

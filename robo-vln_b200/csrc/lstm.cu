@@ -1,0 +1,105 @@
+// RNNStateEncoder (LSTM, 1 layer, hidden 512) recurrence.
+// Reference: habitat_baselines/rl/models/rnn_state_encoder.py:74-142 around torch.nn.LSTM
+// (gate order i,f,g,o).  The input projection gx = x W_ih^T + b_ih + b_hh for all T*N rows is
+// one tensor-core GEMM (gemm_tc.cu); this file does the serial part, one launch per time step
+// (captured in the CUDA graph): gates = gx[t] + (mask-reset h) W_hh^T, then the cell update.
+//
+// Mask semantics reproduced exactly: (h, c) are multiplied by masks[t] at t = 0 and at every
+// later step where ANY env has a zero mask (the reference's segment starts); single-step
+// batches (T == 1) always multiply (single_forward).
+#include "common.cuh"
+#include "rvb.h"
+
+namespace rvb {
+
+namespace {
+
+constexpr int HID = 512;
+constexpr int UNITS_PER_CTA = 8;               // 8 hidden units x 4 gates = 32 rows = 32 lanes
+constexpr int WPITCH = HID + 2;                // bf16 elements; +2 -> row-to-row bank shift of 1 word
+
+__global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict__ gx, const bf16* __restrict__ whh,
+                                                        const float* __restrict__ masks, int mask_stride,
+                                                        const float* __restrict__ h_prev,
+                                                        const float* __restrict__ c_prev, float* __restrict__ h_next,
+                                                        float* __restrict__ c_next, float* __restrict__ h_final,
+                                                        float* __restrict__ y, int t, int N) {
+  __shared__ __align__(16) bf16 sW[32 * WPITCH];
+  __shared__ int s_flag;
+  const int u0 = blockIdx.x * UNITS_PER_CTA;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+  // rows of W_hh owned by this CTA: lane r <-> gate r/8, unit u0 + r%8
+  for (int i = threadIdx.x; i < 32 * (HID / 2); i += blockDim.x) {
+    const int r = i / (HID / 2), k2 = i % (HID / 2);
+    const int wrow = (r >> 3) * HID + u0 + (r & 7);
+    reinterpret_cast<uint32_t*>(sW + r * WPITCH)[k2] =
+        reinterpret_cast<const uint32_t*>(whh + static_cast<long long>(wrow) * HID)[k2];
+  }
+  if (threadIdx.x == 0) s_flag = (t == 0) ? 1 : 0;
+  __syncthreads();
+  if (t != 0 && warp == 0) {
+    int any = 0;
+    for (int n = lane; n < N; n += 32) any |= (masks[(static_cast<long long>(t) * N + n) * mask_stride] == 0.0f) ? 1 : 0;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0 && any) s_flag = 1;
+  }
+  __syncthreads();
+  const bool apply_mask = s_flag != 0;
+
+  const uint32_t* wrow = reinterpret_cast<const uint32_t*>(sW + lane * WPITCH);
+  for (int n = warp; n < N; n += nwarps) {
+    const float m = apply_mask ? masks[(static_cast<long long>(t) * N + n) * mask_stride] : 1.0f;
+    const float* hp = h_prev + static_cast<long long>(n) * HID;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int k2 = 0; k2 < HID / 2; ++k2) {
+      const float2 w2 = unpack_bf16x2(wrow[k2]);
+      const float2 h2 = *reinterpret_cast<const float2*>(hp + 2 * k2);
+      acc = fmaf(w2.x, h2.x, acc);
+      acc = fmaf(w2.y, h2.y, acc);
+    }
+    acc = acc * m;  // (m*h) W^T == m * (h W^T) for a per-env scalar mask
+    const int gate = lane >> 3, u = lane & 7;
+    acc += gx[(static_cast<long long>(t) * N + n) * (4 * HID) + gate * HID + u0 + u];
+    const float gi = __shfl_sync(0xffffffffu, acc, u);
+    const float gf = __shfl_sync(0xffffffffu, acc, 8 + u);
+    const float gg = __shfl_sync(0xffffffffu, acc, 16 + u);
+    const float go = __shfl_sync(0xffffffffu, acc, 24 + u);
+    if (lane < 8) {
+      const long long idx = static_cast<long long>(n) * HID + u0 + u;
+      const float c0 = c_prev[idx] * m;
+      const float i_ = 1.0f / (1.0f + expf(-gi));
+      const float f_ = 1.0f / (1.0f + expf(-gf));
+      const float o_ = 1.0f / (1.0f + expf(-go));
+      const float c1 = f_ * c0 + i_ * tanhf(gg);
+      const float h1 = o_ * tanhf(c1);
+      c_next[idx] = c1;
+      h_next[idx] = h1;
+      if (h_final != nullptr) h_final[idx] = h1;
+      y[(static_cast<long long>(t) * N + n) * HID + u0 + u] = h1;
+    }
+  }
+}
+
+}  // namespace
+
+// gx [T*N, 2048] fp32 (biases included), whh bf16 [2048, 512], masks fp32 (element (t*N+n)*mask_stride),
+// hc_in / hc_out fp32 [2, N, 512] (must not alias), h_scratch fp32 [2, N, 512], y fp32 [T*N, 512].
+void lstm_forward(const float* gx, const bf16* whh, const float* masks, int mask_stride, const float* hc_in,
+                  float* hc_out, float* h_scratch, float* y, int T, int N, cudaStream_t s) {
+  RVB_CHECK(T >= 1 && N >= 1, "lstm: empty batch");
+  RVB_CHECK(hc_in != hc_out, "lstm: hidden state in/out must not alias");
+  const long long NH = static_cast<long long>(N) * HID;
+  for (int t = 0; t < T; ++t) {
+    const float* h_prev = (t == 0) ? hc_in : h_scratch + ((t - 1) & 1) * NH;
+    const float* c_prev = (t == 0) ? hc_in + NH : hc_out + NH;
+    float* h_next = h_scratch + (t & 1) * NH;
+    float* h_final = (t == T - 1) ? hc_out : nullptr;
+    lstm_step_kernel<<<HID / UNITS_PER_CTA, 256, 0, s>>>(gx, whh, masks, mask_stride, h_prev, c_prev, h_next,
+                                                         hc_out + NH, h_final, y, t, N);
+  }
+  RVB_CUDA(cudaGetLastError());
+}
+
+}  // namespace rvb

@@ -1,0 +1,147 @@
+// Internal (C++) declarations shared by the .cu files of librobovln_b200.so.
+// The public C ABI is include/robovln_b200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace rvb {
+
+using bf16 = __nv_bfloat16;
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define RVB_CHECK(cond, msg)                                                                      \
+  do {                                                                                            \
+    if (!(cond)) throw ::rvb::Error(-1, std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+  } while (0)
+
+#define RVB_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      throw ::rvb::Error(static_cast<int>(_e), std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + \
+                                                   #expr + " -> " + cudaGetErrorString(_e));      \
+  } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+// ---------------------------------------------------------------------------------------
+// Convolution-as-GEMM problem:  out[m, n] = act( sum_{tap,c} A(m,tap,c) * W[n, tap*Cin + c] + bias[n] + res[m, n] )
+//   A is an NHWC bf16 tensor [NB, H, W, Cin] (row pitch in_pitch elements per pixel),
+//   m enumerates output pixels (n, ho, wo) row-major; a plain GEMM is the case H=1, W=M, 1x1.
+// ---------------------------------------------------------------------------------------
+struct ConvGemm {
+  // input
+  const bf16* in = nullptr;
+  int NB = 1, H = 1, W = 1, Cin = 0;
+  int64_t in_pitch = 0;          // elements between consecutive pixels (>= Cin, multiple of 8)
+  // filter
+  const bf16* w = nullptr;       // [Cout, KH*KW*Cin] K-major, k = (r*KW + s)*Cin + c
+  int Cout = 0, KH = 1, KW = 1, stride = 1, pad = 0;
+  // epilogue
+  const float* bias = nullptr;   // [Cout] or null
+  const bf16* res = nullptr;     // residual [res_rows, ldr] or null; row = m % res_rows
+  int64_t ldr = 0;
+  int res_rows = 0;              // 0 -> M
+  int act = ACT_NONE;
+  void* out = nullptr;           // bf16 or f32, [M, ldc]
+  int64_t ldc = 0;
+  int out_f32 = 0;
+  // derived
+  int Ho() const { return (H + 2 * pad - KH) / stride + 1; }
+  int Wo() const { return (W + 2 * pad - KW) / stride + 1; }
+  int64_t M() const { return static_cast<int64_t>(NB) * Ho() * Wo(); }
+  bool plain() const { return KH == 1 && KW == 1 && stride == 1 && pad == 0; }
+};
+
+// Device-side parameter block of the tcgen05 kernel.
+struct GemmTcParams {
+  int M, N;
+  int num_kb;        // taps * cblocks
+  int cblocks;       // ceil(Cin / 64)
+  int KW;            // taps decompose as r = tap / KW, s = tap % KW
+  int Cin;
+  int plain;         // 1: A coords (k, m0, 0, 0)
+  int tile_rows;     // valid rows per 128-row M tile
+  int th, nb;        // output rows / images per tile (conv mode)
+  int tiles_per_img; // Ho / th when nb == 1
+  int stride, pad;
+  int m_tiles, n_tiles;
+  uint32_t a_bytes;  // bytes one A box delivers (tile_rows * 128)
+  const float* bias;
+  const bf16* res;
+  long long ldr;
+  int res_rows;
+  int act;
+  void* out;
+  long long ldc;
+  int out_f32;
+};
+
+struct GemmTcPlan {
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  GemmTcParams p;
+  int BN = 128;
+  int grid = 0;
+  bool valid = false;
+  ConvGemm desc;       // kept for the SIMT validation path
+};
+
+// gemm_tc.cu
+void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn = 0);
+void gemm_tc_launch(const GemmTcPlan& plan, cudaStream_t stream);
+int  device_sm_count();
+// gemm_simt.cu -- naive CUDA-core implementation of the same contract (validation only;
+// selected with ROBOVLN_GEMM=simt).  Still a GPU kernel: there is no CPU path anywhere.
+void gemm_simt_launch(const ConvGemm& g, cudaStream_t stream);
+bool use_simt_gemm();
+
+// elementwise.cu
+void rgb_stem_im2col(const float* rgb, bf16* out, int NB, int H, int W, int Kpitch, cudaStream_t s);
+void maxpool3x3s2(const bf16* in, bf16* out, int NB, int H, int W, int C, cudaStream_t s);
+void depth_stem_conv(const float* depth, const float* w, bf16* out, int NB, int H, int W, cudaStream_t s);
+void gn_stats(const bf16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s);
+struct GnApply {
+  const bf16* x; const float* stats; const float* gamma; const float* beta;
+  int NB, HW, C, G;
+  int relu;
+  int res_mode;                  // 0 none, 1 plain bf16 residual, 2 group-normalised residual
+  const bf16* res; const float* res_stats; const float* res_gamma; const float* res_beta;
+  bf16* out; int64_t out_pitch;  // elements per pixel in the output (>= C)
+};
+void gn_apply(const GnApply& a, cudaStream_t s);
+void rgb_pool(const bf16* feat, int NB, int H, int W, int C, bf16* tokens, int64_t tok_pitch, bf16* cellmean,
+              int64_t cm_pitch, bf16* gmean, cudaStream_t s);
+void fill_spatial_embedding(const float* emb_flat, bf16* tokens, int NB, int64_t tok_pitch, int col0, bf16* cellmean,
+                            int64_t cm_pitch, cudaStream_t s);
+void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, int R, int L, const float* word,
+                   const float* pos, const float* type0, const float* g, const float* b, bf16* out, cudaStream_t s);
+void layernorm_rows(const float* x, int M, int D, const float* g, const float* b, float eps, const float* pe, int pe_rows,
+                    bf16* out, cudaStream_t s);
+void token_mean(const bf16* x, int n_mod, int B, int L, int D, bf16* out, int64_t out_pitch, int64_t mod_stride,
+                cudaStream_t s);
+void sub_task_embed(const int64_t* ids, const float* table, int B, bf16* out, int64_t out_pitch, cudaStream_t s);
+void heads_linear(const float* y, int M, int K, const float* w, const float* b, int n_out, float* out, cudaStream_t s);
+void argmax_rows(const float* x, int M, int n, int64_t* out, cudaStream_t s);
+void sinusoid_table(float* pe, int L, int D, cudaStream_t s);
+
+// attention.cu
+void bert_self_attention(const bf16* qkv, bf16* ctx, int R, int L, int heads, cudaStream_t s);
+void vla_cross_attention(const bf16* q, const bf16* kv, bf16* ctx, int B, int L, int n_mod, int q_shared,
+                         cudaStream_t s);
+
+// lstm.cu
+void lstm_forward(const float* gx, const bf16* whh, const float* masks, int mask_stride, const float* hc_in,
+                  float* hc_out, float* h_scratch, float* y, int T, int N, cudaStream_t s);
+
+}  // namespace rvb

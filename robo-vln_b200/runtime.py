@@ -1,0 +1,305 @@
+"""Host-side runtime: owns one C engine (hcm_engine) per hi/lo module pair and device.
+
+PyTorch is used for device memory (weights, workspace, outputs) and for the current CUDA
+stream; every computation of the forward pass happens inside librobovln_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from . import weight_prep as WP
+from ._lib import HcmShape, check
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.int64: 2}
+
+# most recent runtime per device still waiting for its other half (hi <-> lo pairing)
+_open_runtimes: Dict[Tuple[str, int], "HcmRuntime"] = {}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class HcmRuntime:
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError(
+                "robovln_b200 runs on a CUDA device only (there is no CPU path); move the module with .to('cuda')")
+        self.lib = _lib.load()
+        self.device = device
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            check(self.lib.hcm_create(ctypes.byref(self.handle)), "hcm_create")
+        self.hi = None          # weakrefs to the nn.Modules
+        self.lo = None
+        self._tensors: Dict[str, torch.Tensor] = {}   # keeps prepared weights alive
+        self._dirty = True
+        self._shares = False
+        self._shape_key = None
+        self._workspace: Optional[torch.Tensor] = None
+        self._obs_sig = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.hcm_destroy(self.handle)
+        except Exception:
+            pass
+
+    # ---- pairing -------------------------------------------------------------------------
+    @staticmethod
+    def for_module(module, kind: str, device: torch.device) -> "HcmRuntime":
+        if device.type != "cuda":
+            raise RuntimeError(
+                "robovln_b200 runs on a CUDA device only (there is no CPU path); move the module with .to('cuda')")
+        key =(device.type, device.index if device.index is not None else torch.cuda.current_device())
+        rt = _open_runtimes.get(key)
+        if rt is not None and getattr(rt, kind) is None:
+            setattr(rt, kind, weakref.ref(module))
+            rt._dirty = True
+            if rt.hi is not None and rt.lo is not None:
+                _open_runtimes.pop(key, None)
+            return rt
+        rt = HcmRuntime(device)
+        setattr(rt, kind, weakref.ref(module))
+        _open_runtimes[key] = rt
+        return rt
+
+    def mark_dirty(self):
+        self._dirty = True
+
+    # ---- weights ---------------------------------------------------------------------------
+    def _modules(self):
+        hi = self.hi() if self.hi is not None else None
+        lo = self.lo() if self.lo is not None else None
+        return hi, lo
+
+    def sync_weights(self):
+        if not self._dirty:
+            return
+        hi, lo = self._modules()
+        dev = self.device
+        tensors: Dict[str, torch.Tensor] = {}
+        shares = False
+        with torch.no_grad():
+            sd_hi = hi.state_dict() if hi is not None else None
+            sd_lo = lo.state_dict() if lo is not None else None
+            if sd_hi is not None:
+                tensors.update(WP.prep_rgb_trunk(sd_hi, "hi", dev))
+                tensors.update(WP.prep_depth_trunk(sd_hi, "hi", dev))
+                tensors.update(WP.prep_bert(sd_hi, dev))
+                tensors.update(WP.prep_hi_tail(sd_hi, dev))
+            if sd_lo is not None:
+                shares = sd_hi is not None and WP.trunks_identical(sd_hi, sd_lo)
+                if not shares:
+                    tensors.update(WP.prep_rgb_trunk(sd_lo, "lo", dev))
+                    tensors.update(WP.prep_depth_trunk(sd_lo, "lo", dev))
+                tensors.update(WP.prep_lo_tail(sd_lo, dev))
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize()
+            for name, t in tensors.items():
+                shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
+                check(self.lib.hcm_set_tensor(self.handle, name.encode(), _ptr(t), _DT[t.dtype], t.dim(), shape),
+                      f"hcm_set_tensor({name})")
+            check(self.lib.hcm_finalize_weights(self.handle, int(hi is not None), int(lo is not None), int(shares)),
+                  "hcm_finalize_weights")
+        self._tensors = tensors
+        self._shares = shares
+        self._dirty = False
+        self._shape_key = None      # plans capture weight pointers
+        self._obs_sig = None
+
+    # ---- planning --------------------------------------------------------------------------
+    def ensure_plan(self, B: int, N: int, L: int, instr_rows: int, rgb_hw, depth_hw):
+        self.sync_weights()
+        key = (B, N, L, instr_rows, tuple(rgb_hw), tuple(depth_hw))
+        if key == self._shape_key:
+            return
+        shp = HcmShape(B, N, L, instr_rows, rgb_hw[0], rgb_hw[1], depth_hw[0], depth_hw[1])
+        with torch.cuda.device(self.device):
+            need = self.lib.hcm_workspace_bytes(self.handle, ctypes.byref(shp))
+            if need == 0:
+                check(-1, "hcm_workspace_bytes")
+            if self._workspace is None or self._workspace.numel() < need + 1024:
+                self._workspace = None
+                self._workspace = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            base = self._workspace.data_ptr()
+            aligned = (base + 1023) & ~1023
+            torch.cuda.synchronize()
+            check(self.lib.hcm_plan(self.handle, ctypes.byref(shp), ctypes.c_void_p(aligned), need), "hcm_plan")
+        self._shape_key = key
+        self._obs_sig = None
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _prep_obs(self, t: torch.Tensor) -> torch.Tensor:
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        if t.dtype != torch.float32:
+            t = t.float()
+        return t.contiguous()
+
+    @staticmethod
+    def _sig(rgb: torch.Tensor, depth: torch.Tensor):
+        return (rgb.data_ptr(), rgb._version, tuple(rgb.shape), depth.data_ptr(), depth._version, tuple(depth.shape))
+
+    def launches(self) -> int:
+        return int(self.lib.hcm_last_launch_count(self.handle))
+
+    # ---- forward ---------------------------------------------------------------------------
+    def forward_hi(self, rgb, depth, instruction, masks, hidden):
+        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        B = rgb.shape[0]
+        N = hidden.shape[1]
+        instr = instruction
+        if instr.dim() != 2:
+            raise ValueError("instruction must be [1 or B, L]")
+        if instr.shape[0] not in (1, B):
+            raise ValueError(f"instruction has {instr.shape[0]} rows; expected 1 or {B}")
+        instr = instr.to(self.device)
+        i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
+        i_i64 = instr.contiguous() if instr.dtype == torch.int64 else None
+        masks = masks.to(self.device, torch.float32)
+        hidden = hidden.to(self.device, torch.float32).contiguous()
+        self.ensure_plan(B, N, instr.shape[1], instr.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        logits = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+        hc_out = torch.empty_like(hidden)
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_forward_hi(self.handle, _ptr(rgb), _ptr(depth), _ptr(i_f32), _ptr(i_i64), _ptr(masks),
+                                          masks.stride(0), _ptr(hidden), _ptr(logits), _ptr(hc_out), self._stream()),
+                  "hcm_forward_hi")
+        self._obs_sig = self._sig(rgb, depth)
+        self._keep = (rgb, depth, i_f32, i_i64, masks, hidden)   # alive until the stream consumed them
+        return logits, hc_out
+
+    def forward_lo(self, rgb, depth, masks, hidden, sub_goal):
+        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        B = rgb.shape[0]
+        N = hidden.shape[1]
+        masks = masks.to(self.device, torch.float32)
+        hidden = hidden.to(self.device, torch.float32).contiguous()
+        sub_goal = sub_goal.to(self.device, torch.int64).contiguous().view(-1)
+        self.sync_weights()
+        reuse = bool(self._shares and self._shape_key is not None and self._shape_key[0] == B
+                     and self._shape_key[1] == N and self._obs_sig == self._sig(rgb, depth))
+        if not reuse:
+            hi, _ = self._modules()
+            if self._shape_key is not None and self._shape_key[0] == B and self._shape_key[1] == N \
+                    and self._shape_key[4] == tuple(rgb.shape[1:3]):
+                pass  # the current plan already fits (instruction length is irrelevant for lo)
+            else:
+                self.ensure_plan(B, N, 8 if hi is not None else 1, 1, rgb.shape[1:3], depth.shape[1:3])
+        act = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        stop = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        hc_out = torch.empty_like(hidden)
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_forward_lo(self.handle, _ptr(rgb), _ptr(depth), _ptr(masks), masks.stride(0),
+                                          _ptr(sub_goal), _ptr(hidden), _ptr(act), _ptr(stop), _ptr(hc_out),
+                                          int(reuse), self._stream()), "hcm_forward_lo")
+        self._keep_lo = (rgb, depth, masks, hidden, sub_goal)
+        return act, stop, hc_out
+
+    def forward_policy(self, rgb, depth, instruction, masks, hidden_hi, hidden_lo):
+        """hi -> argmax -> lo in one engine call (rollout step, hierarchical_trainer.py:1095-1101)."""
+        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        B, N = rgb.shape[0], hidden_hi.shape[1]
+        instr = instruction.to(self.device)
+        i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
+        i_i64 = instr.contiguous() if instr.dtype == torch.int64 else None
+        masks = masks.to(self.device, torch.float32)
+        hidden_hi = hidden_hi.to(self.device, torch.float32).contiguous()
+        hidden_lo = hidden_lo.to(self.device, torch.float32).contiguous()
+        self.ensure_plan(B, N, instr.shape[1], instr.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        logits = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+        act = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        stop = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        sub = torch.empty((B,), dtype=torch.int64, device=self.device)
+        hc_hi = torch.empty_like(hidden_hi)
+        hc_lo = torch.empty_like(hidden_lo)
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_forward_policy(self.handle, _ptr(rgb), _ptr(depth), _ptr(i_f32), _ptr(i_i64), _ptr(masks),
+                                              masks.stride(0), _ptr(hidden_hi), _ptr(hidden_lo), _ptr(logits), _ptr(act),
+                                              _ptr(stop), _ptr(hc_hi), _ptr(hc_lo), _ptr(sub), self._stream()),
+                  "hcm_forward_policy")
+        self._keep = (rgb, depth, i_f32, i_i64, masks, hidden_hi, hidden_lo)
+        return logits, act, stop, hc_hi, hc_lo, sub
+
+    def profile_policy(self, rgb, depth, instruction, masks, hidden_hi, hidden_lo):
+        """Per-launch device times of one policy step (single stream, CUDA events between
+        launches): list of {"name", "ms", "flops"}."""
+        import json
+
+        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        B, N = rgb.shape[0], hidden_hi.shape[1]
+        instr = instruction.to(self.device)
+        i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
+        i_i64 = instr.contiguous() if instr.dtype == torch.int64 else None
+        masks = masks.to(self.device, torch.float32)
+        hidden_hi = hidden_hi.to(self.device, torch.float32).contiguous()
+        hidden_lo = hidden_lo.to(self.device, torch.float32).contiguous()
+        self.ensure_plan(B, N, instr.shape[1], instr.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        logits = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+        act = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        stop = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        hc_hi = torch.empty_like(hidden_hi)
+        hc_lo = torch.empty_like(hidden_lo)
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_profile_policy(self.handle, _ptr(rgb), _ptr(depth), _ptr(i_f32), _ptr(i_i64), _ptr(masks),
+                                              masks.stride(0), _ptr(hidden_hi), _ptr(hidden_lo), _ptr(logits), _ptr(act),
+                                              _ptr(stop), _ptr(hc_hi), _ptr(hc_lo), buf, cap, self._stream()),
+                  "hcm_profile_policy")
+        return json.loads(buf.value.decode())
+
+    def forward_policy_host(self, rgb, depth, instruction, masks, hidden_hi, hidden_lo, out=None):
+        """Host-buffer entry: all arguments are CPU float32 tensors (pinned for speed); H2D copies,
+        the forward and the D2H copies of the results are inside this call."""
+        B, N = rgb.shape[0], hidden_hi.shape[1]
+        for t in (rgb, depth, instruction, masks, hidden_hi, hidden_lo):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("forward_policy_host expects contiguous float32 CPU tensors")
+        if masks.dim() != 2 or masks.shape[1] != 2:
+            raise ValueError("masks must be [B,2]")
+        self.ensure_plan(B, N, instruction.shape[1], instruction.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        if out is None:
+            out = {
+                "logits": torch.empty((B, 4), dtype=torch.float32).pin_memory(),
+                "actions": torch.empty((B, 2), dtype=torch.float32).pin_memory(),
+                "stop": torch.empty((B, 1), dtype=torch.float32).pin_memory(),
+                "hidden_hi": torch.empty((2, N, 512), dtype=torch.float32).pin_memory(),
+                "hidden_lo": torch.empty((2, N, 512), dtype=torch.float32).pin_memory(),
+            }
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_forward_policy_host(self.handle, _ptr(rgb), _ptr(depth), _ptr(instruction), _ptr(masks),
+                                                   _ptr(hidden_hi), _ptr(hidden_lo), _ptr(out["logits"]),
+                                                   _ptr(out["actions"]), _ptr(out["stop"]), _ptr(out["hidden_hi"]),
+                                                   _ptr(out["hidden_lo"]), self._stream()), "hcm_forward_policy_host")
+        return out
+
+    def get_buffer(self, name: str) -> torch.Tensor:
+        """Copy of an internal stage buffer (parity tests)."""
+        ptr = ctypes.c_void_p()
+        dt = ctypes.c_int()
+        nd = ctypes.c_int()
+        shape = (ctypes.c_int64 * 8)()
+        check(self.lib.hcm_get_buffer(self.handle, name.encode(), ctypes.byref(ptr), ctypes.byref(dt), ctypes.byref(nd),
+                                      shape), f"hcm_get_buffer({name})")
+        shp = [int(shape[i]) for i in range(nd.value)]
+        dtype = {0: torch.float32, 1: torch.bfloat16, 2: torch.int64}[dt.value]
+        numel = 1
+        for s in shp:
+            numel *= s
+        out = torch.empty(shp, dtype=dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_copy_buffer(self.handle, name.encode(), _ptr(out), numel * out.element_size(),
+                                           self._stream()), f"hcm_copy_buffer({name})")
+            torch.cuda.synchronize()
+        return out

@@ -1,0 +1,35 @@
+"""Drop-in for ``robo_vln_baselines.models.seq2seq_lowlevel.Seq2Seq_LowLevel``
+(robo_vln_baselines/models/seq2seq_lowlevel.py:21-162): (RGB, depth, sub-goal id) ->
+(linear/angular velocity [B,2], stop logit [B,1], hidden state).  One call into the sm_100a
+engine (``hcm_forward_lo``); when lo's frozen trunks are bit-identical to the paired hi
+model's and the observations are the tensors hi just saw, the trunk features are reused.
+"""
+from __future__ import annotations
+
+from .modules import HcmModuleBase, build_param_tree
+from .param_spec import lo_spec
+from .seq2seq_highlevel_cma import _check_config
+
+
+class Seq2Seq_LowLevel(HcmModuleBase):
+    _kind = "lo"
+
+    def __init__(self, observation_space=None, num_actions: int = 2, num_sub_tasks: int = 4, model_config=None,
+                 batch_size: int = 1):
+        super().__init__()
+        _check_config(model_config)
+        if num_actions != 2 or num_sub_tasks != 4:
+            raise NotImplementedError("the HCM low-level head is (v, omega) + stop over 4 sub-tasks")
+        self.model_config = model_config
+        self.batch_size = batch_size
+        build_param_tree(self, lo_spec(num_actions, num_sub_tasks))
+
+    def forward(self, batch):
+        r"""(observations, rnn_hidden_states, prev_actions, masks, discrete_actions) = batch
+        -> (actions [B,2], stop_logit [B,1], rnn_hidden_states [2,N,512])"""
+        observations, rnn_hidden_states, prev_actions, masks, discrete_actions = batch
+        del batch
+        if "rgb_features" in observations or "depth_features" in observations:
+            raise NotImplementedError("pre-computed rgb_features/depth_features are not supported yet")
+        rt = self.runtime()
+        return rt.forward_lo(observations["rgb"], observations["depth"], masks, rnn_hidden_states, discrete_actions)

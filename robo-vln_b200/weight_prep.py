@@ -1,0 +1,207 @@
+"""state_dict (reference key names) -> kernel-layout device tensors for the C engine.
+
+Everything here is one-time plumbing in PyTorch: BatchNorm folding, OIHW -> [O, KH*KW*I]
+(K-major, tap-major / channel-minor, the order gemm_tc.cu walks K in), bf16 casts, Q/K/V
+stacking, and the two column permutations that let the kernels consume NHWC "cell-major"
+features where the reference flattens NCHW "channel-major" ones
+(seq2seq_highlevel_cma.py:92-100 depth_linear; resnet_encoders.py:58-62 visual_fc).
+
+Engine tensor names (``ns`` is "hi" or "lo"):
+  {ns}.rgb.stem.{w,b}                     bf16 [64,160] (147 real K, zero padded), f32 [64]
+  {ns}.rgb.l{1-4}.{blk}.{c1,c2,c3,ds}.{w,b}
+  {ns}.depth.stem.w f32 [32,49]; {ns}.depth.stem.gn.{w,b}
+  {ns}.depth.l{1-4}.{blk}.{c1,c2,c3,ds}.w ; .gn{1,2,3}.{w,b} ; .dsgn.{w,b}
+  {ns}.depth.comp.w ; {ns}.depth.comp.gn.{w,b}
+  hi.bert.{word,pos,type0,emb_ln.w,emb_ln.b} ; hi.bert.{i}.{qkv,ao,ff1,ff2}.{w,b} ; .ln{1,2}.{w,b}
+  hi.{rgb_emb,depth_emb} ; hi.{rgb_kv,depth_kv,rgb_linear,depth_linear}.{w,b}
+  hi.vla.{ins_fc,vis_fc,fc_q,fc_kv,fc_o,fc1,fc2}.{w,b} ; hi.vla.ln{0,1,2}.{w,b}
+  hi.lstm.{wih,whh,b} ; hi.linear.{w,b}
+  lo.{depth_fc,rgb_fc}.{w,b} ; lo.sub_emb ; lo.lstm.{wih,whh,b} ; lo.linear.{w,b} ; lo.stop.{w,b}
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+_STAGES = ((3, 1), (4, 2), (6, 2), (3, 2))
+
+
+def _bf(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _conv_kmajor(w: torch.Tensor) -> torch.Tensor:
+    """OIHW -> [O, KH*KW*I] with k = (r*KW + s)*I + c."""
+    o, i, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(o, kh * kw * i)
+
+
+def fold_bn(conv_w: torch.Tensor, g, b, mean, var, eps: float = 1e-5):
+    """Eval-mode BatchNorm folded into the preceding bias-free conv."""
+    scale = g.float() / torch.sqrt(var.float() + eps)
+    return conv_w.float() * scale.view(-1, 1, 1, 1), b.float() - mean.float() * scale
+
+
+def prep_rgb_trunk(sd: Dict[str, torch.Tensor], ns: str, dev) -> Dict[str, torch.Tensor]:
+    p = "rgb_encoder.cnn."
+    out = {}
+
+    def bn(prefix):
+        return (sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"], sd[prefix + ".running_var"])
+
+    w, b = fold_bn(sd[p + "conv1.weight"], *bn(p + "bn1"))
+    wk = torch.zeros((64, 160), dtype=torch.float32, device=w.device)
+    wk[:, :147] = _conv_kmajor(w)
+    out[f"{ns}.rgb.stem.w"] = _bf(wk, dev)
+    out[f"{ns}.rgb.stem.b"] = _f32(b, dev)
+    for li, (nb, _s) in enumerate(_STAGES):
+        for blk in range(nb):
+            q = f"{p}layer{li + 1}.{blk}."
+            e = f"{ns}.rgb.l{li + 1}.{blk}."
+            for ci in (1, 2, 3):
+                w, b = fold_bn(sd[q + f"conv{ci}.weight"], *bn(q + f"bn{ci}"))
+                out[e + f"c{ci}.w"] = _bf(_conv_kmajor(w), dev)
+                out[e + f"c{ci}.b"] = _f32(b, dev)
+            if blk == 0:
+                w, b = fold_bn(sd[q + "downsample.0.weight"], *bn(q + "downsample.1"))
+                out[e + "ds.w"] = _bf(_conv_kmajor(w), dev)
+                out[e + "ds.b"] = _f32(b, dev)
+    return out
+
+
+def prep_depth_trunk(sd: Dict[str, torch.Tensor], ns: str, dev) -> Dict[str, torch.Tensor]:
+    p = "depth_encoder.visual_encoder."
+    b = p + "backbone."
+    out = {}
+    out[f"{ns}.depth.stem.w"] = _f32(sd[b + "conv1.0.weight"].reshape(32, 49), dev)
+    out[f"{ns}.depth.stem.gn.w"] = _f32(sd[b + "conv1.1.weight"], dev)
+    out[f"{ns}.depth.stem.gn.b"] = _f32(sd[b + "conv1.1.bias"], dev)
+    for li, (nb, _s) in enumerate(_STAGES):
+        for blk in range(nb):
+            q = f"{b}layer{li + 1}.{blk}."
+            e = f"{ns}.depth.l{li + 1}.{blk}."
+            for ci, (cw, gn) in enumerate(((0, 1), (3, 4), (6, 7)), start=1):
+                out[e + f"c{ci}.w"] = _bf(_conv_kmajor(sd[q + f"convs.{cw}.weight"]), dev)
+                out[e + f"gn{ci}.w"] = _f32(sd[q + f"convs.{gn}.weight"], dev)
+                out[e + f"gn{ci}.b"] = _f32(sd[q + f"convs.{gn}.bias"], dev)
+            if blk == 0:
+                out[e + "ds.w"] = _bf(_conv_kmajor(sd[q + "downsample.0.weight"]), dev)
+                out[e + "dsgn.w"] = _f32(sd[q + "downsample.1.weight"], dev)
+                out[e + "dsgn.b"] = _f32(sd[q + "downsample.1.bias"], dev)
+    out[f"{ns}.depth.comp.w"] = _bf(_conv_kmajor(sd[p + "compression.0.weight"]), dev)
+    out[f"{ns}.depth.comp.gn.w"] = _f32(sd[p + "compression.1.weight"], dev)
+    out[f"{ns}.depth.comp.gn.b"] = _f32(sd[p + "compression.1.bias"], dev)
+    return out
+
+
+def prep_bert(sd: Dict[str, torch.Tensor], dev) -> Dict[str, torch.Tensor]:
+    p = "embedding_layer."
+    e = p + "embeddings."
+    out = {
+        "hi.bert.word": _f32(sd[e + "word_embeddings.weight"], dev),
+        "hi.bert.pos": _f32(sd[e + "position_embeddings.weight"], dev),
+        "hi.bert.type0": _f32(sd[e + "token_type_embeddings.weight"][0], dev),
+        "hi.bert.emb_ln.w": _f32(sd[e + "LayerNorm.weight"], dev),
+        "hi.bert.emb_ln.b": _f32(sd[e + "LayerNorm.bias"], dev),
+    }
+    for i in range(12):
+        q = f"{p}encoder.layer.{i}."
+        a = q + "attention.self."
+        n = f"hi.bert.{i}."
+        out[n + "qkv.w"] = _bf(torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], 0), dev)
+        out[n + "qkv.b"] = _f32(torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], 0), dev)
+        out[n + "ao.w"] = _bf(sd[q + "attention.output.dense.weight"], dev)
+        out[n + "ao.b"] = _f32(sd[q + "attention.output.dense.bias"], dev)
+        out[n + "ln1.w"] = _f32(sd[q + "attention.output.LayerNorm.weight"], dev)
+        out[n + "ln1.b"] = _f32(sd[q + "attention.output.LayerNorm.bias"], dev)
+        out[n + "ff1.w"] = _bf(sd[q + "intermediate.dense.weight"], dev)
+        out[n + "ff1.b"] = _f32(sd[q + "intermediate.dense.bias"], dev)
+        out[n + "ff2.w"] = _bf(sd[q + "output.dense.weight"], dev)
+        out[n + "ff2.b"] = _f32(sd[q + "output.dense.bias"], dev)
+        out[n + "ln2.w"] = _f32(sd[q + "output.LayerNorm.weight"], dev)
+        out[n + "ln2.b"] = _f32(sd[q + "output.LayerNorm.bias"], dev)
+    return out
+
+
+def prep_hi_tail(sd: Dict[str, torch.Tensor], dev) -> Dict[str, torch.Tensor]:
+    out = {
+        "hi.rgb_emb": _f32(sd["rgb_encoder.spatial_embeddings.weight"], dev),
+        "hi.depth_emb": _f32(sd["depth_encoder.spatial_embeddings.weight"], dev),
+        "hi.rgb_kv.w": _bf(sd["rgb_kv.weight"][:, :, 0], dev),
+        "hi.rgb_kv.b": _f32(sd["rgb_kv.bias"], dev),
+        "hi.depth_kv.w": _bf(sd["depth_kv.weight"][:, :, 0], dev),
+        "hi.depth_kv.b": _f32(sd["depth_kv.bias"], dev),
+        "hi.rgb_linear.w": _bf(sd["rgb_linear.2.weight"], dev),
+        "hi.rgb_linear.b": _f32(sd["rgb_linear.2.bias"], dev),
+        # reference flattens [B,192,16] channel-major (index c*16+cell); tokens are [B,16,192]
+        "hi.depth_linear.w": _bf(sd["depth_linear.1.weight"].reshape(128, 192, 16).permute(0, 2, 1).reshape(128, 3072), dev),
+        "hi.depth_linear.b": _f32(sd["depth_linear.1.bias"], dev),
+    }
+    v = "image_cm_encoder."
+    a = v + "layers.0.enc_att.attention."
+    f = v + "layers.0.pwff."
+    pairs = {
+        "ins_fc": v + "ins_fc", "vis_fc": v + "vis_fc", "fc_q": a + "fc_q", "fc_o": a + "fc_o",
+        "fc1": f + "fc1", "fc2": f + "fc2",
+    }
+    for n, k in pairs.items():
+        out[f"hi.vla.{n}.w"] = _bf(sd[k + ".weight"], dev)
+        out[f"hi.vla.{n}.b"] = _f32(sd[k + ".bias"], dev)
+    out["hi.vla.fc_kv.w"] = _bf(torch.cat([sd[a + "fc_k.weight"], sd[a + "fc_v.weight"]], 0), dev)
+    out["hi.vla.fc_kv.b"] = _f32(torch.cat([sd[a + "fc_k.bias"], sd[a + "fc_v.bias"]], 0), dev)
+    for n, k in (("ln0", v + "layer_norm"), ("ln1", v + "layers.0.enc_att.layer_norm"), ("ln2", f + "layer_norm")):
+        out[f"hi.vla.{n}.w"] = _f32(sd[k + ".weight"], dev)
+        out[f"hi.vla.{n}.b"] = _f32(sd[k + ".bias"], dev)
+    s = "state_encoder.rnn."
+    out["hi.lstm.wih"] = _bf(sd[s + "weight_ih_l0"], dev)
+    out["hi.lstm.whh"] = _bf(sd[s + "weight_hh_l0"], dev)
+    out["hi.lstm.b"] = _f32(sd[s + "bias_ih_l0"].float() + sd[s + "bias_hh_l0"].float(), dev)
+    out["hi.linear.w"] = _f32(sd["linear.weight"], dev)
+    out["hi.linear.b"] = _f32(sd["linear.bias"], dev)
+    return out
+
+
+def prep_lo_tail(sd: Dict[str, torch.Tensor], dev) -> Dict[str, torch.Tensor]:
+    # visual_fc consumes Flatten([B,128,4,4]) (index c*16+cell); the engine feeds the
+    # [B,16,192] depth tokens (128 features + 64 spatial-embedding columns) -> permute to
+    # cell-major and put zeros under the embedding columns.
+    w = sd["depth_encoder.visual_fc.1.weight"].float().reshape(128, 128, 16).permute(0, 2, 1)   # [o, cell, c]
+    wp = torch.zeros((128, 16, 192), dtype=torch.float32, device=w.device)
+    wp[:, :, :128] = w
+    out = {
+        "lo.depth_fc.w": _bf(wp.reshape(128, 3072), dev),
+        "lo.depth_fc.b": _f32(sd["depth_encoder.visual_fc.1.bias"], dev),
+        "lo.rgb_fc.w": _bf(sd["rgb_encoder.fc.weight"], dev),
+        "lo.rgb_fc.b": _f32(sd["rgb_encoder.fc.bias"], dev),
+        "lo.sub_emb": _f32(sd["sub_task_embedding.weight"], dev),
+    }
+    s = "state_encoder.rnn."
+    out["lo.lstm.wih"] = _bf(sd[s + "weight_ih_l0"], dev)
+    out["lo.lstm.whh"] = _bf(sd[s + "weight_hh_l0"], dev)
+    out["lo.lstm.b"] = _f32(sd[s + "bias_ih_l0"].float() + sd[s + "bias_hh_l0"].float(), dev)
+    out["lo.linear.w"] = _f32(sd["linear.weight"], dev)
+    out["lo.linear.b"] = _f32(sd["linear.bias"], dev)
+    out["lo.stop.w"] = _f32(sd["stop_linear.weight"], dev)
+    out["lo.stop.b"] = _f32(sd["stop_linear.bias"], dev)
+    return out
+
+
+TRUNK_PREFIXES = ("rgb_encoder.cnn.", "depth_encoder.visual_encoder.")
+
+
+def trunks_identical(sd_a: Dict[str, torch.Tensor], sd_b: Dict[str, torch.Tensor]) -> bool:
+    """True iff every frozen-trunk tensor of the two models is bit-identical (dedup legality,
+    SURVEY.md 7.2).  ``cnn.fc`` (lo only, unused) is ignored."""
+    keys_a = [k for k in sd_a if k.startswith(TRUNK_PREFIXES) and not k.startswith("rgb_encoder.cnn.fc.")]
+    for k in keys_a:
+        if k not in sd_b:
+            return False
+        a, b = sd_a[k], sd_b[k]
+        if a.shape != b.shape or not torch.equal(a.to(b.device), b):
+            return False
+    return True

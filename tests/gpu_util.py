@@ -1,0 +1,66 @@
+"""Helpers for the -m gpu tests: ctypes calls into librobovln_b200.so with torch tensors."""
+import ctypes
+
+import torch
+
+import robovln_b200  # noqa: F401  (alias package; makes robovln_b200._lib importable)
+from robovln_b200 import _lib
+
+
+def lib():
+    return _lib.load()
+
+
+def P(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def conv_gemm(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows=0, act=0, out_f32=False,
+              force_bn=0, impl=0, ldc=None, out=None):
+    """x: [NB,H,W,Cin] bf16 (contiguous), w: [Cout, KH*KW*Cin] bf16 -> out [M, Cout]."""
+    NB, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    M = NB * Ho * Wo
+    if ldc is None:
+        ldc = Cout
+    if out is None:
+        out = torch.zeros((M, ldc), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    rc = lib().rvb_conv_gemm(P(x), NB, H, W, Cin, Cin, P(w), Cout, KH, KW, stride, pad, P(bias), P(res),
+                             0 if res is None else res.shape[-1], res_rows, act, P(out), ldc, int(out_f32), force_bn,
+                             impl, stream())
+    _lib.check(rc, "rvb_conv_gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+def conv_ref(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows=0, act=0):
+    """fp32 torch reference on the same bf16-rounded operands."""
+    NB, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    w4 = w.float().view(Cout, KH, KW, Cin).permute(0, 3, 1, 2).contiguous()
+    y = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w4, None, stride=stride, padding=pad)
+    y = y.permute(0, 2, 3, 1).reshape(-1, Cout)
+    if bias is not None:
+        y = y + bias.float()
+    if res is not None:
+        r = res.float().view(-1, Cout)
+        if res_rows:
+            idx = torch.arange(y.shape[0], device=y.device) % res_rows
+            r = r[idx]
+        y = y + r
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    return y
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))

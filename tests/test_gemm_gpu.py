@@ -1,0 +1,132 @@
+"""tcgen05 implicit-GEMM kernel (csrc/gemm_tc.cu) against an fp32 torch reference evaluated on
+the same bf16-rounded operands, and against the CUDA-core validation kernel.
+
+Tolerance: outputs are bf16 (8 mantissa bits) -> 1e-2 of the tensor's max magnitude; fp32
+outputs 2e-3 (accumulation-order differences over K <= 9216 only)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2
+F32_TOL = 2e-3
+
+
+def _mk(shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype).contiguous()
+
+
+# (name, NB, H, W, Cin, Cout, K, stride, pad)
+CONV_CASES = [
+    ("plain_tail_m300", 1, 1, 300, 64, 64, 1, 1, 0),
+    ("plain_k32_n32_depth_l1", 2, 32, 32, 32, 32, 1, 1, 0),
+    ("plain_layer1_c64_256", 2, 64, 64, 64, 256, 1, 1, 0),
+    ("plain_many_tiles", 8, 64, 64, 64, 256, 1, 1, 0),           # 256 x 1..2 tiles > 148 CTAs: persistent loop
+    ("plain_k416_tail", 1, 1, 64, 416, 2048, 1, 1, 0),           # LSTM-lo input projection (K tail via OOB fill)
+    ("plain_k2112", 1, 1, 1024, 2112, 256, 1, 1, 0),             # rgb_kv
+    ("plain_bert_qkv", 1, 1, 1600, 768, 2304, 1, 1, 0),
+    ("plain_bert_ff2", 1, 1, 1600, 3072, 768, 1, 1, 0),
+    ("c3x3_64x64_c64", 2, 64, 64, 64, 64, 3, 1, 1),              # RGB layer1 conv2: th=2
+    ("c3x3_32x32_c128", 3, 32, 32, 128, 128, 3, 1, 1),           # th=4
+    ("c3x3_16x16_c256", 3, 16, 16, 256, 256, 3, 1, 1),           # th=8
+    ("c3x3_8x8_c512", 5, 8, 8, 512, 512, 3, 1, 1),               # two images per tile, 72 k-blocks, odd NB
+    ("c3x3_4x4_c1024_comp", 3, 4, 4, 1024, 128, 3, 1, 1),        # eight images per tile, NB < nb
+    ("c3x3_32x32_c32_depth", 2, 32, 32, 32, 32, 3, 1, 1),        # Cin=32: half of every A box is OOB
+    ("c3x3_s2_64_to_32", 2, 64, 64, 128, 128, 3, 2, 1),          # elementStrides = 2
+    ("c3x3_s2_16_to_8", 3, 16, 16, 512, 512, 3, 2, 1),
+    ("c3x3_s2_8_to_4", 3, 8, 8, 256, 256, 3, 2, 1),
+    ("c1x1_s2_ds_64_to_32", 2, 64, 64, 256, 512, 1, 2, 0),       # downsample branch
+    ("c1x1_s2_ds_8_to_4", 3, 8, 8, 512, 1024, 1, 2, 0),
+    ("c3x3_56x56_c64_rgb224", 2, 56, 56, 64, 64, 3, 1, 1),       # 224x224 geometry: 112-row tiles
+    ("c3x3_s2_56_to_28", 2, 56, 56, 128, 128, 3, 2, 1),
+    ("c3x3_14x14_c256", 3, 14, 14, 256, 256, 3, 1, 1),           # th=7 -> 98-row tiles
+    ("c3x3_7x7_c512", 3, 7, 7, 512, 512, 3, 1, 1),               # two 49-pixel images per tile
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm_matches_torch(case):
+    from tests.gpu_util import conv_gemm, conv_ref, rel_err
+
+    name, NB, H, W, Cin, Cout, K, stride, pad = case
+    x = _mk((NB, H, W, Cin), 1.0, 1)
+    w = _mk((Cout, K * K * Cin), (2.0 / (K * K * Cin)) ** 0.5, 2)
+    bias = _mk((Cout,), 0.5, 3, torch.float32)
+    ref = conv_ref(x, w, KH=K, KW=K, stride=stride, pad=pad, bias=bias, act=1)
+    out = conv_gemm(x, w, KH=K, KW=K, stride=stride, pad=pad, bias=bias, act=1)
+    assert out.shape == ref.shape
+    e = rel_err(out, ref)
+    assert e < BF16_TOL, f"{name}: tcgen05 vs torch rel err {e:.3e}"
+    simt = conv_gemm(x, w, KH=K, KW=K, stride=stride, pad=pad, bias=bias, act=1, impl=1)
+    e2 = rel_err(simt, ref)
+    assert e2 < BF16_TOL, f"{name}: simt vs torch rel err {e2:.3e}"
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_forced_tile_widths(bn):
+    from tests.gpu_util import conv_gemm, conv_ref, rel_err
+
+    x = _mk((1, 1, 1000, 512), 1.0, 4)
+    w = _mk((768, 512), 512 ** -0.5, 5)
+    ref = conv_ref(x, w)
+    out = conv_gemm(x, w, force_bn=bn, out_f32=True)
+    e = rel_err(out, ref)
+    assert e < F32_TOL, f"BN={bn}: rel err {e:.3e}"
+
+
+def test_epilogue_variants():
+    from tests.gpu_util import conv_gemm, conv_ref, rel_err
+
+    M, K, N = 640, 256, 256
+    x = _mk((1, 1, M, K), 1.0, 6)
+    w = _mk((N, K), K ** -0.5, 7)
+    bias = _mk((N,), 0.3, 8, torch.float32)
+    res = _mk((M, N), 1.0, 9)
+    # bias + residual, fp32 out (pre-LayerNorm tensors)
+    ref = conv_ref(x, w, bias=bias, res=res)
+    out = conv_gemm(x, w, bias=bias, res=res, out_f32=True)
+    assert rel_err(out, ref) < F32_TOL
+    # residual broadcast over row blocks (cross-modal fc_o: res row = m % res_rows)
+    res2 = _mk((160, N), 1.0, 10)
+    ref = conv_ref(x, w, bias=bias, res=res2, res_rows=160)
+    out = conv_gemm(x, w, bias=bias, res=res2, res_rows=160, out_f32=True)
+    assert rel_err(out, ref) < F32_TOL
+    # GELU(erf), bf16 out
+    ref = conv_ref(x, w, bias=bias, act=2)
+    out = conv_gemm(x, w, bias=bias, act=2)
+    assert rel_err(out, ref) < BF16_TOL
+    # no bias, no activation (depth convs feeding GroupNorm)
+    ref = conv_ref(x, w)
+    out = conv_gemm(x, w)
+    assert rel_err(out, ref) < BF16_TOL
+
+
+def test_output_column_slice_and_pitch():
+    """GEMM epilogues write straight into column slices of the LSTM input (ldc > N)."""
+    from tests.gpu_util import conv_gemm, conv_ref, rel_err
+
+    M, K, N, LDC = 64, 2112, 256, 896
+    x = _mk((1, 1, M, K), 1.0, 11)
+    w = _mk((N, K), K ** -0.5, 12)
+    buf = torch.full((M, LDC), 7.0, dtype=torch.bfloat16, device="cuda")
+    view = buf[:, 384:]
+    out = conv_gemm(x, w, act=1, ldc=LDC, out=view)
+    ref = conv_ref(x, w, act=1)
+    assert rel_err(buf[:, 384:640], ref) < BF16_TOL
+    assert torch.all(buf[:, :384] == 7.0) and torch.all(buf[:, 640:] == 7.0)
+
+
+def test_linearity_full_size():
+    """Size-independent property at BASELINE shapes (RGB layer1, batch 64): conv(a x) = a conv(x)
+    and agreement of two tile widths, without needing a CPU reference at this size."""
+    from tests.gpu_util import conv_gemm, rel_err
+
+    x = _mk((64, 64, 64, 64), 1.0, 13)
+    w = _mk((64, 9 * 64), (2.0 / 576) ** 0.5, 14)
+    y1 = conv_gemm(x, w, KH=3, KW=3, pad=1, out_f32=True)
+    y2 = conv_gemm((x.float() * 2).to(torch.bfloat16), w, KH=3, KW=3, pad=1, out_f32=True)
+    assert rel_err(y2, 2 * y1) < 1e-5          # scaling by 2 is exact in bf16/fp32
+    y3 = conv_gemm(x, w, KH=3, KW=3, pad=1, out_f32=True, force_bn=128)
+    assert rel_err(y3, y1) < 1e-5
