@@ -28,7 +28,13 @@ extern "C" {
 
 typedef struct hcm_engine hcm_engine;
 
-enum { HCM_F32 = 0, HCM_BF16 = 1, HCM_I64 = 2 };
+enum { HCM_F32 = 0, HCM_BF16 = 1, HCM_I64 = 2, HCM_F16 = 3 };
+
+/* The library is compiled for ONE 16-bit storage / tensor-core operand type:
+ * librobovln_b200.so = IEEE fp16 (default), librobovln_b200_bf16.so = bfloat16.  Every
+ * `*_h16` / 16-bit tensor argument below must have the type hcm_dtype() reports
+ * (HCM_F16 or HCM_BF16); accumulation, statistics, softmax and the LSTM state are fp32. */
+int hcm_dtype(void);
 
 /* Shape of one forward call. */
 typedef struct hcm_shape {

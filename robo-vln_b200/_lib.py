@@ -24,6 +24,7 @@ class HcmShape(ctypes.Structure):
 SYMBOLS = {
     "hcm_last_error": (c_char_p, []),
     "hcm_version": (c_char_p, []),
+    "hcm_dtype": (c_int, []),
     "hcm_create": (c_int, [POINTER(c_void_p)]),
     "hcm_destroy": (None, [c_void_p]),
     "hcm_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),
@@ -59,25 +60,41 @@ SYMBOLS = {
     "rvb_depth_stem": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
-_lib = None
+_libs = {}
+LIB_FILES = {"fp16": "librobovln_b200.so", "bf16": "librobovln_b200_bf16.so"}
+DTYPE_CODE = {"fp16": 3, "bf16": 1}
 
 
-def load(build_if_missing: bool = True) -> ctypes.CDLL:
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def default_dtype() -> str:
+    """16-bit operand type of the engine: fp16 unless ROBOVLN_DTYPE=bf16 (csrc/h16.h)."""
+    d = os.environ.get("ROBOVLN_DTYPE", "fp16").lower()
+    if d in ("fp16", "f16", "half", "float16"):
+        return "fp16"
+    if d in ("bf16", "bfloat16"):
+        return "bf16"
+    raise ValueError(f"ROBOVLN_DTYPE={d!r}: expected fp16 or bf16")
+
+
+def load(build_if_missing: bool = True, dtype: str = None) -> ctypes.CDLL:
+    dtype = dtype or default_dtype()
+    if dtype in _libs:
+        return _libs[dtype]
+    path = os.path.join(HERE, LIB_FILES[dtype])
+    if not os.path.exists(path):
         if not build_if_missing:
-            raise ImportError(f"{LIB_PATH} is missing; run `python robo-vln_b200/build.py`")
+            raise ImportError(f"{path} is missing; run `python robo-vln_b200/build.py`")
         from .build import build  # needs nvcc; raises if it is absent
 
         build()
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a header symbol
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if lib.hcm_dtype() != DTYPE_CODE[dtype]:
+        raise ImportError(f"{path} was built for another 16-bit type")
+    lib._rvb_dtype = dtype
+    _libs[dtype] = lib
     return lib
 
 
@@ -85,7 +102,9 @@ class HcmError(RuntimeError):
     pass
 
 
-def check(rc: int, what: str = "") -> None:
+def check(rc: int, what: str = "", lib=None) -> None:
     if rc != 0:
-        msg = load().hcm_last_error()
-        raise HcmError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+        # every successful ABI call clears its library's message, so only the failing one is set
+        libs = [lib] if lib is not None else (list(_libs.values()) or [load()])
+        msg = " | ".join(m.decode() for m in (l.hcm_last_error() for l in libs) if m)
+        raise HcmError(f"{what} failed (code {rc}): {msg}")

@@ -1,9 +1,12 @@
-"""In-tree build of librobovln_b200.so (sm_100a only) with nvcc.
+"""In-tree build of the sm_100a shared libraries with nvcc.
 
     python robo-vln_b200/build.py [--force] [--verbose]
 
-The shared library is written next to this file so that it travels to the GPU box with the
-repo snapshot (it is git-ignored, not gpurun-ignored).
+Two variants of the same sources are produced (csrc/h16.h):
+    librobovln_b200.so       16-bit type = fp16 (default)
+    librobovln_b200_bf16.so  16-bit type = bf16
+They are written next to this file so that they travel to the GPU box with the repo snapshot
+(git-ignored, not gpurun-ignored).
 """
 from __future__ import annotations
 
@@ -17,9 +20,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "librobovln_b200.so")
 SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "elementwise.cu", "attention.cu", "lstm.cu", "engine.cu", "capi.cu"]
-HEADERS = ["common.cuh", "rvb.h", "engine.h", os.path.join("..", "..", "include", "robovln_b200.h")]
+HEADERS = ["common.cuh", "h16.h", "rvb.h", "engine.h", os.path.join("..", "..", "include", "robovln_b200.h")]
+VARIANTS = {"fp16": ("librobovln_b200.so", ["-DRVB_BF16=0"]), "bf16": ("librobovln_b200_bf16.so", ["-DRVB_BF16=1"])}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -29,6 +32,10 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "-cudart", "static",
 ]
+
+
+def lib_path(variant: str = "fp16") -> str:
+    return os.path.join(HERE, VARIANTS[variant][0])
 
 
 def _nvcc() -> str:
@@ -47,41 +54,48 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False):
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return LIB
+    libs = [lib_path(v) for v in VARIANTS]
+    if not force and all(os.path.exists(p) for p in libs) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return libs
     nvcc = _nvcc()
 
-    def compile_one(src: str):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(job):
+        variant, src = job
+        odir = os.path.join(OBJ, variant)
+        os.makedirs(odir, exist_ok=True)
+        obj = os.path.join(odir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *VARIANTS[variant][1], "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        return src, obj, r
+        return variant, src, obj, r
 
-    objs = []
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        for src, obj, r in ex.map(compile_one, SOURCES):
+    jobs = [(v, s) for v in VARIANTS for s in SOURCES]
+    objs = {v: [] for v in VARIANTS}
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        for variant, src, obj, r in ex.map(compile_one, jobs):
             if r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
-                raise RuntimeError(f"nvcc failed on {src}")
+                raise RuntimeError(f"nvcc failed on {src} [{variant}]")
             if verbose:
-                sys.stderr.write(f"==== {src}\n{r.stderr}\n")
-            with open(os.path.join(OBJ, src + ".ptxas.log"), "w") as fh:
+                sys.stderr.write(f"==== {src} [{variant}]\n{r.stderr}\n")
+            with open(os.path.join(OBJ, variant, src + ".ptxas.log"), "w") as fh:
                 fh.write(r.stderr)
-            objs.append(obj)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", LIB, *objs]
-    r = subprocess.run(link, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("link failed")
+            objs[variant].append(obj)
+    for variant in VARIANTS:
+        link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o",
+                lib_path(variant), *objs[variant]]
+        r = subprocess.run(link, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"link failed [{variant}]")
     with open(stamp, "w") as fh:
         fh.write(dig)
-    return LIB
+    return libs
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(path)
+    for p in build(force="--force" in sys.argv, verbose="--verbose" in sys.argv):
+        print(p)

@@ -15,7 +15,7 @@ namespace rvb {
 namespace {
 
 constexpr int HD = 64;        // head dim
-constexpr int PITCH = HD + 8; // smem row pitch (bf16) -> conflict-free ldmatrix
+constexpr int PITCH = HD + 8; // smem row pitch (h16) -> conflict-free ldmatrix
 
 RVB_DEVICE void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -27,37 +27,41 @@ RVB_DEVICE void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uin
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-RVB_DEVICE void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+RVB_DEVICE void mma_h16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                uint32_t b1) {
   asm volatile(
+#if RVB_BF16
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#else
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+#endif
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // LKT = number of 16-key tiles (keys padded to 16*LKT)
 template <int LKT>
-__global__ void __launch_bounds__(256) bert_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ ctx, int L,
+__global__ void __launch_bounds__(256) bert_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ ctx, int L,
                                                         int heads) {
   constexpr int LP = LKT * 16;
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  bf16* sQ = reinterpret_cast<bf16*>(sm_raw);
-  bf16* sK = sQ + LP * PITCH;
-  bf16* sV = sK + LP * PITCH;
+  h16* sQ = reinterpret_cast<h16*>(sm_raw);
+  h16* sK = sQ + LP * PITCH;
+  h16* sV = sK + LP * PITCH;
   const int head = blockIdx.x;
   const int row = blockIdx.y;
   const int H3 = heads * HD * 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
   // stage Q, K, V head slices (zero-padded to LP rows)
-  const bf16* src = qkv + static_cast<long long>(row) * L * H3 + head * HD;
+  const h16* src = qkv + static_cast<long long>(row) * L * H3 + head * HD;
   for (int i = threadIdx.x; i < LP * 8 * 3; i += blockDim.x) {
     const int which = i / (LP * 8);
     const int rem = i - which * LP * 8;
     const int l = rem >> 3, v = rem & 7;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (l < L) val = *reinterpret_cast<const uint4*>(src + static_cast<long long>(l) * H3 + which * heads * HD + v * 8);
-    bf16* dst = (which == 0 ? sQ : (which == 1 ? sK : sV)) + l * PITCH + v * 8;
+    h16* dst = (which == 0 ? sQ : (which == 1 ? sK : sV)) + l * PITCH + v * 8;
     *reinterpret_cast<uint4*>(dst) = val;
   }
   __syncthreads();
@@ -82,8 +86,8 @@ __global__ void __launch_bounds__(256) bert_attn_kernel(const bf16* __restrict__
         const int c = half * 32 + (lane >> 3) * 8;
         uint32_t b0, b1, b2, b3;
         ldmatrix_x4(smem_u32(sK + r * PITCH + c), b0, b1, b2, b3);
-        mma_bf16_16816(s[nt], qa[half * 2][0], qa[half * 2][1], qa[half * 2][2], qa[half * 2][3], b0, b1);
-        mma_bf16_16816(s[nt], qa[half * 2 + 1][0], qa[half * 2 + 1][1], qa[half * 2 + 1][2], qa[half * 2 + 1][3], b2, b3);
+        mma_h16_16816(s[nt], qa[half * 2][0], qa[half * 2][1], qa[half * 2][2], qa[half * 2][3], b0, b1);
+        mma_h16_16816(s[nt], qa[half * 2 + 1][0], qa[half * 2 + 1][1], qa[half * 2 + 1][2], qa[half * 2 + 1][3], b2, b3);
       }
     }
     // softmax over keys (rows g = lane/4 and g+8), scale 1/sqrt(64)
@@ -124,39 +128,39 @@ __global__ void __launch_bounds__(256) bert_attn_kernel(const bf16* __restrict__
     for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.0f;
 #pragma unroll
     for (int kt = 0; kt < LKT; ++kt) {
-      const uint32_t a0 = pack_bf16x2(s[2 * kt][0], s[2 * kt][1]);
-      const uint32_t a1 = pack_bf16x2(s[2 * kt][2], s[2 * kt][3]);
-      const uint32_t a2 = pack_bf16x2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
-      const uint32_t a3 = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+      const uint32_t a0 = pack_h2(s[2 * kt][0], s[2 * kt][1]);
+      const uint32_t a1 = pack_h2(s[2 * kt][2], s[2 * kt][3]);
+      const uint32_t a2 = pack_h2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+      const uint32_t a3 = pack_h2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
 #pragma unroll
       for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-dim tiles
         const int r = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int c = (dp * 2 + (lane >> 4)) * 8;
         uint32_t b0, b1, b2, b3;
         ldmatrix_x4_trans(smem_u32(sV + r * PITCH + c), b0, b1, b2, b3);
-        mma_bf16_16816(o[dp * 2], a0, a1, a2, a3, b0, b1);
-        mma_bf16_16816(o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
+        mma_h16_16816(o[dp * 2], a0, a1, a2, a3, b0, b1);
+        mma_h16_16816(o[dp * 2 + 1], a0, a1, a2, a3, b2, b3);
       }
     }
     const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
     const int q0 = qt * 16 + (lane >> 2), q1 = q0 + 8;
-    bf16* out = ctx + static_cast<long long>(row) * L * heads * HD + head * HD + (lane & 3) * 2;
+    h16* out = ctx + static_cast<long long>(row) * L * heads * HD + head * HD + (lane & 3) * 2;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
       if (q0 < L)
         *reinterpret_cast<uint32_t*>(out + static_cast<long long>(q0) * heads * HD + dt * 8) =
-            pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+            pack_h2(o[dt][0] * inv0, o[dt][1] * inv0);
       if (q1 < L)
         *reinterpret_cast<uint32_t*>(out + static_cast<long long>(q1) * heads * HD + dt * 8) =
-            pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+            pack_h2(o[dt][2] * inv1, o[dt][3] * inv1);
     }
   }
 }
 
 template <int LKT>
-void launch_bert_attn(const bf16* qkv, bf16* ctx, int R, int L, int heads, cudaStream_t s) {
+void launch_bert_attn(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s) {
   constexpr int LP = LKT * 16;
-  const size_t smem = static_cast<size_t>(3) * LP * PITCH * sizeof(bf16);
+  const size_t smem = static_cast<size_t>(3) * LP * PITCH * sizeof(h16);
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     RVB_CUDA(cudaFuncSetAttribute(bert_attn_kernel<LKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -174,15 +178,15 @@ void launch_bert_attn(const bf16* qkv, bf16* ctx, int R, int L, int heads, cudaS
 // kv [n_mod*B*16, 512] (k | v), ctx [n_mod*B*L, 256].  4 heads x 64, 16 keys.
 // ---------------------------------------------------------------------------------------
 constexpr int VH = 4, VK = 16, VP = HD + 1;
-__global__ void __launch_bounds__(256) vla_attn_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
-                                                       bf16* __restrict__ ctx, int B, int L, int q_shared) {
+__global__ void __launch_bounds__(256) vla_attn_kernel(const h16* __restrict__ q, const h16* __restrict__ kv,
+                                                       h16* __restrict__ ctx, int B, int L, int q_shared) {
   __shared__ float sK[VH * VK * VP];
   __shared__ float sV[VH * VK * VP];
   const int b = blockIdx.x, mod = blockIdx.y;
-  const bf16* kvb = kv + (static_cast<long long>(mod) * B + b) * VK * 512;
+  const h16* kvb = kv + (static_cast<long long>(mod) * B + b) * VK * 512;
   for (int i = threadIdx.x; i < VK * 512; i += blockDim.x) {
     const int j = i / 512, c = i % 512;
-    const float v = __bfloat162float(kvb[i]);
+    const float v = from_h16(kvb[i]);
     const int cc = c & 255, h = cc >> 6, d = cc & 63;
     (c < 256 ? sK : sV)[(h * VK + j) * VP + d] = v;
   }
@@ -190,13 +194,13 @@ __global__ void __launch_bounds__(256) vla_attn_kernel(const bf16* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int h = lane >> 3, sub = lane & 7;
   for (int l = warp; l < L; l += nwarps) {
-    const bf16* qp = q + (static_cast<long long>(q_shared ? 0 : b) * L + l) * 256 + h * HD;
+    const h16* qp = q + (static_cast<long long>(q_shared ? 0 : b) * L + l) * 256 + h * HD;
     float s0 = 0.0f, s1 = 0.0f;
     const float* k0 = sK + (h * VK + 2 * sub) * VP;
     const float* k1 = k0 + VP;
 #pragma unroll 8
     for (int d = 0; d < HD; d += 2) {
-      const float2 qq = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + d));
+      const float2 qq = unpack_h2(*reinterpret_cast<const uint32_t*>(qp + d));
       s0 = fmaf(qq.x, k0[d], s0); s0 = fmaf(qq.y, k0[d + 1], s0);
       s1 = fmaf(qq.x, k1[d], s1); s1 = fmaf(qq.y, k1[d + 1], s1);
     }
@@ -223,15 +227,15 @@ __global__ void __launch_bounds__(256) vla_attn_kernel(const bf16* __restrict__ 
       for (int dd = 0; dd < 8; ++dd) o[dd] = fmaf(pj, vr[dd], o[dd]);
     }
     uint4 u;
-    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    u.x = pack_h2(o[0], o[1]); u.y = pack_h2(o[2], o[3]);
+    u.z = pack_h2(o[4], o[5]); u.w = pack_h2(o[6], o[7]);
     *reinterpret_cast<uint4*>(ctx + ((static_cast<long long>(mod) * B + b) * L + l) * 256 + h * HD + sub * 8) = u;
   }
 }
 
 }  // namespace
 
-void bert_self_attention(const bf16* qkv, bf16* ctx, int R, int L, int heads, cudaStream_t s) {
+void bert_self_attention(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s) {
   RVB_CHECK(L >= 1 && L <= 256, "bert attention: 1 <= L <= 256 (INSTRUCTION_ENCODER.max_length is 200)");
   const int lkt = (L + 15) / 16;
   if (lkt <= 2) launch_bert_attn<2>(qkv, ctx, R, L, heads, s);
@@ -241,7 +245,7 @@ void bert_self_attention(const bf16* qkv, bf16* ctx, int R, int L, int heads, cu
   else launch_bert_attn<16>(qkv, ctx, R, L, heads, s);
 }
 
-void vla_cross_attention(const bf16* q, const bf16* kv, bf16* ctx, int B, int L, int n_mod, int q_shared,
+void vla_cross_attention(const h16* q, const h16* kv, h16* ctx, int B, int L, int n_mod, int q_shared,
                          cudaStream_t s) {
   dim3 grid(B, n_mod);
   vla_attn_kernel<<<grid, 256, 0, s>>>(q, kv, ctx, B, L, q_shared);

@@ -17,6 +17,7 @@ thread_local std::string g_last_error;
 template <class F>
 int guarded(F&& f) {
   try {
+    g_last_error.clear();
     f();
     return 0;
   } catch (const Error& e) {
@@ -28,14 +29,15 @@ int guarded(F&& f) {
   }
 }
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-inline const bf16* B16(const void* p) { return reinterpret_cast<const bf16*>(p); }
-inline bf16* B16(void* p) { return reinterpret_cast<bf16*>(p); }
+inline const h16* B16(const void* p) { return reinterpret_cast<const h16*>(p); }
+inline h16* B16(void* p) { return reinterpret_cast<h16*>(p); }
 }  // namespace
 
 extern "C" {
 
 const char* hcm_last_error(void) { return g_last_error.c_str(); }
-const char* hcm_version(void) { return "robovln_b200 0.1 (sm_100a: tcgen05/TMEM/TMA)"; }
+const char* hcm_version(void) { return "robovln_b200 0.1 (sm_100a: tcgen05/TMEM/TMA; 16-bit type " RVB_H16_NAME ")"; }
+int hcm_dtype(void) { return RVB_H16_CODE; }
 
 int hcm_create(hcm_engine** out) {
   return guarded([&] {
@@ -202,7 +204,7 @@ int hcm_copy_buffer(hcm_engine* e, const char* name, void* dst_dev, size_t bytes
     void* src = nullptr;
     int dtype = 0;
     RVB_CHECK(e->eng.get_buffer(name, &src, &dtype, &shp), std::string("unknown buffer '") + name + "'");
-    size_t n = dtype == 0 ? 4 : (dtype == 1 ? 2 : 8);
+    size_t n = dtype == HCM_F32 ? 4 : (dtype == HCM_I64 ? 8 : 2);
     for (auto v : shp) n *= static_cast<size_t>(v);
     RVB_CHECK(bytes == n, "hcm_copy_buffer: size mismatch");
     RVB_CUDA(cudaMemcpyAsync(dst_dev, src, n, cudaMemcpyDeviceToDevice, S(stream)));

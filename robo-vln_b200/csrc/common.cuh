@@ -5,12 +5,13 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace rvb {
+#include "h16.h"
 
-using bf16 = __nv_bfloat16;
+namespace rvb {
 
 #define RVB_DEVICE __device__ __forceinline__
 
@@ -122,7 +123,7 @@ RVB_DEVICE void tmem_dealloc(uint32_t taddr) {        // whole warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 B = 64 bf16,
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 B = 64 h16,
 // 8-row swizzle atoms are 1024 B apart).  Bits: [0,14) addr>>4, [16,30) LBO>>4 (=1, unused
 // for swizzled K-major), [32,46) SBO>>4 (=64), [46,48) version=1, [61,64) layout=2 (SW128).
 RVB_DEVICE uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -135,13 +136,14 @@ RVB_DEVICE uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), both K-major,
-// N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// Instruction descriptor, kind::f16: D=f32 (bit4), A/B format at [7,10)/[10,13) (0 = fp16,
+// 1 = bf16), both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_h16(uint32_t M, uint32_t N) {
+  return (1u << 4) | (static_cast<uint32_t>(RVB_BF16) << 7) | (static_cast<uint32_t>(RVB_BF16) << 10) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-RVB_DEVICE void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+RVB_DEVICE void umma_f16kind(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -175,14 +177,31 @@ RVB_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" :
 // ---------------------------------------------------------------------------------------
 // math / packing
 // ---------------------------------------------------------------------------------------
-RVB_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
+#if RVB_BF16
+RVB_DEVICE uint32_t pack_h2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-RVB_DEVICE float2 unpack_bf16x2(uint32_t u) {
+RVB_DEVICE float2 unpack_h2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+RVB_DEVICE h16 to_h16(float x) { return __float2bfloat16_rn(x); }
+RVB_DEVICE float from_h16(h16 x) { return __bfloat162float(x); }
+#else
+// fp16: saturate to the largest finite value instead of overflowing to inf
+RVB_DEVICE float sat_h(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }
+RVB_DEVICE uint32_t pack_h2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(sat_h(lo), sat_h(hi));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+RVB_DEVICE float2 unpack_h2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+RVB_DEVICE h16 to_h16(float x) { return __float2half_rn(sat_h(x)); }
+RVB_DEVICE float from_h16(h16 x) { return __half2float(x); }
+#endif
 RVB_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 RVB_DEVICE float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 

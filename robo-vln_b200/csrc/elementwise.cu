@@ -1,5 +1,5 @@
 // Bandwidth-bound kernels around the tensor-core contractions: stems, pooling, GroupNorm,
-// LayerNorm, embeddings, small heads.  All activations are NHWC / row-major bf16 with fp32
+// LayerNorm, embeddings, small heads.  All activations are NHWC / row-major h16 with fp32
 // statistics; every kernel moves 16-byte vectors along the contiguous (channel) dimension.
 #include "common.cuh"
 #include "rvb.h"
@@ -10,32 +10,32 @@ namespace rvb {
 
 namespace {
 
-RVB_DEVICE void load8(const bf16* p, float (&f)[8]) {
+RVB_DEVICE void load8(const h16* p, float (&f)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   float2 t;
-  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+  t = unpack_h2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_h2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_h2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_h2(u.w); f[6] = t.x; f[7] = t.y;
 }
-RVB_DEVICE void store8(bf16* p, const float (&f)[8]) {
+RVB_DEVICE void store8(h16* p, const float (&f)[8]) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]);
-  u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]);
-  u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack_h2(f[0], f[1]);
+  u.y = pack_h2(f[2], f[3]);
+  u.z = pack_h2(f[4], f[5]);
+  u.w = pack_h2(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
 
 // ---------------------------------------------------------------------------------------
-// RGB stem: [NB,H,W,3] fp32 0..255 -> im2col rows [NB*Ho*Wo, Kpitch] bf16 for the 7x7 s2 p3
+// RGB stem: [NB,H,W,3] fp32 0..255 -> im2col rows [NB*Ho*Wo, Kpitch] h16 for the 7x7 s2 p3
 // conv (k = r*21 + s*3 + c), with the reference's /255 (resnet_encoders.py:213) folded in.
 // ---------------------------------------------------------------------------------------
 constexpr int STEM_PIX = 32;
-__global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __restrict__ rgb, bf16* __restrict__ out,
+__global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __restrict__ rgb, h16* __restrict__ out,
                                                               int NB, int H, int W, int Ho, int Wo, int Kpitch) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  bf16* tile = reinterpret_cast<bf16*>(sm_raw);  // [STEM_PIX][Kpitch]
+  h16* tile = reinterpret_cast<h16*>(sm_raw);  // [STEM_PIX][Kpitch]
   const long long M = static_cast<long long>(NB) * Ho * Wo;
   const long long m0 = static_cast<long long>(blockIdx.x) * STEM_PIX;
   const int total = STEM_PIX * Kpitch;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __res
       if (h >= 0 && h < H && w >= 0 && w < W)
         v = __ldg(rgb + ((static_cast<long long>(img) * H + h) * W + w) * 3 + c) / 255.0f;
     }
-    tile[e] = __float2bfloat16_rn(v);
+    tile[e] = to_h16(v);
   }
   __syncthreads();
   const long long rows = std::min<long long>(STEM_PIX, M - m0);
@@ -68,9 +68,9 @@ __global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------
-// 3x3 stride-2 pad-1 max pooling, NHWC bf16
+// 3x3 stride-2 pad-1 max pooling, NHWC h16
 // ---------------------------------------------------------------------------------------
-__global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int NB, int H, int W, int C,
+__global__ void maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict__ out, int NB, int H, int W, int C,
                                     int Ho, int Wo) {
   const int cv = C / 8;
   const long long total = static_cast<long long>(NB) * Ho * Wo * cv;
@@ -101,12 +101,12 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in, bf16* __restric
 }
 
 // ---------------------------------------------------------------------------------------
-// Depth stem: [NB,H,W,1] fp32 -> avg_pool2d(2) -> conv7x7 s2 p3 (1->32, no bias) -> raw bf16
+// Depth stem: [NB,H,W,1] fp32 -> avg_pool2d(2) -> conv7x7 s2 p3 (1->32, no bias) -> raw h16
 // [NB,Ho,Wo,32]  (resnet_policy.py:184-186, resnet.py:185-196).  fp32 math on CUDA cores:
 // 12.8 MFLOP per image.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) depth_stem_kernel(const float* __restrict__ depth, const float* __restrict__ w,
-                                                         bf16* __restrict__ out, int H, int W, int Hp, int Wp, int Ho,
+                                                         h16* __restrict__ out, int H, int W, int Hp, int Wp, int Ho,
                                                          int Wo) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* ws = reinterpret_cast<float*>(sm_raw);  // [49][32]
@@ -139,33 +139,31 @@ __global__ void __launch_bounds__(256) depth_stem_kernel(const float* __restrict
 #pragma unroll
       for (int s = 0; s < 7; ++s) acc = fmaf(rows[r * RW + 2 * wo + s], ws[(r * 7 + s) * 32 + ch], acc);
     }
-    out[((static_cast<long long>(img) * Ho + ho) * Wo + wo) * 32 + ch] = __float2bfloat16_rn(acc);
+    out[((static_cast<long long>(img) * Ho + ho) * Wo + wo) * 32 + ch] = to_h16(acc);
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// GroupNorm statistics: stats[img][g] = (sum, sumsq) over HW x (C/G) elements (fp32 atomics
-// on a pre-zeroed buffer).  Thread t owns the 8-channel slot t % (C/8).
+// GroupNorm statistics: stats[img][g] = (sum, sumsq) over HW x (C/G) elements.
+// One CTA per sample and a fixed-order reduction (registers -> smem tree over pixel rows ->
+// per-group serial sum): bit-reproducible from run to run, no atomics, no zero-init needed.
+// Thread t owns the 8-channel slot t % (C/8) and pixel rows t / (C/8), + k * 256/(C/8).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int HW,
+__global__ void __launch_bounds__(256) gn_stats_kernel(const h16* __restrict__ x, float* __restrict__ stats, int HW,
                                                        int C, int G) {
-  __shared__ float sg[64], qg[64];
-  const int img = blockIdx.y;
+  __shared__ float ps[256][8];
+  __shared__ float pq[256][8];
+  const int img = blockIdx.x;
   const int cv = C / 8;
   const int slot = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;
-  const int rows_per_iter = blockDim.x / cv;
+  const int rows_per_iter = blockDim.x / cv;   // power of two
   const int cpg = C / G;
-  if (threadIdx.x < 64) {
-    sg[threadIdx.x] = 0.0f;
-    qg[threadIdx.x] = 0.0f;
-  }
-  __syncthreads();
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0f;
-  const bf16* base = x + static_cast<long long>(img) * HW * C + slot * 8;
-  for (int p = blockIdx.x * rows_per_iter + prow; p < HW; p += gridDim.x * rows_per_iter) {
+  const h16* base = x + static_cast<long long>(img) * HW * C + slot * 8;
+  for (int p = prow; p < HW; p += rows_per_iter) {
     float f[8];
     load8(base + static_cast<long long>(p) * C, f);
 #pragma unroll
@@ -174,36 +172,41 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
       q[j] = fmaf(f[j], f[j], q[j]);
     }
   }
-  if (cpg >= 8) {
-    float ss = 0.0f, qq = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ss += s[j];
-      qq += q[j];
-    }
-    const int g = (slot * 8) / cpg;
-    atomicAdd(&sg[g], ss);
-    atomicAdd(&qg[g], qq);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (slot * 8 + j) / cpg;
-      atomicAdd(&sg[g], s[j]);
-      atomicAdd(&qg[g], q[j]);
-    }
+  for (int j = 0; j < 8; ++j) {
+    ps[threadIdx.x][j] = s[j];
+    pq[threadIdx.x][j] = q[j];
   }
   __syncthreads();
+  for (int stride = rows_per_iter >> 1; stride > 0; stride >>= 1) {
+    if (prow < stride) {
+      const int other = threadIdx.x + stride * cv;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ps[threadIdx.x][j] += ps[other][j];
+        pq[threadIdx.x][j] += pq[other][j];
+      }
+    }
+    __syncthreads();
+  }
+  // rows 0..cv-1 of ps/pq now hold the per-channel totals (channel c -> [c / 8][c % 8])
   if (threadIdx.x < G) {
-    atomicAdd(&stats[(static_cast<long long>(img) * G + threadIdx.x) * 2 + 0], sg[threadIdx.x]);
-    atomicAdd(&stats[(static_cast<long long>(img) * G + threadIdx.x) * 2 + 1], qg[threadIdx.x]);
+    float ss = 0.0f, qq = 0.0f;
+    const int c0 = threadIdx.x * cpg;
+    for (int c = c0; c < c0 + cpg; ++c) {
+      ss += ps[c >> 3][c & 7];
+      qq += pq[c >> 3][c & 7];
+    }
+    stats[(static_cast<long long>(img) * G + threadIdx.x) * 2 + 0] = ss;
+    stats[(static_cast<long long>(img) * G + threadIdx.x) * 2 + 1] = qq;
   }
 }
 
 struct GnApplyDev {
-  const bf16* x; const float* stats; const float* gamma; const float* beta;
+  const h16* x; const float* stats; const float* gamma; const float* beta;
   int NB, HW, C, G, relu, res_mode;
-  const bf16* res; const float* res_stats; const float* res_gamma; const float* res_beta;
-  bf16* out; long long out_pitch;
+  const h16* res; const float* res_stats; const float* res_gamma; const float* res_beta;
+  h16* out; long long out_pitch;
 };
 
 RVB_DEVICE void gn_scale_shift(const float* stats, int img, int G, int g, float cnt, float gamma, float beta,
@@ -266,12 +269,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
 //   cellmean[img][0..C)      = mean over the 16 cells     (rgb_linear's AdaptiveAvgPool1d(1))
 //   gmean[img][0..C)         = global mean                (torchvision avgpool, lo path)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rgb_pool_kernel(const bf16* __restrict__ feat, int H, int W, int C,
-                                                       bf16* __restrict__ tokens, long long tok_pitch,
-                                                       bf16* __restrict__ cellmean, long long cm_pitch,
-                                                       bf16* __restrict__ gmean) {
+__global__ void __launch_bounds__(256) rgb_pool_kernel(const h16* __restrict__ feat, int H, int W, int C,
+                                                       h16* __restrict__ tokens, long long tok_pitch,
+                                                       h16* __restrict__ cellmean, long long cm_pitch,
+                                                       h16* __restrict__ gmean) {
   const int img = blockIdx.x;
-  const bf16* base = feat + static_cast<long long>(img) * H * W * C;
+  const h16* base = feat + static_cast<long long>(img) * H * W * C;
   for (int v = threadIdx.x; v < C / 8; v += blockDim.x) {
     float cm[8], gm[8];
 #pragma unroll
@@ -318,8 +321,8 @@ __global__ void __launch_bounds__(256) rgb_pool_kernel(const bf16* __restrict__ 
 
 // Spatial-embedding channels: the reference views the [16,64] table as [64,4,4]
 // (resnet_encoders.py:91-102): channel c of cell k reads flat[c*16 + k].
-__global__ void fill_spatial_embedding_kernel(const float* __restrict__ flat, bf16* __restrict__ tokens, int NB,
-                                              long long tok_pitch, int col0, bf16* __restrict__ cellmean,
+__global__ void fill_spatial_embedding_kernel(const float* __restrict__ flat, h16* __restrict__ tokens, int NB,
+                                              long long tok_pitch, int col0, h16* __restrict__ cellmean,
                                               long long cm_pitch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NB * 64) return;
@@ -328,9 +331,9 @@ __global__ void fill_spatial_embedding_kernel(const float* __restrict__ flat, bf
   for (int k = 0; k < 16; ++k) {
     const float v = flat[c * 16 + k];
     m += v;
-    tokens[(static_cast<long long>(img) * 16 + k) * tok_pitch + col0 + c] = __float2bfloat16_rn(v);
+    tokens[(static_cast<long long>(img) * 16 + k) * tok_pitch + col0 + c] = to_h16(v);
   }
-  if (cellmean != nullptr) cellmean[static_cast<long long>(img) * cm_pitch + col0 + c] = __float2bfloat16_rn(m / 16.0f);
+  if (cellmean != nullptr) cellmean[static_cast<long long>(img) * cm_pitch + col0 + c] = to_h16(m / 16.0f);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(256) bert_embed_ln_kernel(const long long* __r
                                                             const float* __restrict__ pos,
                                                             const float* __restrict__ type0,
                                                             const float* __restrict__ g, const float* __restrict__ b,
-                                                            bf16* __restrict__ out) {
+                                                            h16* __restrict__ out) {
   constexpr int D = NV * 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -377,20 +380,20 @@ __global__ void __launch_bounds__(256) bert_embed_ln_kernel(const long long* __r
     const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
     uint2 o;
-    o.x = pack_bf16x2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
-    o.y = pack_bf16x2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+    o.x = pack_h2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+    o.y = pack_h2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
     *reinterpret_cast<uint2*>(out + static_cast<long long>(warp) * D + c) = o;
   }
 }
 
 // LayerNorm over fp32 rows (the producing GEMM already added bias and residual), optional
-// additive table (sinusoid PE, transformer.py:271-274) AFTER the norm; bf16 out.
+// additive table (sinusoid PE, transformer.py:271-274) AFTER the norm; h16 out.
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int M,
                                                              const float* __restrict__ g,
                                                              const float* __restrict__ b, float eps,
                                                              const float* __restrict__ pe, int pe_rows,
-                                                             bf16* __restrict__ out) {
+                                                             h16* __restrict__ out) {
   constexpr int D = NV * 128;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -422,34 +425,34 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
       y.x += pp.x; y.y += pp.y; y.z += pp.z; y.w += pp.w;
     }
     uint2 o;
-    o.x = pack_bf16x2(y.x, y.y);
-    o.y = pack_bf16x2(y.z, y.w);
+    o.x = pack_h2(y.x, y.y);
+    o.y = pack_h2(y.z, y.w);
     *reinterpret_cast<uint2*>(out + static_cast<long long>(row) * D + c) = o;
   }
 }
 
 // mean over the L tokens of each (modality, batch row) group: x [n_mod*B*L, D] ->
 // out[b*out_pitch + mod*mod_stride + d]   (cross_pooler, seq2seq_highlevel_cma.py:114-115,209-210)
-__global__ void token_mean_kernel(const bf16* __restrict__ x, int B, int L, int D, bf16* __restrict__ out,
+__global__ void token_mean_kernel(const h16* __restrict__ x, int B, int L, int D, h16* __restrict__ out,
                                   long long out_pitch, long long mod_stride) {
   const int g = blockIdx.x;
   const int mod = g / B, b = g % B;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.0f;
-    const bf16* p = x + static_cast<long long>(g) * L * D + d;
-    for (int l = 0; l < L; ++l) acc += __bfloat162float(p[static_cast<long long>(l) * D]);
-    out[b * out_pitch + mod * mod_stride + d] = __float2bfloat16_rn(acc / static_cast<float>(L));
+    const h16* p = x + static_cast<long long>(g) * L * D + d;
+    for (int l = 0; l < L; ++l) acc += from_h16(p[static_cast<long long>(l) * D]);
+    out[b * out_pitch + mod * mod_stride + d] = to_h16(acc / static_cast<float>(L));
   }
 }
 
 __global__ void sub_task_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ table, int B,
-                                      bf16* __restrict__ out, long long out_pitch) {
+                                      h16* __restrict__ out, long long out_pitch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 32) return;
   const int b = i / 32, c = i % 32;
   long long id = ids[b];
   id = id < 0 ? 0 : (id > 4 ? 4 : id);
-  out[b * out_pitch + c] = __float2bfloat16_rn(table[id * 32 + c]);
+  out[b * out_pitch + c] = to_h16(table[id * 32 + c]);
 }
 
 // out[m][o] = dot(y[m], w[o]) + b[o], one warp per output (tiny heads: 512 -> 4 / 2 / 1)
@@ -498,7 +501,7 @@ int grid_for(long long total, int block, int max_blocks) {
 
 }  // namespace
 
-void rgb_stem_im2col(const float* rgb, bf16* out, int NB, int H, int W, int Kpitch, cudaStream_t s) {
+void rgb_stem_im2col(const float* rgb, h16* out, int NB, int H, int W, int Kpitch, cudaStream_t s) {
   RVB_CHECK(Kpitch >= 147 && Kpitch % 8 == 0, "stem: bad K pitch");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const long long M = static_cast<long long>(NB) * Ho * Wo;
@@ -507,7 +510,7 @@ void rgb_stem_im2col(const float* rgb, bf16* out, int NB, int H, int W, int Kpit
   RVB_CUDA(cudaGetLastError());
 }
 
-void maxpool3x3s2(const bf16* in, bf16* out, int NB, int H, int W, int C, cudaStream_t s) {
+void maxpool3x3s2(const h16* in, h16* out, int NB, int H, int W, int C, cudaStream_t s) {
   RVB_CHECK(C % 8 == 0, "maxpool: C % 8");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(NB) * Ho * Wo * (C / 8);
@@ -515,7 +518,7 @@ void maxpool3x3s2(const bf16* in, bf16* out, int NB, int H, int W, int C, cudaSt
   RVB_CUDA(cudaGetLastError());
 }
 
-void depth_stem_conv(const float* depth, const float* w, bf16* out, int NB, int H, int W, cudaStream_t s) {
+void depth_stem_conv(const float* depth, const float* w, h16* out, int NB, int H, int W, cudaStream_t s) {
   const int Hp = H / 2, Wp = W / 2;
   const int Ho = (Hp + 6 - 7) / 2 + 1, Wo = (Wp + 6 - 7) / 2 + 1;
   const size_t smem = (49 * 32 + 7 * (Wp + 6)) * sizeof(float);
@@ -524,14 +527,10 @@ void depth_stem_conv(const float* depth, const float* w, bf16* out, int NB, int 
   RVB_CUDA(cudaGetLastError());
 }
 
-void gn_stats(const bf16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s) {
+void gn_stats(const h16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s) {
   const int cv = C / 8;
   RVB_CHECK(C % 8 == 0 && cv <= 256 && 256 % cv == 0 && G <= 64 && C % G == 0, "gn_stats: unsupported C/G");
-  const int rows_per_iter = 256 / cv;
-  int gx = (HW + rows_per_iter * 4 - 1) / (rows_per_iter * 4);
-  gx = std::max(1, std::min(gx, 64));
-  dim3 grid(gx, NB);
-  gn_stats_kernel<<<grid, 256, 0, s>>>(x, stats, HW, C, G);
+  gn_stats_kernel<<<NB, 256, 0, s>>>(x, stats, HW, C, G);
   RVB_CUDA(cudaGetLastError());
 }
 
@@ -547,14 +546,14 @@ void gn_apply(const GnApply& a, cudaStream_t s) {
   RVB_CUDA(cudaGetLastError());
 }
 
-void rgb_pool(const bf16* feat, int NB, int H, int W, int C, bf16* tokens, int64_t tok_pitch, bf16* cellmean,
-              int64_t cm_pitch, bf16* gmean, cudaStream_t s) {
+void rgb_pool(const h16* feat, int NB, int H, int W, int C, h16* tokens, int64_t tok_pitch, h16* cellmean,
+              int64_t cm_pitch, h16* gmean, cudaStream_t s) {
   RVB_CHECK(C % 8 == 0 && H >= 4 && W >= 4, "rgb_pool: bad shape");
   rgb_pool_kernel<<<NB, 256, 0, s>>>(feat, H, W, C, tokens, tok_pitch, cellmean, cm_pitch, gmean);
   RVB_CUDA(cudaGetLastError());
 }
 
-void fill_spatial_embedding(const float* emb_flat, bf16* tokens, int NB, int64_t tok_pitch, int col0, bf16* cellmean,
+void fill_spatial_embedding(const float* emb_flat, h16* tokens, int NB, int64_t tok_pitch, int col0, h16* cellmean,
                             int64_t cm_pitch, cudaStream_t s) {
   fill_spatial_embedding_kernel<<<(NB * 64 + 127) / 128, 128, 0, s>>>(emb_flat, tokens, NB, tok_pitch, col0, cellmean,
                                                                       cm_pitch);
@@ -562,7 +561,7 @@ void fill_spatial_embedding(const float* emb_flat, bf16* tokens, int NB, int64_t
 }
 
 void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, int R, int L, const float* word,
-                   const float* pos, const float* type0, const float* g, const float* b, bf16* out, cudaStream_t s) {
+                   const float* pos, const float* type0, const float* g, const float* b, h16* out, cudaStream_t s) {
   const long long warps = static_cast<long long>(R) * L;
   bert_embed_ln_kernel<6><<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(
       reinterpret_cast<const long long*>(ids_i64), ids_f32, id_rows, R, L, word, pos, type0, g, b, out);
@@ -570,7 +569,7 @@ void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, in
 }
 
 void layernorm_rows(const float* x, int M, int D, const float* g, const float* b, float eps, const float* pe,
-                    int pe_rows, bf16* out, cudaStream_t s) {
+                    int pe_rows, h16* out, cudaStream_t s) {
   const int blocks = static_cast<int>((static_cast<long long>(M) * 32 + 255) / 256);
   if (D == 768) layernorm_rows_kernel<6><<<blocks, 256, 0, s>>>(x, M, g, b, eps, pe, pe_rows, out);
   else if (D == 256) layernorm_rows_kernel<2><<<blocks, 256, 0, s>>>(x, M, g, b, eps, pe, pe_rows, out);
@@ -578,13 +577,13 @@ void layernorm_rows(const float* x, int M, int D, const float* g, const float* b
   RVB_CUDA(cudaGetLastError());
 }
 
-void token_mean(const bf16* x, int n_mod, int B, int L, int D, bf16* out, int64_t out_pitch, int64_t mod_stride,
+void token_mean(const h16* x, int n_mod, int B, int L, int D, h16* out, int64_t out_pitch, int64_t mod_stride,
                 cudaStream_t s) {
   token_mean_kernel<<<n_mod * B, 256, 0, s>>>(x, B, L, D, out, out_pitch, mod_stride);
   RVB_CUDA(cudaGetLastError());
 }
 
-void sub_task_embed(const int64_t* ids, const float* table, int B, bf16* out, int64_t out_pitch, cudaStream_t s) {
+void sub_task_embed(const int64_t* ids, const float* table, int B, h16* out, int64_t out_pitch, cudaStream_t s) {
   sub_task_embed_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(reinterpret_cast<const long long*>(ids), table, B, out,
                                                              out_pitch);
   RVB_CUDA(cudaGetLastError());

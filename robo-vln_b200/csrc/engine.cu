@@ -44,8 +44,8 @@ const WTensor& Engine::W(const std::string& name, int dtype, std::initializer_li
   }
   return t;
 }
-const bf16* Engine::Wb(const std::string& n, std::initializer_list<int64_t> s) const {
-  return reinterpret_cast<const bf16*>(W(n, 1, s).ptr);
+const h16* Engine::Wb(const std::string& n, std::initializer_list<int64_t> s) const {
+  return reinterpret_cast<const h16*>(W(n, RVB_H16_CODE, s).ptr);
 }
 const float* Engine::Wf(const std::string& n, std::initializer_list<int64_t> s) const {
   return reinterpret_cast<const float*>(W(n, 0, s).ptr);
@@ -95,8 +95,8 @@ void Engine::label(Stage& st, const std::string& prefix) {
   }
 }
 
-ConvGemm Engine::linear(const bf16* in, int64_t M, int K, int64_t lda, const bf16* w, int N, const float* bias,
-                        int act, void* out, int64_t ldc, int out_f32, const bf16* res, int64_t ldr, int res_rows) {
+ConvGemm Engine::linear(const h16* in, int64_t M, int K, int64_t lda, const h16* w, int N, const float* bias,
+                        int act, void* out, int64_t ldc, int out_f32, const h16* res, int64_t ldr, int res_rows) {
   ConvGemm g;
   g.in = in; g.NB = 1; g.H = 1; g.W = static_cast<int>(M); g.Cin = K; g.in_pitch = lda;
   g.w = w; g.Cout = N; g.KH = g.KW = 1; g.stride = 1; g.pad = 0;
@@ -113,9 +113,9 @@ void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
   const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;   // conv1 7x7 s2 p3
   const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1; // maxpool 3x3 s2 p1
   constexpr int KP = 160;
-  bf16* im2col = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * KP * 2));
-  bf16* stem = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 64 * 2));
-  bf16* x = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 64 * 2));
+  h16* im2col = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * KP * 2));
+  h16* stem = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 64 * 2));
+  h16* x = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 64 * 2));
   if (!dry_) {
     st.push_back([this, im2col, B, H, W](cudaStream_t s) { rgb_stem_im2col(args_.rgb, im2col, B, H, W, KP, s); return 1; });
     add_gemm(st, linear(im2col, static_cast<int64_t>(B) * H1 * W1, KP, KP, Wb(ns + ".rgb.stem.w", {64, KP}), 64,
@@ -130,12 +130,12 @@ void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
       const int stride = (b == 0 && li > 0) ? 2 : 1;
       const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
       const std::string p = ns + ".rgb.l" + std::to_string(li + 1) + "." + std::to_string(b);
-      bf16* t1 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
-      bf16* t2 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
-      bf16* out = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
-      const bf16* idt = x;
+      h16* t1 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
+      h16* t2 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
+      h16* out = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+      const h16* idt = x;
       if (b == 0) {
-        bf16* ds = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+        h16* ds = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
         if (!dry_) {
           ConvGemm g;
           g.in = x; g.NB = B; g.H = h; g.W = w; g.Cin = cin; g.in_pitch = cin;
@@ -161,7 +161,7 @@ void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
   }
   rgb_feat_ = x; rgb_fh_ = h; rgb_fw_ = w;
   if (!dry_) {
-    bf16* feat = x;
+    h16* feat = x;
     const int fh = h, fw = w;
     st.push_back([this, feat, B, fh, fw](cudaStream_t s) {
       rgb_pool(feat, B, fh, fw, 2048, tokens_r_, 2112, cellmean_r_, 2112, gmean_r_, s);
@@ -192,9 +192,9 @@ void Engine::plan_depth_trunk(const std::string& ns, Stage& st) {
     const size_t bytes = gn_stats_cap_ * sizeof(float);
     st.push_back([arena, bytes](cudaStream_t s) { RVB_CUDA(cudaMemsetAsync(arena, 0, bytes, s)); return 1; });
   }
-  bf16* raw0 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
-  bf16* a0 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
-  bf16* x = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 32 * 2));
+  h16* raw0 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
+  h16* a0 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
+  h16* x = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 32 * 2));
   {
     float* st0 = new_stats(G);
     if (!dry_) {
@@ -210,8 +210,8 @@ void Engine::plan_depth_trunk(const std::string& ns, Stage& st) {
   }
   int h = H2, w = W2, cin = 32;
   const int nblocks[4] = {3, 4, 6, 3};
-  auto conv_gn = [&](const bf16* in, int ih, int iw, int ci, const std::string& wname, int co, int k, int stride,
-                     bf16* raw, float* stats) {
+  auto conv_gn = [&](const h16* in, int ih, int iw, int ci, const std::string& wname, int co, int k, int stride,
+                     h16* raw, float* stats) {
     if (dry_) return;
     ConvGemm g;
     g.in = in; g.NB = B; g.H = ih; g.W = iw; g.Cin = ci; g.in_pitch = ci;
@@ -227,19 +227,19 @@ void Engine::plan_depth_trunk(const std::string& ns, Stage& st) {
       const int stride = (b == 0 && li > 0) ? 2 : 1;
       const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
       const std::string p = ns + ".depth.l" + std::to_string(li + 1) + "." + std::to_string(b);
-      bf16* r1 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
-      bf16* t1 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
-      bf16* r2 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
-      bf16* t2 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
-      bf16* r3 = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
-      bf16* out = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+      h16* r1 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
+      h16* t1 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
+      h16* r2 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
+      h16* t2 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
+      h16* r3 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+      h16* out = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
       float* s1 = new_stats(G);
       float* s2 = new_stats(G);
       float* s3 = new_stats(G);
-      bf16* rds = nullptr;
+      h16* rds = nullptr;
       float* sds = nullptr;
       if (b == 0) {
-        rds = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+        rds = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
         sds = new_stats(G);
       }
       if (dry_) { x = out; h = ho; w = wo; cin = cout; continue; }
@@ -269,7 +269,7 @@ void Engine::plan_depth_trunk(const std::string& ns, Stage& st) {
   }
   RVB_CHECK(h == 4 && w == 4, "depth trunk must end at 4x4 (depth frames must be 256x256)");
   // compression conv3x3 1024->128 + GroupNorm(1,128) + ReLU -> tokens_d[:, :, 0:128]
-  bf16* rc = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 16 * 128 * 2));
+  h16* rc = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 16 * 128 * 2));
   float* sc = new_stats(1);
   if (!dry_) {
     ConvGemm g;
@@ -291,12 +291,12 @@ void Engine::plan_bert(Stage& st) {
   const int L = shp_.L;
   const int R = (shp_.instr_rows == 1) ? 1 : shp_.B;   // one BERT pass per DISTINCT instruction row
   const int64_t M = static_cast<int64_t>(R) * L;
-  bf16* xa = reinterpret_cast<bf16*>(alloc(M * 768 * 2));
-  bf16* xb = reinterpret_cast<bf16*>(alloc(M * 768 * 2));
-  bf16* qkv = reinterpret_cast<bf16*>(alloc(M * 2304 * 2));
-  bf16* ctx = reinterpret_cast<bf16*>(alloc(M * 768 * 2));
+  h16* xa = reinterpret_cast<h16*>(alloc(M * 768 * 2));
+  h16* xb = reinterpret_cast<h16*>(alloc(M * 768 * 2));
+  h16* qkv = reinterpret_cast<h16*>(alloc(M * 2304 * 2));
+  h16* ctx = reinterpret_cast<h16*>(alloc(M * 768 * 2));
   float* y = reinterpret_cast<float*>(alloc(M * 768 * 4));
-  bf16* hbuf = reinterpret_cast<bf16*>(alloc(M * 3072 * 2));
+  h16* hbuf = reinterpret_cast<h16*>(alloc(M * 3072 * 2));
   bert_out_ = xa;
   if (dry_) return;
   {
@@ -344,22 +344,22 @@ void Engine::plan_bert(Stage& st) {
 
 // ---------------------------------------------------------------------------------------
 // Visual_Ling_Attn for both modalities at once + token mean-pool
-//   bert: [R*L,768] bf16; kvin: [2*B*16,256] bf16 (rgb rows then depth rows);
+//   bert: [R*L,768] h16; kvin: [2*B*16,256] h16 (rgb rows then depth rows);
 //   pooled -> out[b*out_pitch + mod*256 + d]
 // ---------------------------------------------------------------------------------------
-void Engine::plan_cross_modal(Stage& st, const bf16* bert, const bf16* kvin, bf16* out, int64_t out_pitch) {
+void Engine::plan_cross_modal(Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch) {
   const int B = shp_.B, L = shp_.L;
   const int R = (shp_.instr_rows == 1) ? 1 : B;
   const int64_t MQ = static_cast<int64_t>(R) * L, MV = 2ll * B * 16, MX = 2ll * B * L;
   float* f32a = reinterpret_cast<float*>(alloc(std::max<int64_t>(MX, MV) * 256 * 4));
-  bf16* Q0 = reinterpret_cast<bf16*>(alloc(MQ * 256 * 2));
-  bf16* qq = reinterpret_cast<bf16*>(alloc(MQ * 256 * 2));
-  bf16* vis = reinterpret_cast<bf16*>(alloc(MV * 256 * 2));
-  bf16* kv = reinterpret_cast<bf16*>(alloc(MV * 512 * 2));
-  bf16* ctx = reinterpret_cast<bf16*>(alloc(MX * 256 * 2));
-  bf16* X = reinterpret_cast<bf16*>(alloc(MX * 256 * 2));
-  bf16* hff = reinterpret_cast<bf16*>(alloc(MX * 1024 * 2));
-  bf16* Y = reinterpret_cast<bf16*>(alloc(MX * 256 * 2));
+  h16* Q0 = reinterpret_cast<h16*>(alloc(MQ * 256 * 2));
+  h16* qq = reinterpret_cast<h16*>(alloc(MQ * 256 * 2));
+  h16* vis = reinterpret_cast<h16*>(alloc(MV * 256 * 2));
+  h16* kv = reinterpret_cast<h16*>(alloc(MV * 512 * 2));
+  h16* ctx = reinterpret_cast<h16*>(alloc(MX * 256 * 2));
+  h16* X = reinterpret_cast<h16*>(alloc(MX * 256 * 2));
+  h16* hff = reinterpret_cast<h16*>(alloc(MX * 1024 * 2));
+  h16* Y = reinterpret_cast<h16*>(alloc(MX * 256 * 2));
   float* pe = reinterpret_cast<float*>(alloc(static_cast<size_t>(L) * 256 * 4));
   if (dry_) return;
   const std::string p = "hi.vla";
@@ -405,7 +405,7 @@ void Engine::plan_cross_modal(Stage& st, const bf16* bert, const bf16* kvin, bf1
       return 1;
     });
   }
-  vla_tokens_ = Y;
+  if (&st == &st_hi_tail_) vla_tokens_ = Y;   // the stand-alone cross-modal stage has its own buffers
   st.push_back([Y, B, L, out, out_pitch](cudaStream_t s) { token_mean(Y, 2, B, L, 256, out, out_pitch, 256, s); return 1; });
 }
 
@@ -414,8 +414,8 @@ void Engine::plan_cross_modal(Stage& st, const bf16* bert, const bf16* kvin, bf1
 // ---------------------------------------------------------------------------------------
 void Engine::plan_hi_tail(Stage& pre, Stage& st) {
   const int B = shp_.B, N = shp_.N, T = B / N;
-  kvin_ = reinterpret_cast<bf16*>(alloc(2ull * B * 16 * 256 * 2));
-  concat_hi_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 896 * 2));
+  kvin_ = reinterpret_cast<h16*>(alloc(2ull * B * 16 * 256 * 2));
+  concat_hi_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 896 * 2));
   gx_hi_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 2048 * 4));
   y_hi_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 512 * 4));
   hscr_hi_ = reinterpret_cast<float*>(alloc(2ull * N * 512 * 4));
@@ -445,7 +445,7 @@ void Engine::plan_hi_tail(Stage& pre, Stage& st) {
   add_gemm(st, linear(concat_hi_, B, 896, 896, Wb("hi.lstm.wih", {2048, 896}), 2048, Wf("hi.lstm.b", {2048}), ACT_NONE,
                       gx_hi_, 2048, 1));
   {
-    const bf16* whh = Wb("hi.lstm.whh", {2048, 512});
+    const h16* whh = Wb("hi.lstm.whh", {2048, 512});
     st.push_back([this, whh, T, N](cudaStream_t s) {
       lstm_forward(gx_hi_, whh, args_.masks, args_.mask_stride, args_.hc_hi_in, args_.hc_hi_out, hscr_hi_, y_hi_, T, N, s);
       return T;
@@ -458,7 +458,7 @@ void Engine::plan_hi_tail(Stage& pre, Stage& st) {
 
 void Engine::plan_lo_tail(Stage& st) {
   const int B = shp_.B, N = shp_.N, T = B / N;
-  lo_in_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 416 * 2));
+  lo_in_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 416 * 2));
   gx_lo_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 2048 * 4));
   y_lo_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 512 * 4));
   hscr_lo_ = reinterpret_cast<float*>(alloc(2ull * N * 512 * 4));
@@ -476,7 +476,7 @@ void Engine::plan_lo_tail(Stage& st) {
   }
   add_gemm(st, linear(lo_in_, B, 416, 416, Wb("lo.lstm.wih", {2048, 416}), 2048, Wf("lo.lstm.b", {2048}), ACT_NONE, gx_lo_,
                       2048, 1));
-  const bf16* whh = Wb("lo.lstm.whh", {2048, 512});
+  const h16* whh = Wb("lo.lstm.whh", {2048, 512});
   st.push_back([this, whh, T, N](cudaStream_t s) {
     lstm_forward(gx_lo_, whh, args_.masks, args_.mask_stride, args_.hc_lo_in, args_.hc_lo_out, hscr_lo_, y_lo_, T, N, s);
     return T;
@@ -514,10 +514,10 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
 
   const int B = shp.B;
   // feature buffers shared by hi and lo
-  tokens_r_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 16 * 2112 * 2));
-  cellmean_r_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 2112 * 2));
-  gmean_r_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 2048 * 2));
-  tokens_d_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 16 * 192 * 2));
+  tokens_r_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 16 * 2112 * 2));
+  cellmean_r_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 2112 * 2));
+  gmean_r_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 2048 * 2));
+  tokens_d_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 16 * 192 * 2));
   gn_stats_cap_ = static_cast<size_t>(B) * 16 * 2 * 64;   // 54 GroupNorm layers + compression
   gn_stats_arena_ = reinterpret_cast<float*>(alloc(gn_stats_cap_ * sizeof(float)));
   // host-call staging (hcm_forward_policy_host)
@@ -541,9 +541,9 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
     plan_bert(st_bert_);
     plan_hi_tail(st_pre_, st_hi_tail_);
     // stand-alone cross-modal stage on caller tensors (BASELINE.json configs[2])
-    cm_bert_in_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(shp.instr_rows == 1 ? 1 : B) * shp.L * 768 * 2));
-    cm_kv_in_ = reinterpret_cast<bf16*>(alloc(2ull * B * 16 * 256 * 2));
-    cm_out_ = reinterpret_cast<bf16*>(alloc(static_cast<size_t>(B) * 512 * 2));
+    cm_bert_in_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(shp.instr_rows == 1 ? 1 : B) * shp.L * 768 * 2));
+    cm_kv_in_ = reinterpret_cast<h16*>(alloc(2ull * B * 16 * 256 * 2));
+    cm_out_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 512 * 2));
     plan_cross_modal(st_cm_only_, cm_bert_in_, cm_kv_in_, cm_out_, 512);
   }
   if (have_lo_) plan_lo_tail(st_lo_tail_);
@@ -726,17 +726,17 @@ bool Engine::get_buffer(const std::string& name, void** ptr, int* dtype, std::ve
   if (!planned_) return false;
   const int B = shp_.B, L = shp_.L;
   const int R = shp_.instr_rows == 1 ? 1 : B;
-  if (name == "rgb_tokens") { *ptr = tokens_r_; *dtype = 1; *shape = {B, 16, 2112}; return true; }
-  if (name == "rgb_cellmean") { *ptr = cellmean_r_; *dtype = 1; *shape = {B, 2112}; return true; }
-  if (name == "rgb_gmean") { *ptr = gmean_r_; *dtype = 1; *shape = {B, 2048}; return true; }
-  if (name == "rgb_layer4") { *ptr = rgb_feat_; *dtype = 1; *shape = {B, rgb_fh_, rgb_fw_, 2048}; return true; }
-  if (name == "depth_tokens") { *ptr = tokens_d_; *dtype = 1; *shape = {B, 16, 192}; return true; }
-  if (name == "bert") { *ptr = bert_out_; *dtype = 1; *shape = {R, L, 768}; return true; }
-  if (name == "vla_tokens") { *ptr = vla_tokens_; *dtype = 1; *shape = {2, B, L, 256}; return true; }
-  if (name == "kv_in") { *ptr = kvin_; *dtype = 1; *shape = {2, B * 16, 256}; return true; }
-  if (name == "hi_rnn_in") { *ptr = concat_hi_; *dtype = 1; *shape = {B, 896}; return true; }
+  if (name == "rgb_tokens") { *ptr = tokens_r_; *dtype = RVB_H16_CODE; *shape = {B, 16, 2112}; return true; }
+  if (name == "rgb_cellmean") { *ptr = cellmean_r_; *dtype = RVB_H16_CODE; *shape = {B, 2112}; return true; }
+  if (name == "rgb_gmean") { *ptr = gmean_r_; *dtype = RVB_H16_CODE; *shape = {B, 2048}; return true; }
+  if (name == "rgb_layer4") { *ptr = rgb_feat_; *dtype = RVB_H16_CODE; *shape = {B, rgb_fh_, rgb_fw_, 2048}; return true; }
+  if (name == "depth_tokens") { *ptr = tokens_d_; *dtype = RVB_H16_CODE; *shape = {B, 16, 192}; return true; }
+  if (name == "bert") { *ptr = bert_out_; *dtype = RVB_H16_CODE; *shape = {R, L, 768}; return true; }
+  if (name == "vla_tokens") { *ptr = vla_tokens_; *dtype = RVB_H16_CODE; *shape = {2, B, L, 256}; return true; }
+  if (name == "kv_in") { *ptr = kvin_; *dtype = RVB_H16_CODE; *shape = {2, B * 16, 256}; return true; }
+  if (name == "hi_rnn_in") { *ptr = concat_hi_; *dtype = RVB_H16_CODE; *shape = {B, 896}; return true; }
   if (name == "hi_rnn_out") { *ptr = y_hi_; *dtype = 0; *shape = {B, 512}; return true; }
-  if (name == "lo_rnn_in") { *ptr = lo_in_; *dtype = 1; *shape = {B, 416}; return true; }
+  if (name == "lo_rnn_in") { *ptr = lo_in_; *dtype = RVB_H16_CODE; *shape = {B, 416}; return true; }
   if (name == "lo_rnn_out") { *ptr = y_lo_; *dtype = 0; *shape = {B, 512}; return true; }
   return false;
 }

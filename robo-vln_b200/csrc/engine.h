@@ -89,19 +89,19 @@ class Engine {
 
  private:
   const WTensor& W(const std::string& name, int dtype, std::initializer_list<int64_t> shape) const;
-  const bf16* Wb(const std::string& n, std::initializer_list<int64_t> s) const;
+  const h16* Wb(const std::string& n, std::initializer_list<int64_t> s) const;
   const float* Wf(const std::string& n, std::initializer_list<int64_t> s) const;
   void* alloc(size_t bytes);
   float* new_stats(int G);
   void add_gemm(Stage& st, const ConvGemm& g, int force_bn = 0);
   static void label(Stage& st, const std::string& prefix);
-  static ConvGemm linear(const bf16* in, int64_t M, int K, int64_t lda, const bf16* w, int N, const float* bias, int act,
-                         void* out, int64_t ldc, int out_f32, const bf16* res = nullptr, int64_t ldr = 0,
+  static ConvGemm linear(const h16* in, int64_t M, int K, int64_t lda, const h16* w, int N, const float* bias, int act,
+                         void* out, int64_t ldc, int out_f32, const h16* res = nullptr, int64_t ldr = 0,
                          int res_rows = 0);
   void plan_rgb_trunk(const std::string& ns, Stage& st);
   void plan_depth_trunk(const std::string& ns, Stage& st);
   void plan_bert(Stage& st);
-  void plan_cross_modal(Stage& st, const bf16* bert, const bf16* kvin, bf16* out, int64_t out_pitch);
+  void plan_cross_modal(Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch);
   void plan_hi_tail(Stage& pre, Stage& st);
   void plan_lo_tail(Stage& st);
 
@@ -113,16 +113,16 @@ class Engine {
   std::vector<std::unique_ptr<GemmTcPlan>> gemms_;
 
   // planned buffers
-  bf16 *tokens_r_ = nullptr, *cellmean_r_ = nullptr, *gmean_r_ = nullptr, *tokens_d_ = nullptr;
-  bf16* rgb_feat_ = nullptr;
+  h16 *tokens_r_ = nullptr, *cellmean_r_ = nullptr, *gmean_r_ = nullptr, *tokens_d_ = nullptr;
+  h16* rgb_feat_ = nullptr;
   int rgb_fh_ = 0, rgb_fw_ = 0;
   float* gn_stats_arena_ = nullptr;
   size_t gn_stats_cap_ = 0, gn_stats_used_ = 0;
-  bf16 *bert_out_ = nullptr, *kvin_ = nullptr, *concat_hi_ = nullptr, *lo_in_ = nullptr, *vla_tokens_ = nullptr;
+  h16 *bert_out_ = nullptr, *kvin_ = nullptr, *concat_hi_ = nullptr, *lo_in_ = nullptr, *vla_tokens_ = nullptr;
   float *gx_hi_ = nullptr, *y_hi_ = nullptr, *hscr_hi_ = nullptr, *gx_lo_ = nullptr, *y_lo_ = nullptr, *hscr_lo_ = nullptr;
   float *logits_buf_ = nullptr, *act_buf_ = nullptr, *stop_buf_ = nullptr, *hc_hi_buf_ = nullptr, *hc_lo_buf_ = nullptr;
   int64_t* subgoal_buf_ = nullptr;
-  bf16 *cm_bert_in_ = nullptr, *cm_kv_in_ = nullptr, *cm_out_ = nullptr;
+  h16 *cm_bert_in_ = nullptr, *cm_kv_in_ = nullptr, *cm_out_ = nullptr;
   float *stage_rgb_ = nullptr, *stage_depth_ = nullptr, *stage_instr_ = nullptr, *stage_masks_ = nullptr,
         *stage_hc_hi_ = nullptr, *stage_hc_lo_ = nullptr;
 

@@ -10,7 +10,7 @@ namespace rvb {
 namespace {
 
 struct SimtParams {
-  const bf16* in; const bf16* w; const float* bias; const bf16* res; void* out;
+  const h16* in; const h16* w; const float* bias; const h16* res; void* out;
   int NB, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo;
   long long in_pitch, ldr, ldc, M;
   int res_rows, act, out_f32;
@@ -31,20 +31,20 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
     for (int s = 0; s < p.KW; ++s) {
       const int w = wo * p.stride + s - p.pad;
       if (w < 0 || w >= p.W) continue;
-      const bf16* a = p.in + ((static_cast<long long>(img) * p.H + h) * p.W + w) * p.in_pitch;
-      const bf16* b = p.w + n * Ktot + static_cast<long long>(r * p.KW + s) * p.Cin;
-      for (int c = 0; c < p.Cin; ++c) acc = fmaf(__bfloat162float(a[c]), __bfloat162float(b[c]), acc);
+      const h16* a = p.in + ((static_cast<long long>(img) * p.H + h) * p.W + w) * p.in_pitch;
+      const h16* b = p.w + n * Ktot + static_cast<long long>(r * p.KW + s) * p.Cin;
+      for (int c = 0; c < p.Cin; ++c) acc = fmaf(from_h16(a[c]), from_h16(b[c]), acc);
     }
   }
   if (p.bias != nullptr) acc += p.bias[n];
   if (p.res != nullptr) {
     const long long rr = p.res_rows > 0 ? (m % p.res_rows) : m;
-    acc += __bfloat162float(p.res[rr * p.ldr + n]);
+    acc += from_h16(p.res[rr * p.ldr + n]);
   }
   if (p.act == ACT_RELU) acc = fmaxf(acc, 0.0f);
   else if (p.act == ACT_GELU) acc = gelu_erf(acc);
   if (p.out_f32) reinterpret_cast<float*>(p.out)[m * p.ldc + n] = acc;
-  else reinterpret_cast<bf16*>(p.out)[m * p.ldc + n] = __float2bfloat16_rn(acc);
+  else reinterpret_cast<h16*>(p.out)[m * p.ldc + n] = to_h16(acc);
 }
 
 }  // namespace

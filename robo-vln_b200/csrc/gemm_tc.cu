@@ -9,17 +9,17 @@
 //
 //   out[m, n] = act( sum_{tap, c} A(m, tap, c) * W[n, tap*Cin + c] + bias[n] + res[m, n] )
 //
-// * A operand: NHWC bf16 activations read straight from the tensor by TMA -- no im2col
+// * A operand: NHWC h16 activations read straight from the tensor by TMA -- no im2col
 //   buffer.  For a KHxKW filter the K loop walks (tap, 64-channel block); each step is one
 //   4-D box load (64 ch, Wo, th, nb) whose start coordinate is shifted by the tap offset,
 //   with TMA out-of-bounds zero fill providing the padding and elementStrides providing the
 //   convolution stride.  Because an M tile is a set of full output rows, the box lands in
 //   shared memory exactly as the 128-row, K-major, 128B-swizzled tile UMMA expects.
-// * B operand: weights [Cout, KH*KW*Cin] bf16, K-major, 2-D TMA boxes (64, BN).
+// * B operand: weights [Cout, KH*KW*Cin] h16, K-major, 2-D TMA boxes (64, BN).
 // * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16, fp32 accumulators in TMEM,
 //   double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // * Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 =
-//   epilogue (tcgen05.ld -> bias / residual / ReLU|GELU -> bf16|fp32 global store).
+//   epilogue (tcgen05.ld -> bias / residual / ReLU|GELU -> h16|fp32 global store).
 #include "common.cuh"
 #include "rvb.h"
 
@@ -133,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+      constexpr uint32_t idesc = umma_idesc_h16(BLOCK_M, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -149,8 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+            // advance 16 h16 = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
+            umma_f16kind(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
                       static_cast<uint32_t>((kb | k) != 0));
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -183,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
-      const bf16* res_row = nullptr;
+      const h16* res_row = nullptr;
       if (p.res != nullptr && row_ok) {
         const long long rr = (p.res_rows > 0) ? (m % p.res_rows) : m;
         res_row = p.res + rr * p.ldr;
@@ -220,10 +220,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n + j < p.N) {
               const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res_row + n + j));
               float2 t;
-              t = unpack_bf16x2(r4.x); f[j] += t.x; f[j + 1] += t.y;
-              t = unpack_bf16x2(r4.y); f[j + 2] += t.x; f[j + 3] += t.y;
-              t = unpack_bf16x2(r4.z); f[j + 4] += t.x; f[j + 5] += t.y;
-              t = unpack_bf16x2(r4.w); f[j + 6] += t.x; f[j + 7] += t.y;
+              t = unpack_h2(r4.x); f[j] += t.x; f[j + 1] += t.y;
+              t = unpack_h2(r4.y); f[j + 2] += t.x; f[j + 3] += t.y;
+              t = unpack_h2(r4.z); f[j + 4] += t.x; f[j + 5] += t.y;
+              t = unpack_h2(r4.w); f[j + 6] += t.x; f[j + 7] += t.y;
             }
           }
         }
@@ -241,15 +241,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           }
         } else {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + m * p.ldc + n;
+          h16* o = reinterpret_cast<h16*>(p.out) + m * p.ldc + n;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (n + j < p.N) {
               uint4 q;
-              q.x = pack_bf16x2(f[j], f[j + 1]);
-              q.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              q.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              q.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              q.x = pack_h2(f[j], f[j + 1]);
+              q.y = pack_h2(f[j + 2], f[j + 3]);
+              q.z = pack_h2(f[j + 4], f[j + 5]);
+              q.w = pack_h2(f[j + 6], f[j + 7]);
               *reinterpret_cast<uint4*>(o + j) = q;
             }
           }
@@ -303,7 +303,7 @@ void encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* di
     es[i] = estr[i];
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+  CUresult r = encode_tiled_fn()(map, (RVB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), static_cast<cuuint32_t>(rank),
                                  const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

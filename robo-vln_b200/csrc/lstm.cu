@@ -16,15 +16,15 @@ namespace {
 
 constexpr int HID = 512;
 constexpr int UNITS_PER_CTA = 8;               // 8 hidden units x 4 gates = 32 rows = 32 lanes
-constexpr int WPITCH = HID + 2;                // bf16 elements; +2 -> row-to-row bank shift of 1 word
+constexpr int WPITCH = HID + 2;                // h16 elements; +2 -> row-to-row bank shift of 1 word
 
-__global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict__ gx, const bf16* __restrict__ whh,
+__global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict__ gx, const h16* __restrict__ whh,
                                                         const float* __restrict__ masks, int mask_stride,
                                                         const float* __restrict__ h_prev,
                                                         const float* __restrict__ c_prev, float* __restrict__ h_next,
                                                         float* __restrict__ c_next, float* __restrict__ h_final,
                                                         float* __restrict__ y, int t, int N) {
-  __shared__ __align__(16) bf16 sW[32 * WPITCH];
+  __shared__ __align__(16) h16 sW[32 * WPITCH];
   __shared__ int s_flag;
   const int u0 = blockIdx.x * UNITS_PER_CTA;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict_
     float acc = 0.0f;
 #pragma unroll 8
     for (int k2 = 0; k2 < HID / 2; ++k2) {
-      const float2 w2 = unpack_bf16x2(wrow[k2]);
+      const float2 w2 = unpack_h2(wrow[k2]);
       const float2 h2 = *reinterpret_cast<const float2*>(hp + 2 * k2);
       acc = fmaf(w2.x, h2.x, acc);
       acc = fmaf(w2.y, h2.y, acc);
@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict_
 
 }  // namespace
 
-// gx [T*N, 2048] fp32 (biases included), whh bf16 [2048, 512], masks fp32 (element (t*N+n)*mask_stride),
+// gx [T*N, 2048] fp32 (biases included), whh h16 [2048, 512], masks fp32 (element (t*N+n)*mask_stride),
 // hc_in / hc_out fp32 [2, N, 512] (must not alias), h_scratch fp32 [2, N, 512], y fp32 [T*N, 512].
-void lstm_forward(const float* gx, const bf16* whh, const float* masks, int mask_stride, const float* hc_in,
+void lstm_forward(const float* gx, const h16* whh, const float* masks, int mask_stride, const float* hc_in,
                   float* hc_out, float* h_scratch, float* y, int T, int N, cudaStream_t s) {
   RVB_CHECK(T >= 1 && N >= 1, "lstm: empty batch");
   RVB_CHECK(hc_in != hc_out, "lstm: hidden state in/out must not alias");

@@ -4,15 +4,17 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <stdexcept>
 #include <string>
 
+#include "h16.h"
+
 namespace rvb {
 
-using bf16 = __nv_bfloat16;
 
 struct Error : public std::runtime_error {
   int code;
@@ -36,24 +38,24 @@ enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 // ---------------------------------------------------------------------------------------
 // Convolution-as-GEMM problem:  out[m, n] = act( sum_{tap,c} A(m,tap,c) * W[n, tap*Cin + c] + bias[n] + res[m, n] )
-//   A is an NHWC bf16 tensor [NB, H, W, Cin] (row pitch in_pitch elements per pixel),
+//   A is an NHWC h16 tensor [NB, H, W, Cin] (row pitch in_pitch elements per pixel),
 //   m enumerates output pixels (n, ho, wo) row-major; a plain GEMM is the case H=1, W=M, 1x1.
 // ---------------------------------------------------------------------------------------
 struct ConvGemm {
   // input
-  const bf16* in = nullptr;
+  const h16* in = nullptr;
   int NB = 1, H = 1, W = 1, Cin = 0;
   int64_t in_pitch = 0;          // elements between consecutive pixels (>= Cin, multiple of 8)
   // filter
-  const bf16* w = nullptr;       // [Cout, KH*KW*Cin] K-major, k = (r*KW + s)*Cin + c
+  const h16* w = nullptr;       // [Cout, KH*KW*Cin] K-major, k = (r*KW + s)*Cin + c
   int Cout = 0, KH = 1, KW = 1, stride = 1, pad = 0;
   // epilogue
   const float* bias = nullptr;   // [Cout] or null
-  const bf16* res = nullptr;     // residual [res_rows, ldr] or null; row = m % res_rows
+  const h16* res = nullptr;     // residual [res_rows, ldr] or null; row = m % res_rows
   int64_t ldr = 0;
   int res_rows = 0;              // 0 -> M
   int act = ACT_NONE;
-  void* out = nullptr;           // bf16 or f32, [M, ldc]
+  void* out = nullptr;           // h16 or f32, [M, ldc]
   int64_t ldc = 0;
   int out_f32 = 0;
   // derived
@@ -78,7 +80,7 @@ struct GemmTcParams {
   int m_tiles, n_tiles;
   uint32_t a_bytes;  // bytes one A box delivers (tile_rows * 128)
   const float* bias;
-  const bf16* res;
+  const h16* res;
   long long ldr;
   int res_rows;
   int act;
@@ -107,41 +109,41 @@ void gemm_simt_launch(const ConvGemm& g, cudaStream_t stream);
 bool use_simt_gemm();
 
 // elementwise.cu
-void rgb_stem_im2col(const float* rgb, bf16* out, int NB, int H, int W, int Kpitch, cudaStream_t s);
-void maxpool3x3s2(const bf16* in, bf16* out, int NB, int H, int W, int C, cudaStream_t s);
-void depth_stem_conv(const float* depth, const float* w, bf16* out, int NB, int H, int W, cudaStream_t s);
-void gn_stats(const bf16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s);
+void rgb_stem_im2col(const float* rgb, h16* out, int NB, int H, int W, int Kpitch, cudaStream_t s);
+void maxpool3x3s2(const h16* in, h16* out, int NB, int H, int W, int C, cudaStream_t s);
+void depth_stem_conv(const float* depth, const float* w, h16* out, int NB, int H, int W, cudaStream_t s);
+void gn_stats(const h16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s);
 struct GnApply {
-  const bf16* x; const float* stats; const float* gamma; const float* beta;
+  const h16* x; const float* stats; const float* gamma; const float* beta;
   int NB, HW, C, G;
   int relu;
-  int res_mode;                  // 0 none, 1 plain bf16 residual, 2 group-normalised residual
-  const bf16* res; const float* res_stats; const float* res_gamma; const float* res_beta;
-  bf16* out; int64_t out_pitch;  // elements per pixel in the output (>= C)
+  int res_mode;                  // 0 none, 1 plain h16 residual, 2 group-normalised residual
+  const h16* res; const float* res_stats; const float* res_gamma; const float* res_beta;
+  h16* out; int64_t out_pitch;  // elements per pixel in the output (>= C)
 };
 void gn_apply(const GnApply& a, cudaStream_t s);
-void rgb_pool(const bf16* feat, int NB, int H, int W, int C, bf16* tokens, int64_t tok_pitch, bf16* cellmean,
-              int64_t cm_pitch, bf16* gmean, cudaStream_t s);
-void fill_spatial_embedding(const float* emb_flat, bf16* tokens, int NB, int64_t tok_pitch, int col0, bf16* cellmean,
+void rgb_pool(const h16* feat, int NB, int H, int W, int C, h16* tokens, int64_t tok_pitch, h16* cellmean,
+              int64_t cm_pitch, h16* gmean, cudaStream_t s);
+void fill_spatial_embedding(const float* emb_flat, h16* tokens, int NB, int64_t tok_pitch, int col0, h16* cellmean,
                             int64_t cm_pitch, cudaStream_t s);
 void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, int R, int L, const float* word,
-                   const float* pos, const float* type0, const float* g, const float* b, bf16* out, cudaStream_t s);
+                   const float* pos, const float* type0, const float* g, const float* b, h16* out, cudaStream_t s);
 void layernorm_rows(const float* x, int M, int D, const float* g, const float* b, float eps, const float* pe, int pe_rows,
-                    bf16* out, cudaStream_t s);
-void token_mean(const bf16* x, int n_mod, int B, int L, int D, bf16* out, int64_t out_pitch, int64_t mod_stride,
+                    h16* out, cudaStream_t s);
+void token_mean(const h16* x, int n_mod, int B, int L, int D, h16* out, int64_t out_pitch, int64_t mod_stride,
                 cudaStream_t s);
-void sub_task_embed(const int64_t* ids, const float* table, int B, bf16* out, int64_t out_pitch, cudaStream_t s);
+void sub_task_embed(const int64_t* ids, const float* table, int B, h16* out, int64_t out_pitch, cudaStream_t s);
 void heads_linear(const float* y, int M, int K, const float* w, const float* b, int n_out, float* out, cudaStream_t s);
 void argmax_rows(const float* x, int M, int n, int64_t* out, cudaStream_t s);
 void sinusoid_table(float* pe, int L, int D, cudaStream_t s);
 
 // attention.cu
-void bert_self_attention(const bf16* qkv, bf16* ctx, int R, int L, int heads, cudaStream_t s);
-void vla_cross_attention(const bf16* q, const bf16* kv, bf16* ctx, int B, int L, int n_mod, int q_shared,
+void bert_self_attention(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s);
+void vla_cross_attention(const h16* q, const h16* kv, h16* ctx, int B, int L, int n_mod, int q_shared,
                          cudaStream_t s);
 
 // lstm.cu
-void lstm_forward(const float* gx, const bf16* whh, const float* masks, int mask_stride, const float* hc_in,
+void lstm_forward(const float* gx, const h16* whh, const float* masks, int mask_stride, const float* hc_in,
                   float* hc_out, float* h_scratch, float* y, int T, int N, cudaStream_t s);
 
 }  // namespace rvb

@@ -15,7 +15,7 @@ from . import _lib
 from . import weight_prep as WP
 from ._lib import HcmShape, check
 
-_DT = {torch.float32: 0, torch.bfloat16: 1, torch.int64: 2}
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.int64: 2, torch.float16: 3}
 
 # most recent runtime per device still waiting for its other half (hi <-> lo pairing)
 _open_runtimes: Dict[Tuple[str, int], "HcmRuntime"] = {}
@@ -30,7 +30,9 @@ class HcmRuntime:
         if device.type != "cuda":
             raise RuntimeError(
                 "robovln_b200 runs on a CUDA device only (there is no CPU path); move the module with .to('cuda')")
-        self.lib = _lib.load()
+        self.dtype_name = _lib.default_dtype()        # "fp16" (default) or "bf16" via ROBOVLN_DTYPE
+        self.lib = _lib.load(dtype=self.dtype_name)
+        self.h16 = {"fp16": torch.float16, "bf16": torch.bfloat16}[self.dtype_name]
         self.device = device
         self.handle = ctypes.c_void_p()
         with torch.cuda.device(device):
@@ -86,6 +88,7 @@ class HcmRuntime:
         dev = self.device
         tensors: Dict[str, torch.Tensor] = {}
         shares = False
+        WP.set_h16(self.dtype_name)
         with torch.no_grad():
             sd_hi = hi.state_dict() if hi is not None else None
             sd_lo = lo.state_dict() if lo is not None else None
@@ -293,7 +296,7 @@ class HcmRuntime:
         check(self.lib.hcm_get_buffer(self.handle, name.encode(), ctypes.byref(ptr), ctypes.byref(dt), ctypes.byref(nd),
                                       shape), f"hcm_get_buffer({name})")
         shp = [int(shape[i]) for i in range(nd.value)]
-        dtype = {0: torch.float32, 1: torch.bfloat16, 2: torch.int64}[dt.value]
+        dtype = {0: torch.float32, 1: torch.bfloat16, 2: torch.int64, 3: torch.float16}[dt.value]
         numel = 1
         for s in shp:
             numel *= s

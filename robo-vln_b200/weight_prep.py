@@ -27,8 +27,21 @@ import torch
 _STAGES = ((3, 1), (4, 2), (6, 2), (3, 2))
 
 
+# 16-bit type of the engine the tensors are prepared for (set by the runtime before packing):
+# torch.float16 for librobovln_b200.so, torch.bfloat16 for librobovln_b200_bf16.so
+H16 = {"dtype": torch.float16}
+
+
+def set_h16(dtype_name: str) -> None:
+    H16["dtype"] = {"fp16": torch.float16, "bf16": torch.bfloat16}[dtype_name]
+
+
 def _bf(t: torch.Tensor, dev) -> torch.Tensor:
-    return t.detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous()
+    """fp32 -> the engine's 16-bit operand type (fp16 saturates instead of overflowing)."""
+    t = t.detach().to(device=dev, dtype=torch.float32)
+    if H16["dtype"] == torch.float16:
+        t = t.clamp(-65504.0, 65504.0)
+    return t.to(H16["dtype"]).contiguous()
 
 
 def _f32(t: torch.Tensor, dev) -> torch.Tensor:

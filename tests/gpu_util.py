@@ -1,4 +1,4 @@
-"""Helpers for the -m gpu tests: ctypes calls into librobovln_b200.so with torch tensors."""
+"""Helpers for the -m gpu tests: ctypes calls into librobovln_b200*.so with torch tensors."""
 import ctypes
 
 import torch
@@ -6,9 +6,17 @@ import torch
 import robovln_b200  # noqa: F401  (alias package; makes robovln_b200._lib importable)
 from robovln_b200 import _lib
 
+H16 = {"fp16": torch.float16, "bf16": torch.bfloat16}
+# relative-to-max tolerance of a 16-bit OUTPUT tensor (half an ulp at the top of the range, x2)
+OUT_TOL = {"fp16": 2e-3, "bf16": 1e-2}
 
-def lib():
-    return _lib.load()
+
+def lib(dtype="fp16"):
+    return _lib.load(dtype=dtype)
+
+
+def check(rc, what, dtype="fp16"):
+    _lib.check(rc, what, lib(dtype))
 
 
 def P(t):
@@ -19,9 +27,14 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def dtype_name(t: torch.Tensor) -> str:
+    return "fp16" if t.dtype == torch.float16 else "bf16"
+
+
 def conv_gemm(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows=0, act=0, out_f32=False,
               force_bn=0, impl=0, ldc=None, out=None):
-    """x: [NB,H,W,Cin] bf16 (contiguous), w: [Cout, KH*KW*Cin] bf16 -> out [M, Cout]."""
+    """x: [NB,H,W,Cin] h16 (contiguous), w: [Cout, KH*KW*Cin] h16 -> out [M, Cout]."""
+    dt = dtype_name(x)
     NB, H, W, Cin = x.shape
     Cout = w.shape[0]
     Ho = (H + 2 * pad - KH) // stride + 1
@@ -30,17 +43,17 @@ def conv_gemm(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_row
     if ldc is None:
         ldc = Cout
     if out is None:
-        out = torch.zeros((M, ldc), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
-    rc = lib().rvb_conv_gemm(P(x), NB, H, W, Cin, Cin, P(w), Cout, KH, KW, stride, pad, P(bias), P(res),
-                             0 if res is None else res.shape[-1], res_rows, act, P(out), ldc, int(out_f32), force_bn,
-                             impl, stream())
-    _lib.check(rc, "rvb_conv_gemm")
+        out = torch.zeros((M, ldc), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
+    rc = lib(dt).rvb_conv_gemm(P(x), NB, H, W, Cin, Cin, P(w), Cout, KH, KW, stride, pad, P(bias), P(res),
+                               0 if res is None else res.shape[-1], res_rows, act, P(out), ldc, int(out_f32), force_bn,
+                               impl, stream())
+    check(rc, "rvb_conv_gemm", dt)
     torch.cuda.synchronize()
     return out
 
 
 def conv_ref(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows=0, act=0):
-    """fp32 torch reference on the same bf16-rounded operands."""
+    """fp32 torch reference on the same 16-bit-rounded operands."""
     NB, H, W, Cin = x.shape
     Cout = w.shape[0]
     w4 = w.float().view(Cout, KH, KW, Cin).permute(0, 3, 1, 2).contiguous()

@@ -104,7 +104,7 @@ def test_weight_prep_numerics():
     t.update(WP.prep_depth_trunk(sd, "hi", "cpu"))
     t.update(WP.prep_bert(sd, "cpu"))
     t.update(WP.prep_hi_tail(sd, "cpu"))
-    assert t["hi.rgb.stem.w"].shape == (64, 160) and t["hi.rgb.stem.w"].dtype == torch.bfloat16
+    assert t["hi.rgb.stem.w"].shape == (64, 160) and t["hi.rgb.stem.w"].dtype == torch.float16   # default build
     assert torch.all(t["hi.rgb.stem.w"][:, 147:] == 0)
     assert t["hi.rgb.l4.0.c2.w"].shape == (512, 9 * 512) and t["hi.depth.comp.w"].shape == (128, 9 * 1024)
     assert t["hi.bert.3.qkv.w"].shape == (2304, 768) and t["hi.vla.fc_kv.w"].shape == (512, 256)
