@@ -283,7 +283,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": "obs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": rt.dtype_name, "data": "synthetic",
             "config": {
                 "workload": "cfg2: HCM policy forward (hi -> argmax -> lo), batch=64/GPU rollout-shaped (N=64,T=1), "
                             "256x256 RGB + 256x256 depth, 64 distinct 80-token instructions, random-init weights",

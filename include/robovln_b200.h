@@ -140,7 +140,12 @@ int hcm_copy_buffer(hcm_engine* e, const char* name, void* dst_dev, size_t bytes
 int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in_pitch,
                   const void* w_bf16, int Cout, int KH, int KW, int stride, int pad,
                   const float* bias, const void* res_bf16, int64_t ldr, int res_rows, int act,
-                  void* out, int64_t ldc, int out_f32, int force_bn, int impl, void* stream);
+                  void* out, int64_t ldc, int out_f32, int force_bn, int impl, int window,
+                  int64_t win_row_pitch, void* stream);
+/* window != 0 ("window mode", the RGB stem): `in` is the zero-padded [NB,H,win_row_pitch/8,8] image
+ * written by rvb_rgb_pad_convert, W is the OUTPUT width, KW must be 1 and Cin 64 (8 px x 8 ch per
+ * filter row), weights [Cout, KH*64]. */
+int rvb_rgb_pad_convert(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream);
 int rvb_groupnorm(const void* x_bf16, float* stats /* [NB,G,2] zeroed by the call */, const float* gamma,
                   const float* beta, int NB, int HW, int C, int G, int relu, const void* res_bf16,
                   void* out_bf16, int64_t out_pitch, void* stream);

@@ -47,7 +47,8 @@ SYMBOLS = {
     "hcm_copy_buffer": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),
     "rvb_conv_gemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                               c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int,
-                              c_void_p]),
+                              c_int, c_int64, c_void_p]),
+    "rvb_rgb_pad_convert": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rvb_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_int64, c_void_p]),
     "rvb_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p]),

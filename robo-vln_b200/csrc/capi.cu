@@ -214,9 +214,11 @@ int hcm_copy_buffer(hcm_engine* e, const char* name, void* dst_dev, size_t bytes
 // ---- kernel-level entry points -------------------------------------------------------------
 int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in_pitch, const void* w_bf16, int Cout,
                   int KH, int KW, int stride, int pad, const float* bias, const void* res_bf16, int64_t ldr,
-                  int res_rows, int act, void* out, int64_t ldc, int out_f32, int force_bn, int impl, void* stream) {
+                  int res_rows, int act, void* out, int64_t ldc, int out_f32, int force_bn, int impl, int window,
+                  int64_t win_row_pitch, void* stream) {
   return guarded([&] {
     ConvGemm g;
+    g.window = window; g.win_row_pitch = win_row_pitch;
     g.in = B16(in_bf16); g.NB = NB; g.H = H; g.W = W; g.Cin = Cin; g.in_pitch = in_pitch;
     g.w = B16(w_bf16); g.Cout = Cout; g.KH = KH; g.KW = KW; g.stride = stride; g.pad = pad;
     g.bias = bias; g.res = B16(res_bf16); g.ldr = ldr; g.res_rows = res_rows; g.act = act;
@@ -266,6 +268,10 @@ int rvb_maxpool3x3s2(const void* in_bf16, void* out_bf16, int NB, int H, int W, 
 
 int rvb_rgb_stem_im2col(const float* rgb, void* out_bf16, int NB, int H, int W, int Kpitch, void* stream) {
   return guarded([&] { rgb_stem_im2col(rgb, B16(out_bf16), NB, H, W, Kpitch, S(stream)); });
+}
+
+int rvb_rgb_pad_convert(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream) {
+  return guarded([&] { rgb_pad_convert(rgb, B16(out_h16), NB, H, W, Wp, S(stream)); });
 }
 
 int rvb_depth_stem(const float* depth, const float* w, void* out_bf16, int NB, int H, int W, void* stream) {

@@ -68,6 +68,31 @@ __global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------
+// RGB stem pre-pass: [NB,H,W,3] fp32 0..255 -> zero-padded [NB, H+6, Wp, 8] 16-bit image
+// (3 px of padding on every side, channels 3..7 zero, /255 folded in, resnet_encoders.py:213).
+// The 7x7 stride-2 conv then runs on the tensor cores in "window" mode (gemm_tc.cu) with no
+// im2col buffer.  One thread per padded pixel: 12 B read, 16 B written.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rgb_pad_convert_kernel(const float* __restrict__ rgb, h16* __restrict__ out,
+                                                              int NB, int H, int W, int Hp, int Wp) {
+  const long long total = static_cast<long long>(NB) * Hp * Wp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xp = static_cast<int>(i % Wp);
+    const int yp = static_cast<int>((i / Wp) % Hp);
+    const int img = static_cast<int>(i / (static_cast<long long>(Wp) * Hp));
+    const int x = xp - 3, y = yp - 3;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+      const float* src = rgb + ((static_cast<long long>(img) * H + y) * W + x) * 3;
+      q.x = pack_h2(__ldg(src) / 255.0f, __ldg(src + 1) / 255.0f);   // true division, as the reference
+      q.y = pack_h2(__ldg(src + 2) / 255.0f, 0.0f);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = q;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 max pooling, NHWC h16
 // ---------------------------------------------------------------------------------------
 __global__ void maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict__ out, int NB, int H, int W, int C,
@@ -507,6 +532,13 @@ void rgb_stem_im2col(const float* rgb, h16* out, int NB, int H, int W, int Kpitc
   const long long M = static_cast<long long>(NB) * Ho * Wo;
   const int blocks = static_cast<int>((M + STEM_PIX - 1) / STEM_PIX);
   rgb_stem_im2col_kernel<<<blocks, 256, STEM_PIX * Kpitch * 2, s>>>(rgb, out, NB, H, W, Ho, Wo, Kpitch);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void rgb_pad_convert(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s) {
+  RVB_CHECK(Wp >= W + 6, "rgb_pad_convert: padded width too small");
+  const long long total = static_cast<long long>(NB) * (H + 6) * Wp;
+  rgb_pad_convert_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(rgb, out, NB, H, W, H + 6, Wp);
   RVB_CUDA(cudaGetLastError());
 }
 

@@ -14,6 +14,7 @@ struct SimtParams {
   int NB, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo;
   long long in_pitch, ldr, ldc, M;
   int res_rows, act, out_f32;
+  int window; long long win_row_pitch;
 };
 
 __global__ void gemm_simt_kernel(const SimtParams p) {
@@ -25,7 +26,15 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   const int img = static_cast<int>(m / (static_cast<long long>(p.Wo) * p.Ho));
   const long long Ktot = static_cast<long long>(p.KH) * p.KW * p.Cin;
   float acc = 0.0f;
-  for (int r = 0; r < p.KH; ++r) {
+  if (p.window) {
+    for (int r = 0; r < p.KH; ++r) {
+      const h16* a = p.in + (static_cast<long long>(img) * p.H + ho * p.stride + r) * p.win_row_pitch +
+                     static_cast<long long>(wo) * p.stride * 8;
+      const h16* b = p.w + n * Ktot + static_cast<long long>(r) * p.Cin;
+      for (int c = 0; c < p.Cin; ++c) acc = fmaf(from_h16(a[c]), from_h16(b[c]), acc);
+    }
+  }
+  for (int r = 0; r < (p.window ? 0 : p.KH); ++r) {
     const int h = ho * p.stride + r - p.pad;
     if (h < 0 || h >= p.H) continue;
     for (int s = 0; s < p.KW; ++s) {
@@ -56,6 +65,7 @@ void gemm_simt_launch(const ConvGemm& g, cudaStream_t stream) {
   p.stride = g.stride; p.pad = g.pad; p.Ho = g.Ho(); p.Wo = g.Wo();
   p.in_pitch = g.in_pitch; p.ldr = g.ldr; p.ldc = g.ldc; p.M = g.M();
   p.res_rows = g.res_rows; p.act = g.act; p.out_f32 = g.out_f32;
+  p.window = g.window; p.win_row_pitch = g.win_row_pitch;
   dim3 block(32, 8);
   const long long gx = (p.M + block.y - 1) / block.y;
   RVB_CHECK(gx < (1ll << 31), "simt gemm: M too large");

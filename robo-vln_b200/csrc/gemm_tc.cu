@@ -9,17 +9,23 @@
 //
 //   out[m, n] = act( sum_{tap, c} A(m, tap, c) * W[n, tap*Cin + c] + bias[n] + res[m, n] )
 //
-// * A operand: NHWC h16 activations read straight from the tensor by TMA -- no im2col
+// * A operand: NHWC 16-bit activations read straight from the tensor by TMA -- no im2col
 //   buffer.  For a KHxKW filter the K loop walks (tap, 64-channel block); each step is one
 //   4-D box load (64 ch, Wo, th, nb) whose start coordinate is shifted by the tap offset,
 //   with TMA out-of-bounds zero fill providing the padding and elementStrides providing the
 //   convolution stride.  Because an M tile is a set of full output rows, the box lands in
 //   shared memory exactly as the 128-row, K-major, 128B-swizzled tile UMMA expects.
-// * B operand: weights [Cout, KH*KW*Cin] h16, K-major, 2-D TMA boxes (64, BN).
+//   "Window" mode (the 7x7 stride-2 RGB stem): the input is a zero-padded NHW8 image and the
+//   tensor map strides the W dimension by 2 pixels (32 B) while each row of the box reads 64
+//   contiguous elements = 8 pixels x 8 channels, i.e. overlapping windows: one tap ROW of the
+//   7x7 filter per K block, 7 K blocks in all.
+// * B operand: weights [Cout, KH*KW*Cin], K-major, 2-D TMA boxes (64, BN).
 // * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16, fp32 accumulators in TMEM,
 //   double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// * Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 =
-//   epilogue (tcgen05.ld -> bias / residual / ReLU|GELU -> h16|fp32 global store).
+// * Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+//   warps 2..9 = epilogue in two groups of four (one warp per TMEM lane quadrant); the groups
+//   take alternate 128-byte column chunks: tcgen05.ld -> bias / residual / ReLU|GELU ->
+//   128B-swizzled smem staging -> TMA store (coalesced, clipped at the tensor edges).
 #include "common.cuh"
 #include "rvb.h"
 
@@ -35,22 +41,61 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
+constexpr int STAGING_BYTES = 2 * 16384;              // one 128 x 128B chunk buffer per epilogue group
+constexpr int SMEM_STAGE_BUDGET = 196608;             // 192 KiB of pipeline stages
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int STAGES = (SMEM_STAGE_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_STAGE_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: powers of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+RVB_DEVICE void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// bias + residual + activation on 32 consecutive columns of one output row
+RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, const h16* res_row) {
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (n + j < p.N) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
+    }
+  }
+  if (res_row != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (n + j < p.N) {
+        const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res_row + n + j));
+        float2 t;
+        t = unpack_h2(r4.x); f[j] += t.x; f[j + 1] += t.y;
+        t = unpack_h2(r4.y); f[j + 2] += t.x; f[j + 3] += t.y;
+        t = unpack_h2(r4.z); f[j + 4] += t.x; f[j + 5] += t.y;
+        t = unpack_h2(r4.w); f[j + 6] += t.x; f[j + 7] += t.y;
+      }
+    }
+  }
+  if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmTcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const GemmTcParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
 
@@ -58,7 +103,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint8_t* smem_c = smem + STAGES * C::STAGE_BYTES;  // 2 x 16 KiB staging, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + STAGING_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
@@ -71,13 +117,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -149,9 +196,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 h16 = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
+            // advance 16 elements = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
             umma_f16kind(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                      static_cast<uint32_t>((kb | k) != 0));
+                         static_cast<uint32_t>((kb | k) != 0));
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
@@ -167,17 +214,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ---------------------
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------ epilogue (warps 2..9) ---------------------
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int group = (warp - 2) >> 2;  // 0 or 1: alternate column chunks
+    const int row_in_tile = quad * 32 + lane;
+    const bool leader = (quad == 2 && lane == 0);  // first thread of the group (warps 2 and 6)
+    uint8_t* stage_buf = smem_c + group * 16384;
+    uint8_t* my_row = stage_buf + row_in_tile * 128;
+    const int sw = row_in_tile & 7;
+    // columns per chunk: one 128-byte row segment of the output type
+    const int chunk_cols = p.out_f32 ? 32 : 64;
+    const int n_chunks = BN / chunk_cols;
     int acc = 0;
     uint32_t acc_phase = 0;
+    bool store_pending = false;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles;
       const int nt = tile - mt * p.n_tiles;
-      const int row_in_tile = quad * 32 + lane;
       const long long m = static_cast<long long>(mt) * p.tile_rows + row_in_tile;
       const bool row_ok = (row_in_tile < p.tile_rows) && (m < p.M);
       const int n0 = nt * BN;
+      int img = 0, h0 = 0;
+      if (!p.plain) {
+        if (p.nb == 1) {
+          img = mt / p.tiles_per_img;
+          h0 = (mt - img * p.tiles_per_img) * p.th;
+        } else {
+          img = mt * p.nb;
+        }
+      }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -188,79 +253,112 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long rr = (p.res_rows > 0) ? (m % p.res_rows) : m;
         res_row = p.res + rr * p.ldr;
       }
+
+      if (p.tma_store) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated body below
-        tmem_ld_32x32(taddr + c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 >= BN) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
+        for (int ch = group; ch < n_chunks; ch += 2) {
+          const int c0 = ch * chunk_cols;
+          const int n = n0 + c0;
+          if (n >= p.N) break;  // uniform across the group
+          // the staging buffer is free once the previous store from it has been read out
+          if (store_pending) {
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(1 + group, 128);
+          }
+          if (p.out_f32) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr + c0, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            epilogue_math(f, p, n, res_row);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t v[32];
+              __syncwarp();
+              tmem_ld_32x32(taddr + c0 + half * 32, v);
+              tmem_ld_wait();
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              epilogue_math(f, p, n + half * 32, res_row);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                q.x = pack_h2(f[8 * j], f[8 * j + 1]);
+                q.y = pack_h2(f[8 * j + 2], f[8 * j + 3]);
+                q.z = pack_h2(f[8 * j + 4], f[8 * j + 5]);
+                q.w = pack_h2(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(my_row + (((half * 4 + j) ^ sw) << 4)) = q;
+              }
+            }
+          }
+          fence_proxy_async();  // make the st.shared visible to the TMA (async proxy)
+          named_bar_sync(1 + group, 128);
+          if (leader) {
+            if (p.plain) tma_store_4d(&tmC, stage_buf, n, mt * BLOCK_M, 0, 0);
+            else tma_store_4d(&tmC, stage_buf, n, 0, h0, img);
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
+        // every TMEM read of this warp for this accumulator has completed (wait::ld above)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      } else {
+        // direct global stores (validation path, ROBOVLN_EPILOGUE=direct): 32-column chunks
+#pragma unroll 1
+        for (int c0 = group * 32; c0 < BN; c0 += 64) {
+          uint32_t v[32];
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-        const int n = n0 + c0;
-        if (row_ok && n < p.N) {
-        float f[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+          const int n = n0 + c0;
+          if (row_ok && n < p.N) {
+            float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            epilogue_math(f, p, n, res_row);
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n + j < p.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              for (int j = 0; j < 32; j += 4) {
+                if (n + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              }
+            } else {
+              h16* o = reinterpret_cast<h16*>(p.out) + m * p.ldc + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (n + j < p.N) {
+                  uint4 q;
+                  q.x = pack_h2(f[j], f[j + 1]);
+                  q.y = pack_h2(f[j + 2], f[j + 3]);
+                  q.z = pack_h2(f[j + 4], f[j + 5]);
+                  q.w = pack_h2(f[j + 6], f[j + 7]);
+                  *reinterpret_cast<uint4*>(o + j) = q;
+                }
+              }
             }
           }
         }
-        if (res_row != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j < p.N) {
-              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res_row + n + j));
-              float2 t;
-              t = unpack_h2(r4.x); f[j] += t.x; f[j + 1] += t.y;
-              t = unpack_h2(r4.y); f[j + 2] += t.x; f[j + 3] += t.y;
-              t = unpack_h2(r4.z); f[j + 4] += t.x; f[j + 5] += t.y;
-              t = unpack_h2(r4.w); f[j + 6] += t.x; f[j + 7] += t.y;
-            }
-          }
-        }
-        if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        } else if (p.act == ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          }
-        } else {
-          h16* o = reinterpret_cast<h16*>(p.out) + m * p.ldc + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j < p.N) {
-              uint4 q;
-              q.x = pack_h2(f[j], f[j + 1]);
-              q.y = pack_h2(f[j + 2], f[j + 3]);
-              q.z = pack_h2(f[j + 4], f[j + 5]);
-              q.w = pack_h2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = q;
-            }
-          }
-        }
-        }  // row_ok
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    // staging smem must stay valid until the last bulk store has read it
+    if (leader && store_pending) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -291,8 +389,8 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-void encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box, const uint32_t* estr) {
+void encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr) {
   cuuint64_t gd[5];
   cuuint64_t gs[4];
   cuuint32_t bx[5];
@@ -303,18 +401,21 @@ void encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* di
     es[i] = estr[i];
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = encode_tiled_fn()(map, (RVB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), static_cast<cuuint32_t>(rank),
-                                 const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_tiled_fn()(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs, bx, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::string msg = "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ") dims=";
     for (int i = 0; i < rank; ++i) msg += std::to_string(dims[i]) + (i + 1 < rank ? "x" : "");
     msg += " box=";
     for (int i = 0; i < rank; ++i) msg += std::to_string(box[i]) + (i + 1 < rank ? "x" : "");
+    msg += " strides=";
+    for (int i = 0; i + 1 < rank; ++i) msg += std::to_string(strides_bytes[i]) + (i + 2 < rank ? "," : "");
     throw Error(static_cast<int>(r), msg);
   }
 }
+
+constexpr CUtensorMapDataType kH16Type = RVB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
 template <int BN>
 void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
@@ -323,8 +424,17 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
     RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<plan.grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(plan.tmA, plan.tmB, plan.p);
+  gemm_tc_kernel<BN><<<plan.grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p);
   RVB_CUDA(cudaGetLastError());
+}
+
+bool use_direct_epilogue() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_EPILOGUE");
+    v = (e != nullptr && std::strcmp(e, "direct") == 0) ? 1 : 0;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -350,7 +460,8 @@ bool use_simt_gemm() {
 
 void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   RVB_CHECK(g.in != nullptr && g.w != nullptr && g.out != nullptr, "gemm: null operand");
-  RVB_CHECK(g.Cin % 8 == 0 && g.in_pitch % 8 == 0 && g.in_pitch >= g.Cin, "gemm: Cin / pitch must be multiples of 8");
+  RVB_CHECK(g.Cin % 8 == 0 && g.in_pitch % 8 == 0, "gemm: Cin / pitch must be multiples of 8");
+  RVB_CHECK(g.window || g.in_pitch >= g.Cin, "gemm: pixel pitch smaller than Cin");
   RVB_CHECK((reinterpret_cast<uintptr_t>(g.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
             "gemm: operands must be 16-byte aligned");
   RVB_CHECK(g.Cout % 8 == 0, "gemm: Cout must be a multiple of 8");
@@ -383,7 +494,9 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   p.out = g.out;
   p.ldc = g.ldc;
   p.out_f32 = g.out_f32;
+  p.tma_store = use_direct_epilogue() ? 0 : 1;
 
+  const uint32_t ones[4] = {1, 1, 1, 1};
   const uint64_t pitchB = static_cast<uint64_t>(g.in_pitch) * 2;
   if (p.plain) {
     p.tile_rows = BLOCK_M;
@@ -394,11 +507,10 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
     const uint64_t dims[4] = {static_cast<uint64_t>(g.Cin), static_cast<uint64_t>(M), 1, 1};
     const uint64_t strides[3] = {pitchB, pitchB * static_cast<uint64_t>(M), pitchB * static_cast<uint64_t>(M)};
     const uint32_t box[4] = {BLOCK_K, BLOCK_M, 1, 1};
-    const uint32_t es[4] = {1, 1, 1, 1};
-    encode_map(&plan->tmA, g.in, 4, dims, strides, box, es);
+    encode_map(&plan->tmA, kH16Type, g.in, 4, dims, strides, box, ones);
   } else {
     RVB_CHECK(Wo <= BLOCK_M, "conv: output width > 128 is not supported by the full-row tiling");
-    RVB_CHECK(Wo * g.stride <= 256, "conv: box width exceeds the TMA limit");
+    RVB_CHECK(g.window || Wo * g.stride <= 256, "conv: box width exceeds the TMA limit");
     const int P = Ho * Wo;
     if (P >= BLOCK_M) {
       int th = 1;
@@ -416,13 +528,28 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
       p.tile_rows = p.nb * P;
       p.m_tiles = (g.NB + p.nb - 1) / p.nb;
     }
-    const uint64_t dims[4] = {static_cast<uint64_t>(g.Cin), static_cast<uint64_t>(g.W), static_cast<uint64_t>(g.H),
-                              static_cast<uint64_t>(g.NB)};
-    const uint64_t strides[3] = {pitchB, pitchB * g.W, pitchB * g.W * g.H};
-    const uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(Wo * g.stride), static_cast<uint32_t>(p.th * g.stride),
-                             static_cast<uint32_t>(p.nb)};
-    const uint32_t es[4] = {1, static_cast<uint32_t>(g.stride), static_cast<uint32_t>(g.stride), 1};
-    encode_map(&plan->tmA, g.in, 4, dims, strides, box, es);
+    if (g.window) {
+      // overlapping-window view of a zero-padded NHW8 image: element (k, wo, h, n) lives at
+      // n*H*row + h*row + wo*(stride*8) + k; each K block is one filter ROW (KW folded into k).
+      RVB_CHECK(g.KW == 1 && g.pad == 0 && g.Cin == BLOCK_K && g.win_row_pitch % 8 == 0, "window conv: bad geometry");
+      RVB_CHECK(static_cast<int64_t>(Wo - 1) * g.stride * 8 + BLOCK_K <= g.win_row_pitch, "window conv: row too short");
+      const uint64_t rowB = static_cast<uint64_t>(g.win_row_pitch) * 2;
+      const uint64_t dims[4] = {BLOCK_K, static_cast<uint64_t>(Wo), static_cast<uint64_t>(g.H),
+                                static_cast<uint64_t>(g.NB)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(g.stride) * 8 * 2, rowB, rowB * g.H};
+      const uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(Wo), static_cast<uint32_t>(p.th * g.stride),
+                               static_cast<uint32_t>(p.nb)};
+      const uint32_t es[4] = {1, 1, static_cast<uint32_t>(g.stride), 1};
+      encode_map(&plan->tmA, kH16Type, g.in, 4, dims, strides, box, es);
+    } else {
+      const uint64_t dims[4] = {static_cast<uint64_t>(g.Cin), static_cast<uint64_t>(g.W), static_cast<uint64_t>(g.H),
+                                static_cast<uint64_t>(g.NB)};
+      const uint64_t strides[3] = {pitchB, pitchB * g.W, pitchB * g.W * g.H};
+      const uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(Wo * g.stride), static_cast<uint32_t>(p.th * g.stride),
+                               static_cast<uint32_t>(p.nb)};
+      const uint32_t es[4] = {1, static_cast<uint32_t>(g.stride), static_cast<uint32_t>(g.stride), 1};
+      encode_map(&plan->tmA, kH16Type, g.in, 4, dims, strides, box, es);
+    }
   }
   p.a_bytes = static_cast<uint32_t>(p.tile_rows) * BLOCK_K * 2;
 
@@ -453,9 +580,28 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   const uint64_t bdims[2] = {Ktot, static_cast<uint64_t>(g.Cout)};
   const uint64_t bstrides[1] = {Ktot * 2};
   const uint32_t bbox[2] = {BLOCK_K, static_cast<uint32_t>(best_bn)};
-  const uint32_t bes[2] = {1, 1};
   RVB_CHECK((Ktot * 2) % 16 == 0, "gemm: weight row pitch must be a multiple of 16 bytes");
-  encode_map(&plan->tmB, g.w, 2, bdims, bstrides, bbox, bes);
+  encode_map(&plan->tmB, kH16Type, g.w, 2, bdims, bstrides, bbox, ones);
+
+  // output map (TMA store): same row geometry as the A tile, 128-byte column chunks
+  {
+    const uint64_t esz = g.out_f32 ? 4 : 2;
+    const uint32_t ccols = g.out_f32 ? 32 : 64;
+    const uint64_t pitchC = static_cast<uint64_t>(g.ldc) * esz;
+    const CUtensorMapDataType cdt = g.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : kH16Type;
+    if (p.plain) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(M), 1, 1};
+      const uint64_t strides[3] = {pitchC, pitchC * static_cast<uint64_t>(M), pitchC * static_cast<uint64_t>(M)};
+      const uint32_t box[4] = {ccols, BLOCK_M, 1, 1};
+      encode_map(&plan->tmC, cdt, g.out, 4, dims, strides, box, ones);
+    } else {
+      const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                                static_cast<uint64_t>(g.NB)};
+      const uint64_t strides[3] = {pitchC, pitchC * Wo, pitchC * Wo * Ho};
+      const uint32_t box[4] = {ccols, static_cast<uint32_t>(Wo), static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.nb)};
+      encode_map(&plan->tmC, cdt, g.out, 4, dims, strides, box, ones);
+    }
+  }
 
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   plan->grid = static_cast<int>(std::min<long long>(tiles, sms));

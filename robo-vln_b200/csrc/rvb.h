@@ -58,11 +58,15 @@ struct ConvGemm {
   void* out = nullptr;           // h16 or f32, [M, ldc]
   int64_t ldc = 0;
   int out_f32 = 0;
+  // "window" mode (RGB stem): `in` is a zero-padded [NB, H, win_row_pitch/8, 8] image, KW is folded
+  // into the K dimension (Cin = 64 = 8 pixels x 8 channels per filter row), W is the OUTPUT width.
+  int window = 0;
+  int64_t win_row_pitch = 0;     // elements per padded input row
   // derived
   int Ho() const { return (H + 2 * pad - KH) / stride + 1; }
-  int Wo() const { return (W + 2 * pad - KW) / stride + 1; }
+  int Wo() const { return window ? W : (W + 2 * pad - KW) / stride + 1; }
   int64_t M() const { return static_cast<int64_t>(NB) * Ho() * Wo(); }
-  bool plain() const { return KH == 1 && KW == 1 && stride == 1 && pad == 0; }
+  bool plain() const { return !window && KH == 1 && KW == 1 && stride == 1 && pad == 0; }
 };
 
 // Device-side parameter block of the tcgen05 kernel.
@@ -87,11 +91,13 @@ struct GemmTcParams {
   void* out;
   long long ldc;
   int out_f32;
+  int tma_store;     // 1: smem-staged TMA store epilogue, 0: direct global stores (validation)
 };
 
 struct GemmTcPlan {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmC;
   GemmTcParams p;
   int BN = 128;
   int grid = 0;
@@ -110,6 +116,7 @@ bool use_simt_gemm();
 
 // elementwise.cu
 void rgb_stem_im2col(const float* rgb, h16* out, int NB, int H, int W, int Kpitch, cudaStream_t s);
+void rgb_pad_convert(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s);
 void maxpool3x3s2(const h16* in, h16* out, int NB, int H, int W, int C, cudaStream_t s);
 void depth_stem_conv(const float* depth, const float* w, h16* out, int NB, int H, int W, cudaStream_t s);
 void gn_stats(const h16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s);

@@ -7,7 +7,7 @@ features where the reference flattens NCHW "channel-major" ones
 (seq2seq_highlevel_cma.py:92-100 depth_linear; resnet_encoders.py:58-62 visual_fc).
 
 Engine tensor names (``ns`` is "hi" or "lo"):
-  {ns}.rgb.stem.{w,b}                     bf16 [64,160] (147 real K, zero padded), f32 [64]
+  {ns}.rgb.stem.{w,b}                     h16 [64,448] (7 filter rows x 64-wide window block), f32 [64]
   {ns}.rgb.l{1-4}.{blk}.{c1,c2,c3,ds}.{w,b}
   {ns}.depth.stem.w f32 [32,49]; {ns}.depth.stem.gn.{w,b}
   {ns}.depth.l{1-4}.{blk}.{c1,c2,c3,ds}.w ; .gn{1,2,3}.{w,b} ; .dsgn.{w,b}
@@ -60,6 +60,16 @@ def fold_bn(conv_w: torch.Tensor, g, b, mean, var, eps: float = 1e-5):
     return conv_w.float() * scale.view(-1, 1, 1, 1), b.float() - mean.float() * scale
 
 
+def stem_window_weights(w: torch.Tensor) -> torch.Tensor:
+    """[64,3,7,7] (O,C,R,S) -> [64, 7*64]: one 64-wide K block per filter row r, laid out as the
+    window-mode A operand reads the padded NHW8 image: k = s*8 + c for s < 7, c < 3, zeros
+    elsewhere (channels 3..7 and the 8th pixel of the 64-element window)."""
+    o = w.shape[0]
+    wk = torch.zeros((o, 7, 8, 8), dtype=torch.float32, device=w.device)     # [O, r, s(8), c(8)]
+    wk[:, :, :7, :3] = w.float().permute(0, 2, 3, 1)                          # [O, R, S, C]
+    return wk.reshape(o, 7 * 64)
+
+
 def prep_rgb_trunk(sd: Dict[str, torch.Tensor], ns: str, dev) -> Dict[str, torch.Tensor]:
     p = "rgb_encoder.cnn."
     out = {}
@@ -68,9 +78,7 @@ def prep_rgb_trunk(sd: Dict[str, torch.Tensor], ns: str, dev) -> Dict[str, torch
         return (sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"], sd[prefix + ".running_var"])
 
     w, b = fold_bn(sd[p + "conv1.weight"], *bn(p + "bn1"))
-    wk = torch.zeros((64, 160), dtype=torch.float32, device=w.device)
-    wk[:, :147] = _conv_kmajor(w)
-    out[f"{ns}.rgb.stem.w"] = _bf(wk, dev)
+    out[f"{ns}.rgb.stem.w"] = _bf(stem_window_weights(w), dev)
     out[f"{ns}.rgb.stem.b"] = _f32(b, dev)
     for li, (nb, _s) in enumerate(_STAGES):
         for blk in range(nb):

@@ -46,10 +46,26 @@ def conv_gemm(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_row
         out = torch.zeros((M, ldc), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
     rc = lib(dt).rvb_conv_gemm(P(x), NB, H, W, Cin, Cin, P(w), Cout, KH, KW, stride, pad, P(bias), P(res),
                                0 if res is None else res.shape[-1], res_rows, act, P(out), ldc, int(out_f32), force_bn,
-                               impl, stream())
+                               impl, 0, 0, stream())
     check(rc, "rvb_conv_gemm", dt)
     torch.cuda.synchronize()
     return out
+
+
+def rgb_stem(rgb, w_win, bias, dtype="fp16", impl=0):
+    """RGB stem as the engine runs it: pad/convert pre-pass, then the window-mode 7x7 s2 conv.
+    rgb [NB,H,W,3] f32, w_win [64, 448] h16 (weight_prep.stem_window_weights) -> [NB*Ho*Wo, 64]."""
+    NB, H, W, _ = rgb.shape
+    Hp, Wp = H + 6, W + 6
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    padded = torch.full((NB, Hp, Wp, 8), 3.0, dtype=H16[dtype], device=rgb.device)
+    check(lib(dtype).rvb_rgb_pad_convert(P(rgb), P(padded), NB, H, W, Wp, stream()), "rvb_rgb_pad_convert", dtype)
+    out = torch.zeros((NB * Ho * Wo, 64), dtype=H16[dtype], device=rgb.device)
+    rc = lib(dtype).rvb_conv_gemm(P(padded), NB, Hp, Wo, 64, 8, P(w_win), 64, 7, 1, 2, 0, P(bias), None, 0, 0, 1,
+                                  P(out), 64, 0, 0, impl, 1, Wp * 8, stream())
+    check(rc, "rvb_conv_gemm(window)", dtype)
+    torch.cuda.synchronize()
+    return out, padded
 
 
 def conv_ref(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows=0, act=0):
