@@ -175,6 +175,72 @@ RVB_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
 RVB_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variants: two CTAs of a 2-CTA cluster run ONE M=256 UMMA; each CTA
+// stages its own 128 rows of A and its half of B, the leader (cluster rank 0) issues the MMA.
+// ---------------------------------------------------------------------------------------
+RVB_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+RVB_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+RVB_DEVICE uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+RVB_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <uint32_t kCols>
+RVB_DEVICE void tmem_alloc_2sm(uint32_t* smem_result) {   // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+RVB_DEVICE void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// TMA loads whose completion bytes are credited to an mbarrier given by its shared::cluster
+// address (the leader CTA's "full" barrier), as cta_group::2 requires
+RVB_DEVICE void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t mbar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+RVB_DEVICE void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t mbar_cluster_addr, int c0, int c1,
+                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+RVB_DEVICE void umma_f16kind_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all previously issued MMAs of the pair retire) on the barrier at this smem
+// offset in BOTH CTAs of the pair
+RVB_DEVICE void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // math / packing
 // ---------------------------------------------------------------------------------------
 #if RVB_BF16
@@ -202,7 +268,21 @@ RVB_DEVICE float2 unpack_h2(uint32_t u) {
 RVB_DEVICE h16 to_h16(float x) { return __float2half_rn(sat_h(x)); }
 RVB_DEVICE float from_h16(h16 x) { return __half2float(x); }
 #endif
-RVB_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU(erf) as BERT uses it.  erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below
+// the 16-bit output rounding): ~15 instructions instead of erff's ~40, which matters because
+// the FFN1 epilogue applies it to 15.7 M elements per BERT layer.
+RVB_DEVICE float gelu_erf(float x) {
+  const float z = x * 0.70710678118654752f;
+  const float a = fabsf(z);
+  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, __expf(-a * a), 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, z));
+}
 RVB_DEVICE float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 RVB_DEVICE float warp_sum(float v) {

@@ -587,6 +587,7 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s) {
   Stage& rgb = (lo_weights && !st_rgb_lo_.empty()) ? st_rgb_lo_ : st_rgb_;
   Stage& dep = (lo_weights && !st_depth_lo_.empty()) ? st_depth_lo_ : st_depth_;
   if (!multi) {
+    if (before_rgb_) before_rgb_(s);
     launches_ += run(rgb, s);
     launches_ += run(dep, s);
     if (with_bert) launches_ += run(st_bert_, s);
@@ -601,6 +602,7 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s) {
     launches_ += run(st_bert_, side_[1]);
     RVB_CUDA(cudaEventRecord(events_[2], side_[1]));
   }
+  if (before_rgb_) before_rgb_(s);   // host entry: the (large) RGB upload overlaps depth trunk + BERT
   launches_ += run(rgb, s);
   RVB_CUDA(cudaStreamWaitEvent(s, events_[1], 0));
   if (with_bert) RVB_CUDA(cudaStreamWaitEvent(s, events_[2], 0));
@@ -693,7 +695,12 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
   const size_t dep_b = static_cast<size_t>(B) * shp_.depth_h * shp_.depth_w * 4;
   const size_t ins_b = static_cast<size_t>(shp_.instr_rows) * shp_.L * 4;
   const size_t hc_b = 2ull * N * 512 * 4;
-  RVB_CUDA(cudaMemcpyAsync(stage_rgb_, rgb, rgb_b, cudaMemcpyHostToDevice, s));
+  // small uploads first; the 50 MB RGB upload is issued right before the RGB trunk so that the
+  // depth trunk and BERT (side streams) run underneath it
+  float* stage_rgb = stage_rgb_;
+  before_rgb_ = [stage_rgb, rgb, rgb_b](cudaStream_t st) {
+    RVB_CUDA(cudaMemcpyAsync(stage_rgb, rgb, rgb_b, cudaMemcpyHostToDevice, st));
+  };
   RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, s));
   RVB_CUDA(cudaMemcpyAsync(stage_instr_, instr, ins_b, cudaMemcpyHostToDevice, s));
   RVB_CUDA(cudaMemcpyAsync(stage_masks_, masks, static_cast<size_t>(B) * 2 * 4, cudaMemcpyHostToDevice, s));
@@ -707,7 +714,13 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
   a.logits = logits_buf_; a.actions = act_buf_; a.stop = stop_buf_;
   a.sub_goal_out = nullptr;
   args_ = a;
-  forward_policy(s);
+  try {
+    forward_policy(s);
+  } catch (...) {
+    before_rgb_ = nullptr;
+    throw;
+  }
+  before_rgb_ = nullptr;
   RVB_CUDA(cudaMemcpyAsync(logits, logits_buf_, static_cast<size_t>(B) * 4 * 4, cudaMemcpyDeviceToHost, s));
   RVB_CUDA(cudaMemcpyAsync(actions, act_buf_, static_cast<size_t>(B) * 2 * 4, cudaMemcpyDeviceToHost, s));
   RVB_CUDA(cudaMemcpyAsync(stop, stop_buf_, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));

@@ -82,6 +82,7 @@ class Engine {
   RunArgs args_;
   int64_t launches_ = 0;
   bool multi_stream_ = false;
+  std::function<void(cudaStream_t)> before_rgb_;   // enqueued right before the RGB trunk (host-entry upload)
   bool planned_ = false;
   bool have_hi_ = false, have_lo_ = false, lo_shares_trunks_ = false;
   hcm_shape shp_{};

@@ -46,9 +46,12 @@ constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
 constexpr int STAGING_BYTES = 2 * 16384;              // one 128 x 128B chunk buffer per epilogue group
 constexpr int SMEM_STAGE_BUDGET = 196608;             // 192 KiB of pipeline stages
 
-template <int BN>
+// CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (2-CTA cluster) owns a 256 x BN
+// tile; each CTA stages its 128 rows of A and HALF of B (BN/2 rows) per K block, which doubles
+// the FLOPs per byte pulled into each SM -- the per-SM L2 ingress is what bounds the 1-CTA form.
+template <int BN, int CTAS = 1>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_STAGE_BYTES = (BN / CTAS) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (SMEM_STAGE_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_STAGE_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // 128, 256 or 512: powers of two >= 32
@@ -92,12 +95,15 @@ RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, cons
   }
 }
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmTcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
   constexpr int STAGES = C::STAGES;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int unit = (CTAS == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_units = (CTAS == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,28 +130,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], NUM_EPI_WARPS * CTAS);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    if (CTAS == 2) tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<C::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // work units: 128 x BN tiles (CTAS == 1) or 256 x BN pair tiles (CTAS == 2, this CTA = rows rank*128..)
+  const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
+  const int total_tiles = m_units * p.n_tiles;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int nt = tile - mt * p.n_tiles;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
+        const int mu = tile / p.n_tiles;
+        const int nt = tile - mu * p.n_tiles;
+        const int mt = mu * CTAS + static_cast<int>(cta_rank);   // may be one past the end for the peer: OOB -> zeros
         int img = 0, h0 = 0;
         if (!p.plain) {
           if (p.nb == 1) {
@@ -157,11 +168,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + C::B_STAGE_BYTES);
           const int tap = kb / p.cblocks;
           const int cb = kb - tap * p.cblocks;
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
+          if (CTAS == 2) {
+            // both CTAs' bytes are credited to the LEADER's full barrier, which the leader arms
+            const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_bytes + C::B_STAGE_BYTES));
+            if (p.plain) {
+              tma_load_4d_2sm(sa, &tmA, full_leader, cb * BLOCK_K, mt * BLOCK_M, 0, 0);
+            } else {
+              const int r = tap / p.KW;
+              const int s = tap - r * p.KW;
+              tma_load_4d_2sm(sa, &tmA, full_leader, cb * BLOCK_K, s - p.pad, h0 * p.stride + r - p.pad, img);
+            }
+            tma_load_2d_2sm(sb, &tmB, full_leader, tap * p.Cin + cb * BLOCK_K,
+                            nt * BN + static_cast<int>(cta_rank) * (BN / 2));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + C::B_STAGE_BYTES);
           if (p.plain) {
             tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, mt * BLOCK_M, 0, 0);
           } else {
@@ -179,13 +209,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_h16(BLOCK_M, BN);
+    if (lane == 0 && cta_rank == 0) {   // in a pair only the leader issues MMAs
+      constexpr uint32_t idesc = umma_idesc_h16(BLOCK_M * CTAS, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -197,16 +227,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 elements = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
-            umma_f16kind(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                         static_cast<uint32_t>((kb | k) != 0));
+            if (CTAS == 2)
+              umma_f16kind_2sm(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                               static_cast<uint32_t>((kb | k) != 0));
+            else
+              umma_f16kind(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                           static_cast<uint32_t>((kb | k) != 0));
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CTAS == 2) umma_commit_2sm(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -228,9 +266,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     bool store_pending = false;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles;
-      const int nt = tile - mt * p.n_tiles;
+    const uint32_t tempty_leader0 = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
+    const uint32_t tempty_leader1 = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
+    for (int tile = unit; tile < total_tiles; tile += num_units) {
+      const int mu = tile / p.n_tiles;
+      const int nt = tile - mu * p.n_tiles;
+      const int mt = mu * CTAS + static_cast<int>(cta_rank);
       const long long m = static_cast<long long>(mt) * p.tile_rows + row_in_tile;
       const bool row_ok = (row_in_tile < p.tile_rows) && (m < p.M);
       const int n0 = nt * BN;
@@ -311,7 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // every TMEM read of this warp for this accumulator has completed (wait::ld above)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       } else {
         // direct global stores (validation path, ROBOVLN_EPILOGUE=direct): 32-column chunks
 #pragma unroll 1
@@ -350,7 +394,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       }
       if (++acc == 2) {
         acc = 0;
@@ -363,9 +410,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer may still be using this CTA's barriers / TMEM half
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (CTAS == 2) tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -417,15 +466,37 @@ void encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int 
 
 constexpr CUtensorMapDataType kH16Type = RVB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
-template <int BN>
+template <int BN, int CTAS>
 void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
+  using C = Cfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<plan.grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(plan.tmA, plan.tmB, plan.tmC, plan.p);
-  RVB_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan.grid, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CTAS == 2) ? 1 : 0;
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS>, plan.tmA, plan.tmB, plan.tmC, plan.p));
+}
+
+bool use_pair_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_PAIR_MMA");
+    v = (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 bool use_direct_epilogue() {
@@ -553,33 +624,43 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   }
   p.a_bytes = static_cast<uint32_t>(p.tile_rows) * BLOCK_K * 2;
 
-  // N tile: prefer the candidate with the best wave efficiency on this device; ties -> larger BN.
+  // Tile configuration: minimise (waves x tile work / relative tile efficiency).  The relative
+  // efficiencies reflect the operand bytes each SM must pull from L2 per FLOP (128x128: 1/64,
+  // 128x256: 1/85, pair 256x256: 1/128 B/FLOP) as measured on B200 (profiles/): the 1-CTA forms
+  // are ingress-bound long before the tensor pipe saturates.  The pair form needs enough K to
+  // amortise its cluster hand-shakes and is only built for BN = 256.
   const int sms = device_sm_count();
-  int best_bn = 0;
-  double best_score = -1.0;
-  const int cands[3] = {256, 128, 64};
-  for (int bn : cands) {
-    if (force_bn != 0 && bn != force_bn) continue;
-    if (force_bn == 0 && bn > 64 && g.Cout <= bn / 2) continue;  // more than half the tile would be padding
-    const int nt = (g.Cout + bn - 1) / bn;
-    const long long tiles = static_cast<long long>(p.m_tiles) * nt;
-    const long long waves = (tiles + sms - 1) / sms;
-    const double eff = static_cast<double>(tiles) / static_cast<double>(waves * sms);
-    const double fill = static_cast<double>(g.Cout) / static_cast<double>(nt * bn);
-    const double score = eff * fill * (bn == 64 ? 0.85 : 1.0);  // BN=64 runs the tensor pipe at lower efficiency
-    if (score > best_score + 1e-9) {
-      best_score = score;
-      best_bn = bn;
+  struct Cand { int bn, ctas; double eff; };
+  const Cand cands[4] = {{256, 2, 1.0}, {256, 1, 0.62}, {128, 1, 0.5}, {64, 1, 0.33}};
+  const long long Kdepth = static_cast<long long>(g.KH) * g.KW * g.Cin;
+  int best_bn = 0, best_ctas = 1;
+  double best_cost = 1e300;
+  for (const Cand& c : cands) {
+    if (force_bn != 0 && (c.bn != (force_bn & 0xffff) || c.ctas != ((force_bn >> 16) ? 2 : 1))) continue;
+    if (force_bn == 0) {
+      if (c.bn > 64 && g.Cout <= c.bn / 2) continue;          // more than half the tile would be padding
+      if (c.ctas == 2 && (Kdepth < 512 || p.m_tiles < 2 || g.Cout < 256 || !use_pair_mma())) continue;
+    }
+    const int nt = (g.Cout + c.bn - 1) / c.bn;
+    const long long units = static_cast<long long>((p.m_tiles + c.ctas - 1) / c.ctas) * nt;
+    const long long slots = sms / c.ctas;
+    const long long waves = (units + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * c.bn / c.eff;   // time ~ waves x per-SM tile area (128 x BN) / efficiency
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best_bn = c.bn;
+      best_ctas = c.ctas;
     }
   }
   RVB_CHECK(best_bn != 0, "gemm: no tile configuration");
   plan->BN = best_bn;
+  plan->ctas = best_ctas;
   p.n_tiles = (g.Cout + best_bn - 1) / best_bn;
 
   const uint64_t Ktot = static_cast<uint64_t>(g.KH) * g.KW * g.Cin;
   const uint64_t bdims[2] = {Ktot, static_cast<uint64_t>(g.Cout)};
   const uint64_t bstrides[1] = {Ktot * 2};
-  const uint32_t bbox[2] = {BLOCK_K, static_cast<uint32_t>(best_bn)};
+  const uint32_t bbox[2] = {BLOCK_K, static_cast<uint32_t>(best_bn / best_ctas)};
   RVB_CHECK((Ktot * 2) % 16 == 0, "gemm: weight row pitch must be a multiple of 16 bytes");
   encode_map(&plan->tmB, kH16Type, g.w, 2, bdims, bstrides, bbox, ones);
 
@@ -603,8 +684,8 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
     }
   }
 
-  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
-  plan->grid = static_cast<int>(std::min<long long>(tiles, sms));
+  const long long units = static_cast<long long>((p.m_tiles + best_ctas - 1) / best_ctas) * p.n_tiles;
+  plan->grid = static_cast<int>(std::min<long long>(units, sms / best_ctas)) * best_ctas;
   plan->valid = true;
 }
 
@@ -614,10 +695,15 @@ void gemm_tc_launch(const GemmTcPlan& plan, cudaStream_t stream) {
     gemm_simt_launch(plan.desc, stream);
     return;
   }
+  if (plan.ctas == 2) {
+    RVB_CHECK(plan.BN == 256, "gemm: the CTA-pair kernel is built for BN = 256");
+    launch_bn<256, 2>(plan, stream);
+    return;
+  }
   switch (plan.BN) {
-    case 64: launch_bn<64>(plan, stream); break;
-    case 128: launch_bn<128>(plan, stream); break;
-    case 256: launch_bn<256>(plan, stream); break;
+    case 64: launch_bn<64, 1>(plan, stream); break;
+    case 128: launch_bn<128, 1>(plan, stream); break;
+    case 256: launch_bn<256, 1>(plan, stream); break;
     default: RVB_CHECK(false, "gemm: bad BN");
   }
 }

@@ -100,6 +100,7 @@ struct GemmTcPlan {
   alignas(64) CUtensorMap tmC;
   GemmTcParams p;
   int BN = 128;
+  int ctas = 1;        // 2: CTA-pair (cta_group::2) kernel, 256 x BN tiles
   int grid = 0;
   bool valid = false;
   ConvGemm desc;       // kept for the SIMT validation path

@@ -72,9 +72,12 @@ def conv_ref(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows
     """fp32 torch reference on the same 16-bit-rounded operands."""
     NB, H, W, Cin = x.shape
     Cout = w.shape[0]
-    w4 = w.float().view(Cout, KH, KW, Cin).permute(0, 3, 1, 2).contiguous()
-    y = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w4, None, stride=stride, padding=pad)
-    y = y.permute(0, 2, 3, 1).reshape(-1, Cout)
+    if KH == 1 and KW == 1 and stride == 1 and pad == 0:
+        y = x.float().reshape(-1, Cin) @ w.float().t()          # plain GEMM (avoids slow cuDNN paths for H=1 images)
+    else:
+        w4 = w.float().view(Cout, KH, KW, Cin).permute(0, 3, 1, 2).contiguous()
+        y = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w4, None, stride=stride, padding=pad)
+        y = y.permute(0, 2, 3, 1).reshape(-1, Cout)
     if bias is not None:
         y = y + bias.float()
     if res is not None:

@@ -82,6 +82,36 @@ def test_forced_tile_widths(bn, dtype):
     assert e < F32_TOL, f"BN={bn}: rel err {e:.3e}"
 
 
+PAIR = 256 | (1 << 16)   # force_bn encoding of the CTA-pair (cta_group::2) kernel, 256 x 256 tiles
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", [
+    ("pair_plain_even", 1, 1, 1024, 768, 768, 1, 1, 0),
+    ("pair_plain_odd_tiles_tail", 1, 1, 1600 + 37, 512, 512, 1, 1, 0),      # 13 M tiles (odd) + ragged tail
+    ("pair_plain_n_tail", 1, 1, 512, 1024, 384, 1, 1, 0),                   # N not a multiple of 256
+    ("pair_c3x3_16x16", 4, 16, 16, 256, 256, 3, 1, 1),
+    ("pair_c3x3_s2_8x8_two_imgs", 5, 16, 16, 512, 512, 3, 2, 1),             # 2 images per 128-row tile, odd tile count
+    ("pair_many_units", 1, 1, 128 * 60, 512, 1024, 1, 1, 0),                # 30 x 4 = 120 pair tiles > 74 clusters
+], ids=lambda c: c[0])
+def test_cta_pair_kernel(case, dtype):
+    """cta_group::2: two CTAs of a cluster run one M=256 UMMA, each staging half of B."""
+    from tests.gpu_util import OUT_TOL, conv_gemm, conv_ref, rel_err
+
+    name, NB, H, W, Cin, Cout, K, stride, pad = case
+    x = _mk((NB, H, W, Cin), 1.0, 31, dtype)
+    w = _mk((Cout, K * K * Cin), (2.0 / (K * K * Cin)) ** 0.5, 32, dtype)
+    bias = _mk((Cout,), 0.5, 33, "f32")
+    M = NB * ((H + 2 * pad - K) // stride + 1) * ((W + 2 * pad - K) // stride + 1)
+    res = _mk((M, Cout), 1.0, 34, dtype)
+    ref = conv_ref(x, w, KH=K, KW=K, stride=stride, pad=pad, bias=bias, res=res, act=1)
+    out = conv_gemm(x, w, KH=K, KW=K, stride=stride, pad=pad, bias=bias, res=res, act=1, force_bn=PAIR)
+    assert rel_err(out, ref) < OUT_TOL[dtype], name
+    one = conv_gemm(x, w, KH=K, KW=K, stride=stride, pad=pad, bias=bias, res=res, act=1, force_bn=128, out_f32=True)
+    two = conv_gemm(x, w, KH=K, KW=K, stride=stride, pad=pad, bias=bias, res=res, act=1, force_bn=PAIR, out_f32=True)
+    assert rel_err(two, one) < 1e-5, name          # same products, same fp32 accumulation order per K block
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_epilogue_variants(dtype):
     from tests.gpu_util import OUT_TOL, conv_gemm, conv_ref, rel_err
