@@ -639,7 +639,11 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
     if (force_bn != 0 && (c.bn != (force_bn & 0xffff) || c.ctas != ((force_bn >> 16) ? 2 : 1))) continue;
     if (force_bn == 0) {
       if (c.bn > 64 && g.Cout <= c.bn / 2) continue;          // more than half the tile would be padding
-      if (c.ctas == 2 && (Kdepth < 512 || p.m_tiles < 2 || g.Cout < 256 || !use_pair_mma())) continue;
+      // measured (profiles/r01_gemm_probe.txt): the pair form wins once there are >= 2 full waves of
+      // 256 x 256 tiles and the epilogue is light; below that its coarser tiles lose to quantisation
+      const long long pair_units = static_cast<long long>((p.m_tiles + 1) / 2) * ((g.Cout + 255) / 256);
+      if (c.ctas == 2 && (Kdepth < 512 || g.Cout < 256 || pair_units < 2 * (sms / 2) || g.act == ACT_GELU ||
+                          !use_pair_mma())) continue;
     }
     const int nt = (g.Cout + c.bn - 1) / c.bn;
     const long long units = static_cast<long long>((p.m_tiles + c.ctas - 1) / c.ctas) * nt;
