@@ -122,6 +122,12 @@ int hcm_profile_policy(hcm_engine* e, const float* rgb, const float* depth, cons
 int hcm_run_rgb_trunk(hcm_engine* e, const float* rgb, int use_lo_weights, void* stream);
 int hcm_run_depth_trunk(hcm_engine* e, const float* depth, int use_lo_weights, void* stream);
 int hcm_run_bert(hcm_engine* e, const float* instr_f32, const int64_t* instr_i64, void* stream);
+/* The three frozen encoders of one call (RGB trunk, depth trunk and, if with_bert, BERT) on the
+ * engine's stream fork; results in the buffers "rgb_tokens", "rgb_cellmean", "rgb_gmean",
+ * "depth_tokens", "bert".  Used by the training path: the trainable tail then runs under
+ * autograd on the host framework side (robo-vln_b200/torch_tail.py). */
+int hcm_run_encoders(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                     const int64_t* instr_i64, int with_bert, int use_lo_weights, void* stream);
 /* cross-modal block on caller tensors: bert [R*L,768] bf16 (R = B or 1 per the plan),
  * rgb_spatial / depth_spatial [B*16,256] bf16 (outputs of rgb_kv / depth_kv) ->
  * pooled [B, 512] bf16 (ins_rgb_att | ins_depth_att).  BASELINE.json configs[2]. */

@@ -42,6 +42,7 @@ SYMBOLS = {
     "hcm_run_rgb_trunk": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "hcm_run_depth_trunk": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "hcm_run_bert": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hcm_run_encoders": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "hcm_run_cross_modal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hcm_get_buffer": (c_int, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
     "hcm_copy_buffer": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),

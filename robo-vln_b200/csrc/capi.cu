@@ -175,6 +175,22 @@ int hcm_run_depth_trunk(hcm_engine* e, const float* depth, int use_lo_weights, v
   });
 }
 
+int hcm_run_encoders(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,
+                     const int64_t* instr_i64, int with_bert, int use_lo_weights, void* stream) {
+  return guarded([&] {
+    RVB_CHECK(e->eng.planned_, "engine not planned");
+    RVB_CHECK(rgb != nullptr && depth != nullptr, "hcm_run_encoders: null observation");
+    RVB_CHECK(!with_bert || (e->eng.have_hi_ && (instr_f32 != nullptr || instr_i64 != nullptr)),
+              "hcm_run_encoders: BERT needs the hi weights and an instruction");
+    e->eng.args_.rgb = rgb;
+    e->eng.args_.depth = depth;
+    e->eng.args_.instr_f32 = instr_f32;
+    e->eng.args_.instr_i64 = instr_i64;
+    e->eng.launches_ = e->eng.run(e->eng.st_pre_, S(stream));
+    e->eng.run_encoders(with_bert != 0, use_lo_weights != 0, S(stream));
+  });
+}
+
 int hcm_run_bert(hcm_engine* e, const float* instr_f32, const int64_t* instr_i64, void* stream) {
   return guarded([&] {
     RVB_CHECK(e->eng.planned_ && e->eng.have_hi_, "engine not planned");

@@ -65,6 +65,13 @@ class HcmModuleBase(nn.Module):
                 rt.mark_dirty()
         return out
 
+    def train(self, mode: bool = True):
+        # leaving training mode: optimizer steps may have changed the trainable tail, so the
+        # engine's packed copies are re-made on the next inference call
+        if self.training and not mode:
+            self._weights_changed()
+        return super().train(mode)
+
     def notify_weights_updated(self):
         """Call after an optimizer step so the next forward re-packs the trainable weights."""
         self._weights_changed()

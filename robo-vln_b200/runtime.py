@@ -89,20 +89,39 @@ class HcmRuntime:
         tensors: Dict[str, torch.Tensor] = {}
         shares = False
         WP.set_h16(self.dtype_name)
+        frozen_cache = getattr(self, "_frozen_cache", {})
+
+        def frozen(tag, sd, prefixes, fn):
+            """Re-pack a frozen sub-network only if one of its tensors changed (storage or version):
+            after an optimizer step only the ~5 M-parameter tail needs new kernel-layout copies."""
+            sig = tuple((v.data_ptr(), v._version) for k, v in sd.items() if k.startswith(prefixes))
+            hit = frozen_cache.get(tag)
+            if hit is not None and hit[0] == sig:
+                return hit[1]
+            out = fn()
+            frozen_cache[tag] = (sig, out)
+            return out
+
         with torch.no_grad():
-            sd_hi = hi.state_dict() if hi is not None else None
-            sd_lo = lo.state_dict() if lo is not None else None
+            sd_hi = hi.state_dict(keep_vars=True) if hi is not None else None
+            sd_lo = lo.state_dict(keep_vars=True) if lo is not None else None
             if sd_hi is not None:
-                tensors.update(WP.prep_rgb_trunk(sd_hi, "hi", dev))
-                tensors.update(WP.prep_depth_trunk(sd_hi, "hi", dev))
-                tensors.update(WP.prep_bert(sd_hi, dev))
+                tensors.update(frozen("hi.rgb", sd_hi, ("rgb_encoder.cnn.",), lambda: WP.prep_rgb_trunk(sd_hi, "hi", dev)))
+                tensors.update(frozen("hi.depth", sd_hi, ("depth_encoder.visual_encoder.",),
+                                      lambda: WP.prep_depth_trunk(sd_hi, "hi", dev)))
+                tensors.update(frozen("hi.bert", sd_hi, ("embedding_layer.",), lambda: WP.prep_bert(sd_hi, dev)))
                 tensors.update(WP.prep_hi_tail(sd_hi, dev))
             if sd_lo is not None:
-                shares = sd_hi is not None and WP.trunks_identical(sd_hi, sd_lo)
+                shares = sd_hi is not None and frozen(
+                    "shares", {**{"a." + k: v for k, v in sd_hi.items() if k.startswith(WP.TRUNK_PREFIXES)},
+                               **{"b." + k: v for k, v in sd_lo.items() if k.startswith(WP.TRUNK_PREFIXES)}},
+                    ("a.", "b."), lambda: WP.trunks_identical(sd_hi, sd_lo))
                 if not shares:
-                    tensors.update(WP.prep_rgb_trunk(sd_lo, "lo", dev))
-                    tensors.update(WP.prep_depth_trunk(sd_lo, "lo", dev))
+                    tensors.update(frozen("lo.rgb", sd_lo, ("rgb_encoder.cnn.",), lambda: WP.prep_rgb_trunk(sd_lo, "lo", dev)))
+                    tensors.update(frozen("lo.depth", sd_lo, ("depth_encoder.visual_encoder.",),
+                                          lambda: WP.prep_depth_trunk(sd_lo, "lo", dev)))
                 tensors.update(WP.prep_lo_tail(sd_lo, dev))
+        self._frozen_cache = frozen_cache
         with torch.cuda.device(dev):
             torch.cuda.synchronize()
             for name, t in tensors.items():
@@ -233,6 +252,46 @@ class HcmRuntime:
                   "hcm_forward_policy")
         self._keep = (rgb, depth, i_f32, i_i64, masks, hidden_hi, hidden_lo)
         return logits, act, stop, hc_hi, hc_lo, sub
+
+    def encode(self, rgb, depth, instruction=None, n_envs: int = 1, use_lo_weights: bool = False):
+        """Frozen encoders only (training path): returns fp32 feature tensors
+        {"rgb_feat" [B,16,2048], "rgb_gmean" [B,2048], "depth_feat" [B,16,128], "bert" [1|B,L,768]}."""
+        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        B = rgb.shape[0]
+        hi, _ = self._modules()
+        with_bert = instruction is not None
+        i_f32 = i_i64 = None
+        if with_bert:
+            instr = instruction.to(self.device)
+            if instr.dim() != 2 or instr.shape[0] not in (1, B):
+                raise ValueError("instruction must be [1 or B, L]")
+            i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
+            i_i64 = instr.contiguous() if instr.dtype == torch.int64 else None
+            L, rows = instr.shape[1], instr.shape[0]
+        else:
+            L, rows = (self._shape_key[2], self._shape_key[3]) if (self._shape_key and self._shape_key[0] == B) else (8, 1)
+        N = n_envs if B % max(n_envs, 1) == 0 else 1
+        if not (self._shape_key and self._shape_key[0] == B and self._shape_key[4] == tuple(rgb.shape[1:3])
+                and (not with_bert or (self._shape_key[2], self._shape_key[3]) == (L, rows))):
+            self.ensure_plan(B, N, L, rows, rgb.shape[1:3], depth.shape[1:3])
+        else:
+            self.sync_weights()
+        sig = self._sig(rgb, depth)
+        fresh = not (sig == self._obs_sig and (self._shares or not use_lo_weights))
+        if fresh or with_bert:
+            with torch.cuda.device(self.device):
+                check(self.lib.hcm_run_encoders(self.handle, _ptr(rgb), _ptr(depth), _ptr(i_f32), _ptr(i_i64),
+                                                int(with_bert), int(use_lo_weights), self._stream()), "hcm_run_encoders")
+            self._obs_sig = sig
+            self._keep = (rgb, depth, i_f32, i_i64)
+        out = {
+            "rgb_feat": self.get_buffer("rgb_tokens")[:, :, :2048].float(),
+            "rgb_gmean": self.get_buffer("rgb_gmean").float(),
+            "depth_feat": self.get_buffer("depth_tokens")[:, :, :128].float(),
+        }
+        if with_bert:
+            out["bert"] = self.get_buffer("bert").float()
+        return out
 
     def profile_policy(self, rgb, depth, instruction, masks, hidden_hi, hidden_lo):
         """Per-launch device times of one policy step (single stream, CUDA events between

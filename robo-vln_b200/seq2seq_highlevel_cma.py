@@ -53,6 +53,8 @@ class Seq2Seq_HighLevel_CMA(HcmModuleBase):
             raise NotImplementedError("the HCM high-level head has 4 sub-goal logits")
         self.model_config = model_config
         self.batch_size = batch_size
+        vla = getattr(model_config, "VISUAL_LING_ATTN", None) if model_config is not None else None
+        self.dropout_p = float(getattr(vla, "dropout", 0.25)) if vla is not None else 0.25
         build_param_tree(self, hi_spec(num_actions))
 
     def forward(self, batch):
@@ -64,7 +66,20 @@ class Seq2Seq_HighLevel_CMA(HcmModuleBase):
             raise NotImplementedError("pre-computed rgb_features/depth_features are not supported yet")
         instruction = observations["instruction"]
         rt = self.runtime()
-        logits, hidden = rt.forward_hi(observations["rgb"], observations["depth"], instruction, masks,
-                                       rnn_hidden_states)
+        if self.training and torch.is_grad_enabled():
+            # training step (hierarchical_trainer.py:506-513): frozen encoders on the engine, the
+            # trainable tail under autograd (torch_tail.py).  BatchNorm stays in eval mode -- the
+            # reference's train()-mode drift of the frozen ResNet statistics is not reproduced.
+            from . import torch_tail
+
+            dev = rt.device
+            feats = rt.encode(observations["rgb"], observations["depth"], instruction,
+                              n_envs=rnn_hidden_states.shape[1])
+            logits, hidden = torch_tail.hi_tail(self, feats["rgb_feat"], feats["depth_feat"], feats["bert"],
+                                                rnn_hidden_states.to(dev, torch.float32),
+                                                masks.to(dev, torch.float32), self.dropout_p)
+        else:
+            logits, hidden = rt.forward_hi(observations["rgb"], observations["depth"], instruction, masks,
+                                           rnn_hidden_states)
         del observations["instruction"]            # the reference mutates the caller's dict (:196)
         return logits, hidden

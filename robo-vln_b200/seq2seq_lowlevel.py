@@ -6,6 +6,8 @@ model's and the observations are the tensors hi just saw, the trunk features are
 """
 from __future__ import annotations
 
+import torch
+
 from .modules import HcmModuleBase, build_param_tree
 from .param_spec import lo_spec
 from .seq2seq_highlevel_cma import _check_config
@@ -32,4 +34,14 @@ class Seq2Seq_LowLevel(HcmModuleBase):
         if "rgb_features" in observations or "depth_features" in observations:
             raise NotImplementedError("pre-computed rgb_features/depth_features are not supported yet")
         rt = self.runtime()
+        if self.training and torch.is_grad_enabled():
+            # training step (hierarchical_trainer.py:539-555): see Seq2Seq_HighLevel_CMA.forward
+            from . import torch_tail
+
+            dev = rt.device
+            feats = rt.encode(observations["rgb"], observations["depth"], None, n_envs=rnn_hidden_states.shape[1],
+                              use_lo_weights=True)
+            return torch_tail.lo_tail(self, feats["rgb_gmean"], feats["depth_feat"],
+                                      rnn_hidden_states.to(dev, torch.float32), masks.to(dev, torch.float32),
+                                      discrete_actions.to(dev))
         return rt.forward_lo(observations["rgb"], observations["depth"], masks, rnn_hidden_states, discrete_actions)
