@@ -252,6 +252,12 @@ int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in
 int rvb_groupnorm(const void* x_bf16, float* stats, const float* gamma, const float* beta, int NB, int HW, int C, int G,
                   int relu, const void* res_bf16, void* out_bf16, int64_t out_pitch, void* stream) {
   return guarded([&] {
+    if (stats == nullptr) {   // fused statistics + apply (what the engine runs)
+      GnApply a{B16(x_bf16), nullptr, gamma, beta, NB, HW, C, G, relu, res_bf16 != nullptr ? 1 : 0, B16(res_bf16),
+                nullptr, nullptr, nullptr, B16(out_bf16), out_pitch};
+      gn_fused(a, S(stream));
+      return;
+    }
     RVB_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(NB) * G * 2 * sizeof(float), S(stream)));
     gn_stats(B16(x_bf16), stats, NB, HW, C, G, S(stream));
     GnApply a{B16(x_bf16), stats, gamma, beta, NB, HW, C, G, relu, res_bf16 != nullptr ? 1 : 0, B16(res_bf16),

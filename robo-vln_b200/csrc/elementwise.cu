@@ -289,6 +289,111 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused GroupNorm: statistics + normalise + affine (+ residual | + second normalised branch)
+// + ReLU in ONE launch, one CTA per sample.  Pass 1 reduces (sum, sumsq) per channel in a fixed
+// order (bit-reproducible), turns them into per-channel scale/shift tables in shared memory;
+// pass 2 re-reads the sample (L2-resident: <= 256 KB) and writes the result.  Halves the number
+// of launches of the latency-bound depth trunk compared with separate stats / apply kernels.
+// ---------------------------------------------------------------------------------------
+constexpr int GNF_THREADS = 512;
+__global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const GnApplyDev a) {
+  extern __shared__ __align__(16) uint8_t gnf_dyn[];
+  float (*ps)[8] = reinterpret_cast<float (*)[8]>(gnf_dyn);
+  float (*pq)[8] = ps + GNF_THREADS;
+  float* sc_x = reinterpret_cast<float*>(pq + GNF_THREADS);   // [C] scale, [C] shift for x; then for res (mode 2)
+  float* sh_x = sc_x + a.C;
+  float* sc_r = sh_x + a.C;
+  float* sh_r = sc_r + a.C;
+  const int img = blockIdx.x;
+  const int cv = a.C / 8;
+  const int slot = threadIdx.x % cv;
+  const int prow = threadIdx.x / cv;
+  const int rows_per_iter = blockDim.x / cv;   // power of two
+  const int cpg = a.C / a.G;
+  const float cnt = static_cast<float>(a.HW) * static_cast<float>(cpg);
+  const int n_src = (a.res_mode == 2) ? 2 : 1;
+  for (int src = 0; src < n_src; ++src) {
+    const h16* base = (src == 0 ? a.x : a.res) + static_cast<long long>(img) * a.HW * a.C + slot * 8;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0f;
+    for (int p = prow; p < a.HW; p += rows_per_iter) {
+      float f[8];
+      load8(base + static_cast<long long>(p) * a.C, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+    }
+    __syncthreads();   // previous use of ps/pq finished
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ps[threadIdx.x][j] = s[j];
+      pq[threadIdx.x][j] = q[j];
+    }
+    __syncthreads();
+    for (int stride = rows_per_iter >> 1; stride > 0; stride >>= 1) {
+      if (prow < stride) {
+        const int other = threadIdx.x + stride * cv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ps[threadIdx.x][j] += ps[other][j];
+          pq[threadIdx.x][j] += pq[other][j];
+        }
+      }
+      __syncthreads();
+    }
+    // per-channel scale / shift (thread c: group of channel c, fixed-order sum over its cpg channels)
+    const float* gam = (src == 0) ? a.gamma : a.res_gamma;
+    const float* bet = (src == 0) ? a.beta : a.res_beta;
+    float* sc = (src == 0) ? sc_x : sc_r;
+    float* sh = (src == 0) ? sh_x : sh_r;
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      const int c0 = (c / cpg) * cpg;
+      float ss = 0.0f, qq = 0.0f;
+      for (int k = c0; k < c0 + cpg; ++k) {
+        ss += ps[k >> 3][k & 7];
+        qq += pq[k >> 3][k & 7];
+      }
+      const float mean = ss / cnt;
+      const float var = fmaxf(qq / cnt - mean * mean, 0.0f);
+      const float scale = rsqrtf(var + 1e-5f) * __ldg(gam + c);
+      sc[c] = scale;
+      sh[c] = __ldg(bet + c) - mean * scale;
+    }
+    __syncthreads();
+  }
+  // pass 2
+  const long long pix0 = static_cast<long long>(img) * a.HW;
+  for (int i = threadIdx.x; i < a.HW * cv; i += blockDim.x) {
+    const int v = i % cv;
+    const long long pix = pix0 + i / cv;
+    const int c0 = v * 8;
+    float f[8];
+    load8(a.x + pix * a.C + c0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc_x[c0 + j], sh_x[c0 + j]);
+    if (a.res_mode == 1) {
+      float r[8];
+      load8(a.res + pix * a.C + c0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    } else if (a.res_mode == 2) {
+      float r[8];
+      load8(a.res + pix * a.C + c0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += fmaf(r[j], sc_r[c0 + j], sh_r[c0 + j]);
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+    store8(a.out + pix * a.out_pitch + c0, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // RGB head pooling: layer4 output [NB,H,W,C] ->
 //   tokens[img][cell][0..C)  = adaptive_avg_pool2d(4,4)   (resnet_encoders.py:162-166)
 //   cellmean[img][0..C)      = mean over the 16 cells     (rgb_linear's AdaptiveAvgPool1d(1))
@@ -563,6 +668,25 @@ void gn_stats(const h16* x, float* stats, int NB, int HW, int C, int G, cudaStre
   const int cv = C / 8;
   RVB_CHECK(C % 8 == 0 && cv <= 256 && 256 % cv == 0 && G <= 64 && C % G == 0, "gn_stats: unsupported C/G");
   gn_stats_kernel<<<NB, 256, 0, s>>>(x, stats, HW, C, G);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void gn_fused(const GnApply& a, cudaStream_t s) {
+  const int cv = a.C / 8;
+  RVB_CHECK(a.C % 8 == 0 && a.C % a.G == 0 && a.out_pitch % 8 == 0 && cv <= GNF_THREADS && GNF_THREADS % cv == 0 &&
+                a.C <= 2048, "gn_fused: unsupported shape");
+  GnApplyDev d;
+  d.x = a.x; d.stats = nullptr; d.gamma = a.gamma; d.beta = a.beta;
+  d.NB = a.NB; d.HW = a.HW; d.C = a.C; d.G = a.G; d.relu = a.relu; d.res_mode = a.res_mode;
+  d.res = a.res; d.res_stats = nullptr; d.res_gamma = a.res_gamma; d.res_beta = a.res_beta;
+  d.out = a.out; d.out_pitch = a.out_pitch;
+  const size_t smem = static_cast<size_t>(2) * GNF_THREADS * 8 * sizeof(float) + static_cast<size_t>(4) * a.C * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    RVB_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GNF_THREADS * 8 * 4 + 4 * 2048 * 4));
+    attr = true;
+  }
+  gn_fused_kernel<<<a.NB, GNF_THREADS, smem, s>>>(d);
   RVB_CUDA(cudaGetLastError());
 }
 

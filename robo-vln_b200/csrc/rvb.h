@@ -130,6 +130,7 @@ struct GnApply {
   h16* out; int64_t out_pitch;  // elements per pixel in the output (>= C)
 };
 void gn_apply(const GnApply& a, cudaStream_t s);
+void gn_fused(const GnApply& a, cudaStream_t s);   // statistics + apply in one launch (a.stats / a.res_stats unused)
 void rgb_pool(const h16* feat, int NB, int H, int W, int C, h16* tokens, int64_t tok_pitch, h16* cellmean,
               int64_t cm_pitch, h16* gmean, cudaStream_t s);
 void fill_spatial_embedding(const float* emb_flat, h16* tokens, int NB, int64_t tok_pitch, int col0, h16* cellmean,

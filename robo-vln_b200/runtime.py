@@ -258,7 +258,7 @@ class HcmRuntime:
         {"rgb_feat" [B,16,2048], "rgb_gmean" [B,2048], "depth_feat" [B,16,128], "bert" [1|B,L,768]}."""
         rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
         B = rgb.shape[0]
-        hi, _ = self._modules()
+        self.sync_weights()          # may invalidate the current plan (new weights / newly attached half)
         with_bert = instruction is not None
         i_f32 = i_i64 = None
         if with_bert:
@@ -274,8 +274,6 @@ class HcmRuntime:
         if not (self._shape_key and self._shape_key[0] == B and self._shape_key[4] == tuple(rgb.shape[1:3])
                 and (not with_bert or (self._shape_key[2], self._shape_key[3]) == (L, rows))):
             self.ensure_plan(B, N, L, rows, rgb.shape[1:3], depth.shape[1:3])
-        else:
-            self.sync_weights()
         sig = self._sig(rgb, depth)
         fresh = not (sig == self._obs_sig and (self._shares or not use_lo_weights))
         if fresh or with_bert:

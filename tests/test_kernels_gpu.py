@@ -39,6 +39,16 @@ def test_groupnorm(C, G, HW, NB, dtype):
     xr = x.float().permute(0, 2, 1)  # [NB, C, HW]
     ref = torch.relu(F.group_norm(xr, G, gamma, beta, 1e-5) + res.float().permute(0, 2, 1)).permute(0, 2, 1)
     assert _rel(out, ref) < OUT_TOL[dtype]
+    # fused statistics + apply kernel (stats = NULL): what the depth trunk runs; must agree bit for bit
+    # from run to run (fixed-order reductions) and with the two-kernel path up to fp32 summation order
+    out2 = torch.empty_like(out)
+    out3 = torch.empty_like(out)
+    for o in (out2, out3):
+        check(lib(dtype).rvb_groupnorm(P(x), None, P(gamma), P(beta), NB, HW, C, G, 1, P(res), P(o), C, stream()),
+              "rvb_groupnorm(fused)", dtype)
+    torch.cuda.synchronize()
+    assert _rel(out2, ref) < OUT_TOL[dtype]
+    assert torch.equal(out2, out3)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
