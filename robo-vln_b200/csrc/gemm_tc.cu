@@ -303,8 +303,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (n >= p.N) break;  // uniform across the group
           // the staging buffer is free once the previous store from it has been read out
           if (store_pending) {
-            if (leader) tma_store_wait_read<0>();
-            named_bar_sync(1 + group, 128);
+            if (p.plain) {   // per-warp stores: only this warp's previous store has to have drained
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            } else {
+              if (leader) tma_store_wait_read<0>();
+              named_bar_sync(1 + group, 128);
+            }
           }
           if (p.out_f32) {
             uint32_t v[32];
@@ -341,11 +346,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           fence_proxy_async();  // make the st.shared visible to the TMA (async proxy)
-          named_bar_sync(1 + group, 128);
-          if (leader) {
-            if (p.plain) tma_store_4d(&tmC, stage_buf, n, mt * BLOCK_M, 0, 0);
-            else tma_store_4d(&tmC, stage_buf, n, 0, h0, img);
-            tma_store_commit();
+          if (p.plain) {
+            // plain GEMM: the output box is 32 rows, so every warp stores its own quarter of the
+            // tile as soon as it is staged -- no cross-warp barrier, the eight warps run decoupled
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmC, stage_buf + quad * 4096, n, mt * BLOCK_M + quad * 32, 0, 0);
+              tma_store_commit();
+            }
+          } else {
+            named_bar_sync(1 + group, 128);
+            if (leader) {
+              tma_store_4d(&tmC, stage_buf, n, 0, h0, img);
+              tma_store_commit();
+            }
           }
           store_pending = true;
         }
@@ -405,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     // staging smem must stay valid until the last bulk store has read it
-    if (leader && store_pending) tma_store_wait_read<0>();
+    if (store_pending && (p.plain ? (lane == 0) : leader)) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -677,7 +691,7 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
     if (p.plain) {
       const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(M), 1, 1};
       const uint64_t strides[3] = {pitchC, pitchC * static_cast<uint64_t>(M), pitchC * static_cast<uint64_t>(M)};
-      const uint32_t box[4] = {ccols, BLOCK_M, 1, 1};
+      const uint32_t box[4] = {ccols, 32, 1, 1};   // one epilogue warp's rows (per-warp stores)
       encode_map(&plan->tmC, cdt, g.out, 4, dims, strides, box, ones);
     } else {
       const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
