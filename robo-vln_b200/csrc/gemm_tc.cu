@@ -98,9 +98,11 @@ RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, cons
 template <int BN, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmTcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const GemmTcParams p) {
   using C = Cfg<BN, CTAS>;
-  constexpr int STAGES = C::STAGES;
+  constexpr int STAGES = C::STAGES;       // ring capacity; p.nstages (<= STAGES) are in use
+  const int nstages = p.nstages;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;   // 0 = leader of the pair
   const int unit = (CTAS == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int num_units = (CTAS == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -116,6 +118,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* rbar_base = bars + 2 * STAGES + 5;   // [8] residual-slice barriers, one per epilogue warp
+  // residual-prefetch mode: the pipeline runs with fewer stages and the B buffers of the unused
+  // stages hold eight 4 KiB residual slices (32 rows x 128 B, one per epilogue warp)
+  uint8_t* res_slices = smem_b + nstages * C::B_STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,6 +130,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if (p.res_tma) tma_prefetch_desc(&tmR);
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&rbar_base[i], 1);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -185,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tma_load_2d_2sm(sb, &tmB, full_leader, tap * p.Cin + cb * BLOCK_K,
                             nt * BN + static_cast<int>(cta_rank) * (BN / 2));
-            if (++stage == STAGES) {
+            if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
             }
@@ -200,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, s - p.pad, h0 * p.stride + r - p.pad, img);
           }
           tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cb * BLOCK_K, nt * BN);
-          if (++stage == STAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -237,7 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
           if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]);
           else umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -268,6 +276,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     bool store_pending = false;
     const uint32_t tempty_leader0 = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
     const uint32_t tempty_leader1 = (CTAS == 2) ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u;
+    // ---- residual prefetch (plain GEMM, 16-bit output): each warp TMA-loads the residual of its
+    // next (tile, chunk) into its private slice while it is still busy with the current one, so
+    // the DRAM latency of the residual never sits on the epilogue's critical path
+    uint8_t* rslice = res_slices + (warp - 2) * 4096;
+    uint64_t* rbar = &rbar_base[warp - 2];
+    uint32_t rphase = 0;
+    auto issue_res = [&](int tile_, int ch_) {   // lane 0 only
+      const int mu_ = tile_ / p.n_tiles;
+      const int nt_ = tile_ - mu_ * p.n_tiles;
+      const int mt_ = mu_ * CTAS + static_cast<int>(cta_rank);
+      mbar_arrive_expect_tx(rbar, 4096);
+      tma_load_4d(rslice, &tmR, rbar, nt_ * BN + ch_ * 64, mt_ * BLOCK_M + quad * 32, 0, 0);
+    };
+    auto chunk_exists = [&](int tile_, int ch_) {
+      if (tile_ >= total_tiles || ch_ >= BN / 64) return false;
+      const int nt_ = tile_ % p.n_tiles;
+      return nt_ * BN + ch_ * 64 < p.N;
+    };
+    if (p.res_tma && lane == 0 && chunk_exists(unit, group)) issue_res(unit, group);
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int mu = tile / p.n_tiles;
       const int nt = tile - mu * p.n_tiles;
@@ -324,16 +351,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
+            if (p.res_tma) {   // this chunk's residual slice has landed
+              mbar_wait(rbar, rphase);
+              rphase ^= 1;
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               uint32_t v[32];
               __syncwarp();
               tmem_ld_32x32(taddr + c0 + half * 32, v);
+              uint4 rv[4];
+              if (p.res_tma) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  rv[j] = *reinterpret_cast<const uint4*>(rslice + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4));
+                if (half == 1) {
+                  // every lane has read its row: the slice can take the next (tile, chunk)
+                  __syncwarp();
+                  if (lane == 0) {
+                    if (chunk_exists(tile, ch + 2)) issue_res(tile, ch + 2);
+                    else if (chunk_exists(tile + num_units, group)) issue_res(tile + num_units, group);
+                  }
+                }
+              }
               tmem_ld_wait();
               float f[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-              epilogue_math(f, p, n + half * 32, res_row);
+              if (p.res_tma) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float2 t;
+                  t = unpack_h2(rv[j].x); f[8 * j] += t.x; f[8 * j + 1] += t.y;
+                  t = unpack_h2(rv[j].y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
+                  t = unpack_h2(rv[j].z); f[8 * j + 4] += t.x; f[8 * j + 5] += t.y;
+                  t = unpack_h2(rv[j].w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
+                }
+              }
+              epilogue_math(f, p, n + half * 32, p.res_tma ? nullptr : res_row);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 q;
@@ -501,13 +556,22 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CTAS == 2) ? 1 : 0;
-  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS>, plan.tmA, plan.tmB, plan.tmC, plan.p));
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
 }
 
 bool use_pair_mma() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("ROBOVLN_PAIR_MMA");
+    v = (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+bool use_res_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_RES_TMA");
     v = (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
   }
   return v == 1;
@@ -700,6 +764,25 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
       const uint32_t box[4] = {ccols, static_cast<uint32_t>(Wo), static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.nb)};
       encode_map(&plan->tmC, cdt, g.out, 4, dims, strides, box, ones);
     }
+  }
+
+  // residual prefetch through TMA (plain GEMM, 16-bit output, one residual row per output row)
+  p.res_tma = (p.tma_store && p.plain && !g.out_f32 && g.res != nullptr && g.res_rows == 0 && use_res_tma()) ? 1 : 0;
+  {
+    const int b_stage = (best_bn / best_ctas) * BLOCK_K * 2;
+    const int max_stages = std::min(8, SMEM_STAGE_BUDGET / (A_STAGE_BYTES + b_stage));
+    // the residual slices (32 KiB) live in the B buffers of the stages given up
+    p.nstages = p.res_tma ? max_stages - (32768 + b_stage - 1) / b_stage : max_stages;
+    RVB_CHECK(p.nstages >= 2, "gemm: too few pipeline stages");
+  }
+  if (p.res_tma) {
+    const uint64_t pitchR = static_cast<uint64_t>(g.ldr) * 2;
+    const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(M), 1, 1};
+    const uint64_t strides[3] = {pitchR, pitchR * static_cast<uint64_t>(M), pitchR * static_cast<uint64_t>(M)};
+    const uint32_t box[4] = {64, 32, 1, 1};
+    encode_map(&plan->tmR, kH16Type, g.res, 4, dims, strides, box, ones);
+  } else {
+    plan->tmR = plan->tmC;
   }
 
   const long long units = static_cast<long long>((p.m_tiles + best_ctas - 1) / best_ctas) * p.n_tiles;

@@ -92,12 +92,15 @@ struct GemmTcParams {
   long long ldc;
   int out_f32;
   int tma_store;     // 1: smem-staged TMA store epilogue, 0: direct global stores (validation)
+  int res_tma;       // 1: residual chunks prefetched by TMA into per-warp smem slices
+  int nstages;       // pipeline stages in use (fewer when the residual slices take their place)
 };
 
 struct GemmTcPlan {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmC;
+  alignas(64) CUtensorMap tmR;   // residual (plain GEMM, 32-row boxes); a copy of tmC when unused
   GemmTcParams p;
   int BN = 128;
   int ctas = 1;        // 2: CTA-pair (cta_group::2) kernel, 256 x BN tiles
