@@ -91,7 +91,7 @@ RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, cons
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
   } else if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
   }
 }
 
