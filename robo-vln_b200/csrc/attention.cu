@@ -43,6 +43,7 @@ RVB_DEVICE void mma_h16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t 
 template <int LKT>
 __global__ void __launch_bounds__(256) bert_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ ctx, int L,
                                                         int heads) {
+  RVB_PDL_PROLOGUE();
   constexpr int LP = LKT * 16;
   extern __shared__ __align__(16) uint8_t sm_raw[];
   h16* sQ = reinterpret_cast<h16*>(sm_raw);
@@ -169,7 +170,7 @@ void launch_bert_attn(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStr
   const int qtiles = (L + 15) / 16;
   const int nwarps = qtiles < 8 ? qtiles : 8;
   dim3 grid(heads, R);
-  bert_attn_kernel<LKT><<<grid, nwarps * 32, smem, s>>>(qkv, ctx, L, heads);
+  launch_k(bert_attn_kernel<LKT>, dim3(grid), dim3(nwarps * 32), smem, s, qkv, ctx, L, heads);
   RVB_CUDA(cudaGetLastError());
 }
 
@@ -180,6 +181,7 @@ void launch_bert_attn(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStr
 constexpr int VH = 4, VK = 16, VP = HD + 1;
 __global__ void __launch_bounds__(256) vla_attn_kernel(const h16* __restrict__ q, const h16* __restrict__ kv,
                                                        h16* __restrict__ ctx, int B, int L, int q_shared) {
+  RVB_PDL_PROLOGUE();
   __shared__ float sK[VH * VK * VP];
   __shared__ float sV[VH * VK * VP];
   const int b = blockIdx.x, mod = blockIdx.y;
@@ -248,7 +250,7 @@ void bert_self_attention(const h16* qkv, h16* ctx, int R, int L, int heads, cuda
 void vla_cross_attention(const h16* q, const h16* kv, h16* ctx, int B, int L, int n_mod, int q_shared,
                          cudaStream_t s) {
   dim3 grid(B, n_mod);
-  vla_attn_kernel<<<grid, 256, 0, s>>>(q, kv, ctx, B, L, q_shared);
+  launch_k(vla_attn_kernel, dim3(grid), dim3(256), 0, s, q, kv, ctx, B, L, q_shared);
   RVB_CUDA(cudaGetLastError());
 }
 

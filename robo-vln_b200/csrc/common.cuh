@@ -31,6 +31,21 @@ RVB_DEVICE bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may become resident while the
+// previous kernel of the stream is still draining.  pdl_wait() blocks until that kernel has
+// completed and its writes are visible; everything before it (barrier init, TMEM allocation,
+// descriptor prefetch, staging of constant weights) overlaps the predecessor's tail.
+// ---------------------------------------------------------------------------------------
+RVB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+RVB_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define RVB_PDL_PROLOGUE()            \
+  do {                                \
+    ::rvb::pdl_launch_dependents();   \
+    ::rvb::pdl_wait();                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------
 RVB_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

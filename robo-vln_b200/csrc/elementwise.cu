@@ -5,6 +5,8 @@
 #include "rvb.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace rvb {
 
@@ -34,6 +36,7 @@ RVB_DEVICE void store8(h16* p, const float (&f)[8]) {
 constexpr int STEM_PIX = 32;
 __global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __restrict__ rgb, h16* __restrict__ out,
                                                               int NB, int H, int W, int Ho, int Wo, int Kpitch) {
+  RVB_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint8_t sm_raw[];
   h16* tile = reinterpret_cast<h16*>(sm_raw);  // [STEM_PIX][Kpitch]
   const long long M = static_cast<long long>(NB) * Ho * Wo;
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(256) rgb_stem_im2col_kernel(const float* __res
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rgb_pad_convert_kernel(const float* __restrict__ rgb, h16* __restrict__ out,
                                                               int NB, int H, int W, int Hp, int Wp) {
+  RVB_PDL_PROLOGUE();
   const long long total = static_cast<long long>(NB) * Hp * Wp;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -97,6 +101,7 @@ __global__ void __launch_bounds__(256) rgb_pad_convert_kernel(const float* __res
 // ---------------------------------------------------------------------------------------
 __global__ void maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict__ out, int NB, int H, int W, int C,
                                     int Ho, int Wo) {
+  RVB_PDL_PROLOGUE();
   const int cv = C / 8;
   const long long total = static_cast<long long>(NB) * Ho * Wo * cv;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -133,6 +138,7 @@ __global__ void maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict_
 __global__ void __launch_bounds__(256) depth_stem_kernel(const float* __restrict__ depth, const float* __restrict__ w,
                                                          h16* __restrict__ out, int H, int W, int Hp, int Wp, int Ho,
                                                          int Wo) {
+  RVB_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* ws = reinterpret_cast<float*>(sm_raw);  // [49][32]
   float* rows = ws + 49 * 32;                    // [7][Wp + 6]
@@ -176,6 +182,7 @@ __global__ void __launch_bounds__(256) depth_stem_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_stats_kernel(const h16* __restrict__ x, float* __restrict__ stats, int HW,
                                                        int C, int G) {
+  RVB_PDL_PROLOGUE();
   __shared__ float ps[256][8];
   __shared__ float pq[256][8];
   const int img = blockIdx.x;
@@ -246,6 +253,7 @@ RVB_DEVICE void gn_scale_shift(const float* stats, int img, int G, int g, float 
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
+  RVB_PDL_PROLOGUE();
   const int cv = a.C / 8;
   const int cpg = a.C / a.G;
   const float cnt = static_cast<float>(a.HW) * static_cast<float>(cpg);
@@ -297,6 +305,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
 // ---------------------------------------------------------------------------------------
 constexpr int GNF_THREADS = 512;
 __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const GnApplyDev a) {
+  RVB_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint8_t gnf_dyn[];
   float (*ps)[8] = reinterpret_cast<float (*)[8]>(gnf_dyn);
   float (*pq)[8] = ps + GNF_THREADS;
@@ -403,6 +412,7 @@ __global__ void __launch_bounds__(256) rgb_pool_kernel(const h16* __restrict__ f
                                                        h16* __restrict__ tokens, long long tok_pitch,
                                                        h16* __restrict__ cellmean, long long cm_pitch,
                                                        h16* __restrict__ gmean) {
+  RVB_PDL_PROLOGUE();
   const int img = blockIdx.x;
   const h16* base = feat + static_cast<long long>(img) * H * W * C;
   for (int v = threadIdx.x; v < C / 8; v += blockDim.x) {
@@ -454,6 +464,7 @@ __global__ void __launch_bounds__(256) rgb_pool_kernel(const h16* __restrict__ f
 __global__ void fill_spatial_embedding_kernel(const float* __restrict__ flat, h16* __restrict__ tokens, int NB,
                                               long long tok_pitch, int col0, h16* __restrict__ cellmean,
                                               long long cm_pitch) {
+  RVB_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NB * 64) return;
   const int img = i / 64, c = i % 64;
@@ -477,6 +488,7 @@ __global__ void __launch_bounds__(256) bert_embed_ln_kernel(const long long* __r
                                                             const float* __restrict__ type0,
                                                             const float* __restrict__ g, const float* __restrict__ b,
                                                             h16* __restrict__ out) {
+  RVB_PDL_PROLOGUE();
   constexpr int D = NV * 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -524,6 +536,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
                                                              const float* __restrict__ b, float eps,
                                                              const float* __restrict__ pe, int pe_rows,
                                                              h16* __restrict__ out) {
+  RVB_PDL_PROLOGUE();
   constexpr int D = NV * 128;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -565,6 +578,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 // out[b*out_pitch + mod*mod_stride + d]   (cross_pooler, seq2seq_highlevel_cma.py:114-115,209-210)
 __global__ void token_mean_kernel(const h16* __restrict__ x, int B, int L, int D, h16* __restrict__ out,
                                   long long out_pitch, long long mod_stride) {
+  RVB_PDL_PROLOGUE();
   const int g = blockIdx.x;
   const int mod = g / B, b = g % B;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -577,6 +591,7 @@ __global__ void token_mean_kernel(const h16* __restrict__ x, int B, int L, int D
 
 __global__ void sub_task_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ table, int B,
                                       h16* __restrict__ out, long long out_pitch) {
+  RVB_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 32) return;
   const int b = i / 32, c = i % 32;
@@ -588,6 +603,7 @@ __global__ void sub_task_embed_kernel(const long long* __restrict__ ids, const f
 // out[m][o] = dot(y[m], w[o]) + b[o], one warp per output (tiny heads: 512 -> 4 / 2 / 1)
 __global__ void heads_linear_kernel(const float* __restrict__ y, int M, int K, const float* __restrict__ w,
                                     const float* __restrict__ b, int n_out, float* __restrict__ out) {
+  RVB_PDL_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M * n_out) return;
@@ -599,6 +615,7 @@ __global__ void heads_linear_kernel(const float* __restrict__ y, int M, int K, c
 }
 
 __global__ void argmax_rows_kernel(const float* __restrict__ x, int M, int n, long long* __restrict__ out) {
+  RVB_PDL_PROLOGUE();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   int best = 0;
@@ -615,6 +632,7 @@ __global__ void argmax_rows_kernel(const float* __restrict__ x, int M, int n, lo
 
 // PE[p,2i] = sin(p / 10000^(2i/D)), PE[p,2i+1] = cos(same)   (common/utils.py:167-185)
 __global__ void sinusoid_table_kernel(float* __restrict__ pe, int L, int D) {
+  RVB_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L * (D / 2)) return;
   const int p = i / (D / 2), k = i % (D / 2);
@@ -636,14 +654,14 @@ void rgb_stem_im2col(const float* rgb, h16* out, int NB, int H, int W, int Kpitc
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const long long M = static_cast<long long>(NB) * Ho * Wo;
   const int blocks = static_cast<int>((M + STEM_PIX - 1) / STEM_PIX);
-  rgb_stem_im2col_kernel<<<blocks, 256, STEM_PIX * Kpitch * 2, s>>>(rgb, out, NB, H, W, Ho, Wo, Kpitch);
+  launch_k(rgb_stem_im2col_kernel, dim3(blocks), dim3(256), STEM_PIX * Kpitch * 2, s, rgb, out, NB, H, W, Ho, Wo, Kpitch);
   RVB_CUDA(cudaGetLastError());
 }
 
 void rgb_pad_convert(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s) {
   RVB_CHECK(Wp >= W + 6, "rgb_pad_convert: padded width too small");
   const long long total = static_cast<long long>(NB) * (H + 6) * Wp;
-  rgb_pad_convert_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(rgb, out, NB, H, W, H + 6, Wp);
+  launch_k(rgb_pad_convert_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, rgb, out, NB, H, W, H + 6, Wp);
   RVB_CUDA(cudaGetLastError());
 }
 
@@ -651,7 +669,7 @@ void maxpool3x3s2(const h16* in, h16* out, int NB, int H, int W, int C, cudaStre
   RVB_CHECK(C % 8 == 0, "maxpool: C % 8");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(NB) * Ho * Wo * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(in, out, NB, H, W, C, Ho, Wo);
+  launch_k(maxpool3x3s2_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, in, out, NB, H, W, C, Ho, Wo);
   RVB_CUDA(cudaGetLastError());
 }
 
@@ -660,21 +678,21 @@ void depth_stem_conv(const float* depth, const float* w, h16* out, int NB, int H
   const int Ho = (Hp + 6 - 7) / 2 + 1, Wo = (Wp + 6 - 7) / 2 + 1;
   const size_t smem = (49 * 32 + 7 * (Wp + 6)) * sizeof(float);
   dim3 grid(Ho, NB);
-  depth_stem_kernel<<<grid, 256, smem, s>>>(depth, w, out, H, W, Hp, Wp, Ho, Wo);
+  launch_k(depth_stem_kernel, dim3(grid), dim3(256), smem, s, depth, w, out, H, W, Hp, Wp, Ho, Wo);
   RVB_CUDA(cudaGetLastError());
 }
 
 void gn_stats(const h16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s) {
   const int cv = C / 8;
   RVB_CHECK(C % 8 == 0 && cv <= 256 && 256 % cv == 0 && G <= 64 && C % G == 0, "gn_stats: unsupported C/G");
-  gn_stats_kernel<<<NB, 256, 0, s>>>(x, stats, HW, C, G);
+  launch_k(gn_stats_kernel, dim3(NB), dim3(256), 0, s, x, stats, HW, C, G);
   RVB_CUDA(cudaGetLastError());
 }
 
 void gn_fused(const GnApply& a, cudaStream_t s) {
   const int cv = a.C / 8;
   RVB_CHECK(a.C % 8 == 0 && a.C % a.G == 0 && a.out_pitch % 8 == 0 && cv <= GNF_THREADS && GNF_THREADS % cv == 0 &&
-                a.C <= 2048, "gn_fused: unsupported shape");
+                a.C <= 2048 && a.G <= 16, "gn_fused: unsupported shape");
   GnApplyDev d;
   d.x = a.x; d.stats = nullptr; d.gamma = a.gamma; d.beta = a.beta;
   d.NB = a.NB; d.HW = a.HW; d.C = a.C; d.G = a.G; d.relu = a.relu; d.res_mode = a.res_mode;
@@ -686,7 +704,7 @@ void gn_fused(const GnApply& a, cudaStream_t s) {
     RVB_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GNF_THREADS * 8 * 4 + 4 * 2048 * 4));
     attr = true;
   }
-  gn_fused_kernel<<<a.NB, GNF_THREADS, smem, s>>>(d);
+  launch_k(gn_fused_kernel, dim3(a.NB), dim3(GNF_THREADS), smem, s, d);
   RVB_CUDA(cudaGetLastError());
 }
 
@@ -698,20 +716,20 @@ void gn_apply(const GnApply& a, cudaStream_t s) {
   d.res = a.res; d.res_stats = a.res_stats; d.res_gamma = a.res_gamma; d.res_beta = a.res_beta;
   d.out = a.out; d.out_pitch = a.out_pitch;
   const long long total = static_cast<long long>(a.NB) * a.HW * (a.C / 8);
-  gn_apply_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(d);
+  launch_k(gn_apply_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, d);
   RVB_CUDA(cudaGetLastError());
 }
 
 void rgb_pool(const h16* feat, int NB, int H, int W, int C, h16* tokens, int64_t tok_pitch, h16* cellmean,
               int64_t cm_pitch, h16* gmean, cudaStream_t s) {
   RVB_CHECK(C % 8 == 0 && H >= 4 && W >= 4, "rgb_pool: bad shape");
-  rgb_pool_kernel<<<NB, 256, 0, s>>>(feat, H, W, C, tokens, tok_pitch, cellmean, cm_pitch, gmean);
+  launch_k(rgb_pool_kernel, dim3(NB), dim3(256), 0, s, feat, H, W, C, tokens, tok_pitch, cellmean, cm_pitch, gmean);
   RVB_CUDA(cudaGetLastError());
 }
 
 void fill_spatial_embedding(const float* emb_flat, h16* tokens, int NB, int64_t tok_pitch, int col0, h16* cellmean,
                             int64_t cm_pitch, cudaStream_t s) {
-  fill_spatial_embedding_kernel<<<(NB * 64 + 127) / 128, 128, 0, s>>>(emb_flat, tokens, NB, tok_pitch, col0, cellmean,
+  launch_k(fill_spatial_embedding_kernel, dim3((NB * 64 + 127) / 128), dim3(128), 0, s, emb_flat, tokens, NB, tok_pitch, col0, cellmean,
                                                                       cm_pitch);
   RVB_CUDA(cudaGetLastError());
 }
@@ -719,7 +737,7 @@ void fill_spatial_embedding(const float* emb_flat, h16* tokens, int NB, int64_t 
 void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, int R, int L, const float* word,
                    const float* pos, const float* type0, const float* g, const float* b, h16* out, cudaStream_t s) {
   const long long warps = static_cast<long long>(R) * L;
-  bert_embed_ln_kernel<6><<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(
+  launch_k(bert_embed_ln_kernel<6>, dim3(static_cast<int>((warps * 32 + 255) / 256)), dim3(256), 0, s, 
       reinterpret_cast<const long long*>(ids_i64), ids_f32, id_rows, R, L, word, pos, type0, g, b, out);
   RVB_CUDA(cudaGetLastError());
 }
@@ -727,20 +745,20 @@ void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, in
 void layernorm_rows(const float* x, int M, int D, const float* g, const float* b, float eps, const float* pe,
                     int pe_rows, h16* out, cudaStream_t s) {
   const int blocks = static_cast<int>((static_cast<long long>(M) * 32 + 255) / 256);
-  if (D == 768) layernorm_rows_kernel<6><<<blocks, 256, 0, s>>>(x, M, g, b, eps, pe, pe_rows, out);
-  else if (D == 256) layernorm_rows_kernel<2><<<blocks, 256, 0, s>>>(x, M, g, b, eps, pe, pe_rows, out);
+  if (D == 768) launch_k(layernorm_rows_kernel<6>, dim3(blocks), dim3(256), 0, s, x, M, g, b, eps, pe, pe_rows, out);
+  else if (D == 256) launch_k(layernorm_rows_kernel<2>, dim3(blocks), dim3(256), 0, s, x, M, g, b, eps, pe, pe_rows, out);
   else RVB_CHECK(false, "layernorm: D must be 256 or 768");
   RVB_CUDA(cudaGetLastError());
 }
 
 void token_mean(const h16* x, int n_mod, int B, int L, int D, h16* out, int64_t out_pitch, int64_t mod_stride,
                 cudaStream_t s) {
-  token_mean_kernel<<<n_mod * B, 256, 0, s>>>(x, B, L, D, out, out_pitch, mod_stride);
+  launch_k(token_mean_kernel, dim3(n_mod * B), dim3(256), 0, s, x, B, L, D, out, out_pitch, mod_stride);
   RVB_CUDA(cudaGetLastError());
 }
 
 void sub_task_embed(const int64_t* ids, const float* table, int B, h16* out, int64_t out_pitch, cudaStream_t s) {
-  sub_task_embed_kernel<<<(B * 32 + 127) / 128, 128, 0, s>>>(reinterpret_cast<const long long*>(ids), table, B, out,
+  launch_k(sub_task_embed_kernel, dim3((B * 32 + 127) / 128), dim3(128), 0, s, reinterpret_cast<const long long*>(ids), table, B, out,
                                                              out_pitch);
   RVB_CUDA(cudaGetLastError());
 }
@@ -748,18 +766,18 @@ void sub_task_embed(const int64_t* ids, const float* table, int B, h16* out, int
 void heads_linear(const float* y, int M, int K, const float* w, const float* b, int n_out, float* out,
                   cudaStream_t s) {
   const long long warps = static_cast<long long>(M) * n_out;
-  heads_linear_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(y, M, K, w, b, n_out, out);
+  launch_k(heads_linear_kernel, dim3(static_cast<int>((warps * 32 + 255) / 256)), dim3(256), 0, s, y, M, K, w, b, n_out, out);
   RVB_CUDA(cudaGetLastError());
 }
 
 void argmax_rows(const float* x, int M, int n, int64_t* out, cudaStream_t s) {
-  argmax_rows_kernel<<<(M + 127) / 128, 128, 0, s>>>(x, M, n, reinterpret_cast<long long*>(out));
+  launch_k(argmax_rows_kernel, dim3((M + 127) / 128), dim3(128), 0, s, x, M, n, reinterpret_cast<long long*>(out));
   RVB_CUDA(cudaGetLastError());
 }
 
 void sinusoid_table(float* pe, int L, int D, cudaStream_t s) {
   const int total = L * (D / 2);
-  sinusoid_table_kernel<<<(total + 255) / 256, 256, 0, s>>>(pe, L, D);
+  launch_k(sinusoid_table_kernel, dim3((total + 255) / 256), dim3(256), 0, s, pe, L, D);
   RVB_CUDA(cudaGetLastError());
 }
 

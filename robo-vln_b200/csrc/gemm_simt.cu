@@ -18,6 +18,7 @@ struct SimtParams {
 };
 
 __global__ void gemm_simt_kernel(const SimtParams p) {
+  RVB_PDL_PROLOGUE();
   const int n = blockIdx.y * blockDim.x + threadIdx.x;
   const long long m = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y;
   if (n >= p.Cout || m >= p.M) return;
@@ -70,7 +71,7 @@ void gemm_simt_launch(const ConvGemm& g, cudaStream_t stream) {
   const long long gx = (p.M + block.y - 1) / block.y;
   RVB_CHECK(gx < (1ll << 31), "simt gemm: M too large");
   dim3 grid(static_cast<unsigned>(gx), (p.Cout + block.x - 1) / block.x);
-  gemm_simt_kernel<<<grid, block, 0, stream>>>(p);
+  launch_k(gemm_simt_kernel, dim3(grid), dim3(block), 0, stream, p);
   RVB_CUDA(cudaGetLastError());
 }
 

@@ -151,6 +151,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CTAS == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; its outputs (our A operand and
+  // residual) and our output buffer (which it may still be reading) are safe only from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   // work units: 128 x BN tiles (CTAS == 1) or 256 x BN pair tiles (CTAS == 2, this CTA = rows rank*128..)
   const int m_units = (p.m_tiles + CTAS - 1) / CTAS;
@@ -549,13 +553,22 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CTAS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CTAS == 2) ? 1 : 0;
+  cfg.numAttrs = na;
   RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
 }
 
@@ -587,6 +600,15 @@ bool use_direct_epilogue() {
 }
 
 }  // namespace
+
+bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_PDL");
+    v = (e != nullptr && std::strcmp(e, "1") == 0) ? 1 : 0;   // measured slower on B200: off by default
+  }
+  return v == 1;
+}
 
 int device_sm_count() {
   static int sms = 0;

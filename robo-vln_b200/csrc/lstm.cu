@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) lstm_step_kernel(const float* __restrict_
     dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
   }
   if (threadIdx.x == 0) s_flag = (t == 0) ? 1 : 0;
+  RVB_PDL_PROLOGUE();   // W_hh (constant) is staged above while the previous kernel drains
   __syncthreads();
   if (t != 0 && warp == 0) {
     int any = 0;
@@ -138,7 +139,7 @@ void lstm_forward(const float* gx, const h16* whh, const float* masks, int mask_
     const float* c_prev = (t == 0) ? hc_in + NH : hc_out + NH;
     float* h_next = h_scratch + (t & 1) * NH;
     float* h_final = (t == T - 1) ? hc_out : nullptr;
-    lstm_step_kernel<<<HID / UNITS_PER_CTA, 256, LSTM_SMEM, s>>>(gx, whh, masks, mask_stride, h_prev, c_prev, h_next,
+    launch_k(lstm_step_kernel, dim3(HID / UNITS_PER_CTA), dim3(256), LSTM_SMEM, s, gx, whh, masks, mask_stride, h_prev, c_prev, h_next,
                                                                  hc_out + NH, h_final, y, t, N);
   }
   RVB_CUDA(cudaGetLastError());

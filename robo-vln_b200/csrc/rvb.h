@@ -34,6 +34,25 @@ struct Error : public std::runtime_error {
                                                    #expr + " -> " + cudaGetErrorString(_e));      \
   } while (0)
 
+// Kernel launch with the programmatic-stream-serialization (PDL) attribute; every kernel of the
+// library calls griddepcontrol.wait before touching data a predecessor may still be writing.
+// ROBOVLN_PDL=0 launches plainly (validation).
+bool use_pdl();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 // ---------------------------------------------------------------------------------------
