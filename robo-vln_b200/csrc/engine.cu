@@ -348,11 +348,12 @@ void Engine::plan_bert(Stage& st) {
 //   bert: [R*L,768] h16; kvin: [2*B*16,256] h16 (rgb rows then depth rows);
 //   pooled -> out[b*out_pitch + mod*256 + d]
 // ---------------------------------------------------------------------------------------
-void Engine::plan_cross_modal(Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch) {
+void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch) {
   const int B = shp_.B, L = shp_.L;
   const int R = (shp_.instr_rows == 1) ? 1 : B;
   const int64_t MQ = static_cast<int64_t>(R) * L, MV = 2ll * B * 16, MX = 2ll * B * L;
   float* f32a = reinterpret_cast<float*>(alloc(std::max<int64_t>(MX, MV) * 256 * 4));
+  float* f32q = reinterpret_cast<float*>(alloc(MQ * 256 * 4));   // query side has its own scratch: it may run concurrently
   h16* Q0 = reinterpret_cast<h16*>(alloc(MQ * 256 * 2));
   h16* qq = reinterpret_cast<h16*>(alloc(MQ * 256 * 2));
   h16* vis = reinterpret_cast<h16*>(alloc(MV * 256 * 2));
@@ -366,15 +367,15 @@ void Engine::plan_cross_modal(Stage& st, const h16* bert, const h16* kvin, h16* 
   const std::string p = "hi.vla";
   const float* ln0w = Wf(p + ".ln0.w", {256});
   const float* ln0b = Wf(p + ".ln0.b", {256});
-  st.push_back([pe, L](cudaStream_t s) { sinusoid_table(pe, L, 256, s); return 1; });
-  // query side (shared by both modalities)
-  add_gemm(st, linear(bert, MQ, 768, 768, Wb(p + ".ins_fc.w", {256, 768}), 256, Wf(p + ".ins_fc.b", {256}), ACT_RELU,
-                      f32a, 256, 1));
-  st.push_back([f32a, MQ, ln0w, ln0b, pe, L, Q0](cudaStream_t s) {
-    layernorm_rows(f32a, static_cast<int>(MQ), 256, ln0w, ln0b, 1e-5f, pe, L, Q0, s);
+  // query side (shared by both modalities; depends on BERT only -> stage stq)
+  stq.push_back([pe, L](cudaStream_t s) { sinusoid_table(pe, L, 256, s); return 1; });
+  add_gemm(stq, linear(bert, MQ, 768, 768, Wb(p + ".ins_fc.w", {256, 768}), 256, Wf(p + ".ins_fc.b", {256}), ACT_RELU,
+                       f32q, 256, 1));
+  stq.push_back([f32q, MQ, ln0w, ln0b, pe, L, Q0](cudaStream_t s) {
+    layernorm_rows(f32q, static_cast<int>(MQ), 256, ln0w, ln0b, 1e-5f, pe, L, Q0, s);
     return 1;
   });
-  add_gemm(st, linear(Q0, MQ, 256, 256, Wb(p + ".fc_q.w", {256, 256}), 256, Wf(p + ".fc_q.b", {256}), ACT_NONE, qq, 256, 0));
+  add_gemm(stq, linear(Q0, MQ, 256, 256, Wb(p + ".fc_q.w", {256, 256}), 256, Wf(p + ".fc_q.b", {256}), ACT_NONE, qq, 256, 0));
   // key/value side
   add_gemm(st, linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
                       f32a, 256, 1));
@@ -431,18 +432,18 @@ void Engine::plan_hi_tail(Stage& pre, Stage& st) {
     pre.push_back([this, er, B](cudaStream_t s) { fill_spatial_embedding(er, tokens_r_, B, 2112, 2048, cellmean_r_, 2112, s); return 1; });
     pre.push_back([this, ed, B](cudaStream_t s) { fill_spatial_embedding(ed, tokens_d_, B, 192, 128, nullptr, 0, s); return 1; });
     // rgb_kv / depth_kv: Conv1d(k=1) == per-cell linear (seq2seq_highlevel_cma.py:102-112,198-199)
-    add_gemm(st, linear(tokens_r_, static_cast<int64_t>(B) * 16, 2112, 2112, Wb("hi.rgb_kv.w", {256, 2112}), 256,
+    add_gemm(st_rgb_post_hi_, linear(tokens_r_, static_cast<int64_t>(B) * 16, 2112, 2112, Wb("hi.rgb_kv.w", {256, 2112}), 256,
                         Wf("hi.rgb_kv.b", {256}), ACT_NONE, kvin_, 256, 0));
-    add_gemm(st, linear(tokens_d_, static_cast<int64_t>(B) * 16, 192, 192, Wb("hi.depth_kv.w", {256, 192}), 256,
+    add_gemm(st_depth_post_hi_, linear(tokens_d_, static_cast<int64_t>(B) * 16, 192, 192, Wb("hi.depth_kv.w", {256, 192}), 256,
                         Wf("hi.depth_kv.b", {256}), ACT_NONE, kvin_ + static_cast<size_t>(B) * 16 * 256, 256, 0));
+    // rgb_linear (mean over cells -> Linear -> ReLU), depth_linear (Flatten -> Linear -> ReLU)
+    add_gemm(st_rgb_post_hi_, linear(cellmean_r_, B, 2112, 2112, Wb("hi.rgb_linear.w", {256, 2112}), 256,
+                                     Wf("hi.rgb_linear.b", {256}), ACT_RELU, concat_hi_, 896, 0));
+    add_gemm(st_depth_post_hi_, linear(tokens_d_, B, 3072, 3072, Wb("hi.depth_linear.w", {128, 3072}), 128,
+                                       Wf("hi.depth_linear.b", {128}), ACT_RELU, concat_hi_ + 256, 896, 0));
   }
-  plan_cross_modal(st, bert_out_, kvin_, concat_hi_ + 384, 896);
+  plan_cross_modal(st_bert_post_, st, bert_out_, kvin_, concat_hi_ + 384, 896);
   if (dry_) return;
-  // rgb_linear (mean over cells -> Linear -> ReLU), depth_linear (Flatten -> Linear -> ReLU)
-  add_gemm(st, linear(cellmean_r_, B, 2112, 2112, Wb("hi.rgb_linear.w", {256, 2112}), 256, Wf("hi.rgb_linear.b", {256}),
-                      ACT_RELU, concat_hi_, 896, 0));
-  add_gemm(st, linear(tokens_d_, B, 3072, 3072, Wb("hi.depth_linear.w", {128, 3072}), 128, Wf("hi.depth_linear.b", {128}),
-                      ACT_RELU, concat_hi_ + 256, 896, 0));
   add_gemm(st, linear(concat_hi_, B, 896, 896, Wb("hi.lstm.wih", {2048, 896}), 2048, Wf("hi.lstm.b", {2048}), ACT_NONE,
                       gx_hi_, 2048, 1));
   {
@@ -467,10 +468,10 @@ void Engine::plan_lo_tail(Stage& st) {
   stop_buf_ = reinterpret_cast<float*>(alloc(static_cast<size_t>(B) * 4));
   hc_lo_buf_ = reinterpret_cast<float*>(alloc(2ull * N * 512 * 4));
   if (dry_) return;
-  add_gemm(st, linear(tokens_d_, B, 3072, 3072, Wb("lo.depth_fc.w", {128, 3072}), 128, Wf("lo.depth_fc.b", {128}),
-                      ACT_RELU, lo_in_, 416, 0));
-  add_gemm(st, linear(gmean_r_, B, 2048, 2048, Wb("lo.rgb_fc.w", {256, 2048}), 256, Wf("lo.rgb_fc.b", {256}), ACT_RELU,
-                      lo_in_ + 128, 416, 0));
+  add_gemm(st_depth_post_lo_, linear(tokens_d_, B, 3072, 3072, Wb("lo.depth_fc.w", {128, 3072}), 128,
+                                     Wf("lo.depth_fc.b", {128}), ACT_RELU, lo_in_, 416, 0));
+  add_gemm(st_rgb_post_lo_, linear(gmean_r_, B, 2048, 2048, Wb("lo.rgb_fc.w", {256, 2048}), 256, Wf("lo.rgb_fc.b", {256}),
+                                   ACT_RELU, lo_in_ + 128, 416, 0));
   {
     const float* tbl = Wf("lo.sub_emb", {5, 32});
     st.push_back([this, tbl, B](cudaStream_t s) { sub_task_embed(args_.sub_goal, tbl, B, lo_in_ + 384, 416, s); return 1; });
@@ -509,7 +510,7 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
   arena_cap_ = bytes;
   gemms_.clear();
   for (Stage* s : {&st_rgb_, &st_depth_, &st_rgb_lo_, &st_depth_lo_, &st_bert_, &st_pre_, &st_hi_tail_, &st_lo_tail_,
-                   &st_cm_only_})
+                   &st_cm_only_, &st_rgb_post_hi_, &st_depth_post_hi_, &st_bert_post_, &st_rgb_post_lo_, &st_depth_post_lo_})
     s->clear();
   planned_ = false;
 
@@ -545,12 +546,14 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
     cm_bert_in_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(shp.instr_rows == 1 ? 1 : B) * shp.L * 768 * 2));
     cm_kv_in_ = reinterpret_cast<h16*>(alloc(2ull * B * 16 * 256 * 2));
     cm_out_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * 512 * 2));
-    plan_cross_modal(st_cm_only_, cm_bert_in_, cm_kv_in_, cm_out_, 512);
+    plan_cross_modal(st_cm_only_, st_cm_only_, cm_bert_in_, cm_kv_in_, cm_out_, 512);
   }
   if (have_lo_) plan_lo_tail(st_lo_tail_);
   label(st_rgb_, "rgb"); label(st_depth_, "depth"); label(st_rgb_lo_, "rgb_lo"); label(st_depth_lo_, "depth_lo");
   label(st_bert_, "bert"); label(st_pre_, "pre"); label(st_hi_tail_, "hi_tail"); label(st_lo_tail_, "lo_tail");
   label(st_cm_only_, "cross_modal");
+  label(st_rgb_post_hi_, "rgb_post"); label(st_depth_post_hi_, "depth_post"); label(st_bert_post_, "bert_post");
+  label(st_rgb_post_lo_, "rgb_post_lo"); label(st_depth_post_lo_, "depth_post_lo");
 
   const size_t need = arena_off_ + 1024;
   if (!dry_) {
@@ -576,15 +579,28 @@ int Engine::run(const Stage& st, cudaStream_t s) {
 }
 
 // trunks (RGB on the caller's stream, depth and BERT on side streams), joined before the tail
-void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s) {
+void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool posts_hi, bool posts_lo) {
   const bool multi = multi_stream_;
-  Stage& rgb = (lo_weights && !st_rgb_lo_.empty()) ? st_rgb_lo_ : st_rgb_;
-  Stage& dep = (lo_weights && !st_depth_lo_.empty()) ? st_depth_lo_ : st_depth_;
+  // per-stream op lists: the encoder followed by the tail ops that consume only that encoder
+  std::vector<const Op*> rgb, dep, bert;
+  auto append = [](std::vector<const Op*>& v, const Stage& st) { for (const Op& op : st) v.push_back(&op); };
+  append(rgb, (lo_weights && !st_rgb_lo_.empty()) ? st_rgb_lo_ : st_rgb_);
+  append(dep, (lo_weights && !st_depth_lo_.empty()) ? st_depth_lo_ : st_depth_);
+  if (with_bert) append(bert, st_bert_);
+  if (posts_hi) {
+    append(rgb, st_rgb_post_hi_);
+    append(dep, st_depth_post_hi_);
+    if (with_bert) append(bert, st_bert_post_);
+  }
+  if (posts_lo) {
+    append(rgb, st_rgb_post_lo_);
+    append(dep, st_depth_post_lo_);
+  }
   if (!multi) {
     if (before_rgb_) before_rgb_(s);
-    launches_ += run(rgb, s);
-    launches_ += run(dep, s);
-    if (with_bert) launches_ += run(st_bert_, s);
+    for (const Op* op : rgb) launches_ += (*op)(s);
+    for (const Op* op : dep) launches_ += (*op)(s);
+    for (const Op* op : bert) launches_ += (*op)(s);
     return;
   }
   // Fork: the three encoders are independent until the cross-modal block.  The host issues their
@@ -596,7 +612,7 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s) {
   if (with_bert) RVB_CUDA(cudaStreamWaitEvent(side_[1], events_[0], 0));
   if (before_rgb_) before_rgb_(s);   // host entry: the (large) RGB upload overlaps depth trunk + BERT
   size_t ir = 0, id = 0, ib = 0;
-  size_t nb = with_bert ? st_bert_.size() : 0;
+  size_t nb = bert.size();
   // timing experiments only (results are wrong): ROBOVLN_SKIP=rgb|depth|bert drops a stage
   static const char* skip = std::getenv("ROBOVLN_SKIP");
   if (skip != nullptr) {
@@ -605,9 +621,9 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s) {
     if (std::strstr(skip, "bert")) nb = 0;
   }
   while (ir < rgb.size() || id < dep.size() || ib < nb) {
-    if (ir < rgb.size()) launches_ += rgb[ir++](s);
-    if (ib < nb) launches_ += st_bert_[ib++](side_[1]);
-    for (int k = 0; k < 3 && id < dep.size(); ++k) launches_ += dep[id++](side_[0]);
+    if (ir < rgb.size()) launches_ += (*rgb[ir++])(s);
+    if (ib < nb) launches_ += (*bert[ib++])(side_[1]);
+    for (int k = 0; k < 3 && id < dep.size(); ++k) launches_ += (*dep[id++])(side_[0]);
   }
   RVB_CUDA(cudaEventRecord(events_[1], side_[0]));
   RVB_CUDA(cudaStreamWaitEvent(s, events_[1], 0));
@@ -623,7 +639,7 @@ void Engine::forward_hi(cudaStream_t s) {
                 args_.hc_hi_out && args_.logits, "forward_hi: null argument");
   launches_ = 0;
   launches_ += run(st_pre_, s);
-  run_encoders(true, false, s);
+  run_encoders(true, false, s, true, have_lo_ && lo_shares_trunks_);
   launches_ += run(st_hi_tail_, s);
   trunks_valid_ = true;
 }
@@ -637,7 +653,7 @@ void Engine::forward_lo(bool reuse_trunks, cudaStream_t s) {
     RVB_CHECK(trunks_valid_ && (lo_shares_trunks_ || !have_hi_), "forward_lo: no reusable trunk features");
   } else {
     RVB_CHECK(args_.rgb && args_.depth, "forward_lo: null observation");
-    run_encoders(false, true, s);
+    run_encoders(false, true, s, false, true);
     trunks_valid_ = !have_hi_ || lo_shares_trunks_;
   }
   launches_ += run(st_lo_tail_, s);
@@ -660,7 +676,8 @@ void Engine::forward_policy(cudaStream_t s) {
 std::vector<OpTiming> Engine::profile_policy(cudaStream_t s) {
   RVB_CHECK(planned_ && have_hi_ && have_lo_ && lo_shares_trunks_, "profile_policy needs a planned hi+lo engine");
   int64_t* sg = args_.sub_goal_out != nullptr ? args_.sub_goal_out : subgoal_buf_;
-  std::vector<const Stage*> order = {&st_pre_, &st_rgb_, &st_depth_, &st_bert_, &st_hi_tail_};
+  std::vector<const Stage*> order = {&st_pre_, &st_rgb_, &st_rgb_post_hi_, &st_rgb_post_lo_, &st_depth_, &st_depth_post_hi_,
+                                     &st_depth_post_lo_, &st_bert_, &st_bert_post_, &st_hi_tail_};
   std::vector<OpTiming> out;
   size_t nops = 2;
   for (auto* st : order) nops += st->size();

@@ -73,7 +73,10 @@ class Engine {
                            const float* hc_hi_in, const float* hc_lo_in, float* logits, float* actions, float* stop,
                            float* hc_hi_out, float* hc_lo_out, cudaStream_t s);
   void run_cross_modal(const void* bert, const void* rgb_sp, const void* depth_sp, void* pooled, cudaStream_t s);
-  void run_encoders(bool with_bert, bool lo_weights, cudaStream_t s);
+  // posts_hi / posts_lo: also run the tail ops that depend on ONE encoder only (rgb_kv, rgb_linear,
+  // depth_kv, depth_linear, the query side of the cross-modal block; lo's rgb_fc / depth_fc) on
+  // that encoder's stream, off the serial tail
+  void run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool posts_hi = false, bool posts_lo = false);
   // single-stream replay of forward_policy with a CUDA event between every op
   std::vector<OpTiming> profile_policy(cudaStream_t s);
   int run(const Stage& st, cudaStream_t s);
@@ -87,6 +90,8 @@ class Engine {
   bool have_hi_ = false, have_lo_ = false, lo_shares_trunks_ = false;
   hcm_shape shp_{};
   Stage st_rgb_, st_depth_, st_rgb_lo_, st_depth_lo_, st_bert_, st_pre_, st_hi_tail_, st_lo_tail_, st_cm_only_;
+  // single-encoder consumers, issued on the encoder's own stream before the join
+  Stage st_rgb_post_hi_, st_depth_post_hi_, st_bert_post_, st_rgb_post_lo_, st_depth_post_lo_;
 
  private:
   const WTensor& W(const std::string& name, int dtype, std::initializer_list<int64_t> shape) const;
@@ -102,7 +107,7 @@ class Engine {
   void plan_rgb_trunk(const std::string& ns, Stage& st);
   void plan_depth_trunk(const std::string& ns, Stage& st);
   void plan_bert(Stage& st);
-  void plan_cross_modal(Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch);
+  void plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch);
   void plan_hi_tail(Stage& pre, Stage& st);
   void plan_lo_tail(Stage& st);
 
