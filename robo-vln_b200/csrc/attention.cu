@@ -178,33 +178,46 @@ void launch_bert_attn(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStr
 // Visual_Ling_Attn cross attention: q [B*L,256] (shared by both modalities),
 // kv [n_mod*B*16, 512] (k | v), ctx [n_mod*B*L, 256].  4 heads x 64, 16 keys.
 // ---------------------------------------------------------------------------------------
-constexpr int VH = 4, VK = 16, VP = HD + 1;
+constexpr int VH = 4, VK = 16, VP = HD + 4;   // pitch 68 floats: 16-byte aligned rows, odd number of 16 B chunks
 __global__ void __launch_bounds__(256) vla_attn_kernel(const h16* __restrict__ q, const h16* __restrict__ kv,
                                                        h16* __restrict__ ctx, int B, int L, int q_shared) {
   RVB_PDL_PROLOGUE();
-  __shared__ float sK[VH * VK * VP];
-  __shared__ float sV[VH * VK * VP];
+  __shared__ __align__(16) float sK[VH * VK * VP];
+  __shared__ __align__(16) float sV[VH * VK * VP];
   const int b = blockIdx.x, mod = blockIdx.y;
   const h16* kvb = kv + (static_cast<long long>(mod) * B + b) * VK * 512;
-  for (int i = threadIdx.x; i < VK * 512; i += blockDim.x) {
-    const int j = i / 512, c = i % 512;
-    const float v = from_h16(kvb[i]);
+  for (int i = threadIdx.x; i < VK * 64; i += blockDim.x) {   // 16-byte loads: 8 channels each
+    const int j = i >> 6, c = (i & 63) * 8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(kvb + j * 512 + c));
     const int cc = c & 255, h = cc >> 6, d = cc & 63;
-    (c < 256 ? sK : sV)[(h * VK + j) * VP + d] = v;
+    float* dst = (c < 256 ? sK : sV) + (h * VK + j) * VP + d;
+    const float2 t0 = unpack_h2(u.x), t1 = unpack_h2(u.y), t2 = unpack_h2(u.z), t3 = unpack_h2(u.w);
+    *reinterpret_cast<float4*>(dst) = make_float4(t0.x, t0.y, t1.x, t1.y);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(t2.x, t2.y, t3.x, t3.y);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int h = lane >> 3, sub = lane & 7;
-  for (int l = warp; l < L; l += nwarps) {
-    const h16* qp = q + (static_cast<long long>(q_shared ? 0 : b) * L + l) * 256 + h * HD;
+  // lane (h, sub): scores of keys sub and sub + 8 of head h; output dims [4 sub, 4 sub + 4) and
+  // [32 + 4 sub, 32 + 4 sub + 4) -- every shared-memory access below is a conflict-free float4.
+  // Query rows are split over gridDim.z CTAs (each stages the 16 KB of K/V again: cheaper than
+  // leaving most SMs idle on this latency-bound step of the serial tail).
+  const float4* k0 = reinterpret_cast<const float4*>(sK + (h * VK + sub) * VP);
+  const float4* k1 = reinterpret_cast<const float4*>(sK + (h * VK + sub + 8) * VP);
+  for (int l = blockIdx.z * nwarps + warp; l < L; l += nwarps * gridDim.z) {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + (static_cast<long long>(q_shared ? 0 : b) * L + l) * 256 + h * HD);
+    uint4 qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = __ldg(qp + i);
     float s0 = 0.0f, s1 = 0.0f;
-    const float* k0 = sK + (h * VK + 2 * sub) * VP;
-    const float* k1 = k0 + VP;
-#pragma unroll 8
-    for (int d = 0; d < HD; d += 2) {
-      const float2 qq = unpack_h2(*reinterpret_cast<const uint32_t*>(qp + d));
-      s0 = fmaf(qq.x, k0[d], s0); s0 = fmaf(qq.y, k0[d + 1], s0);
-      s1 = fmaf(qq.x, k1[d], s1); s1 = fmaf(qq.y, k1[d + 1], s1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 q0 = unpack_h2(qv[i].x), q1 = unpack_h2(qv[i].y), q2 = unpack_h2(qv[i].z), q3 = unpack_h2(qv[i].w);
+      const float4 a0 = k0[2 * i], a1 = k0[2 * i + 1], b0 = k1[2 * i], b1 = k1[2 * i + 1];
+      s0 = fmaf(q0.x, a0.x, s0); s0 = fmaf(q0.y, a0.y, s0); s0 = fmaf(q1.x, a0.z, s0); s0 = fmaf(q1.y, a0.w, s0);
+      s0 = fmaf(q2.x, a1.x, s0); s0 = fmaf(q2.y, a1.y, s0); s0 = fmaf(q3.x, a1.z, s0); s0 = fmaf(q3.y, a1.w, s0);
+      s1 = fmaf(q0.x, b0.x, s1); s1 = fmaf(q0.y, b0.y, s1); s1 = fmaf(q1.x, b0.z, s1); s1 = fmaf(q1.y, b0.w, s1);
+      s1 = fmaf(q2.x, b1.x, s1); s1 = fmaf(q2.y, b1.y, s1); s1 = fmaf(q3.x, b1.z, s1); s1 = fmaf(q3.y, b1.w, s1);
     }
     s0 *= 0.125f; s1 *= 0.125f;
     float mx = fmaxf(s0, s1);
@@ -223,15 +236,15 @@ __global__ void __launch_bounds__(256) vla_attn_kernel(const h16* __restrict__ q
     for (int dd = 0; dd < 8; ++dd) o[dd] = 0.0f;
 #pragma unroll
     for (int j = 0; j < VK; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, (j & 1) ? p1 : p0, (h << 3) + (j >> 1));
-      const float* vr = sV + (h * VK + j) * VP + sub * 8;
-#pragma unroll
-      for (int dd = 0; dd < 8; ++dd) o[dd] = fmaf(pj, vr[dd], o[dd]);
+      const float pj = __shfl_sync(0xffffffffu, (j >> 3) ? p1 : p0, (h << 3) + (j & 7));
+      const float4* vr = reinterpret_cast<const float4*>(sV + (h * VK + j) * VP);
+      const float4 va = vr[sub], vb = vr[8 + sub];
+      o[0] = fmaf(pj, va.x, o[0]); o[1] = fmaf(pj, va.y, o[1]); o[2] = fmaf(pj, va.z, o[2]); o[3] = fmaf(pj, va.w, o[3]);
+      o[4] = fmaf(pj, vb.x, o[4]); o[5] = fmaf(pj, vb.y, o[5]); o[6] = fmaf(pj, vb.z, o[6]); o[7] = fmaf(pj, vb.w, o[7]);
     }
-    uint4 u;
-    u.x = pack_h2(o[0], o[1]); u.y = pack_h2(o[2], o[3]);
-    u.z = pack_h2(o[4], o[5]); u.w = pack_h2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(ctx + ((static_cast<long long>(mod) * B + b) * L + l) * 256 + h * HD + sub * 8) = u;
+    h16* op = ctx + ((static_cast<long long>(mod) * B + b) * L + l) * 256 + h * HD;
+    *reinterpret_cast<uint2*>(op + sub * 4) = make_uint2(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]));
+    *reinterpret_cast<uint2*>(op + 32 + sub * 4) = make_uint2(pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
   }
 }
 
@@ -249,7 +262,8 @@ void bert_self_attention(const h16* qkv, h16* ctx, int R, int L, int heads, cuda
 
 void vla_cross_attention(const h16* q, const h16* kv, h16* ctx, int B, int L, int n_mod, int q_shared,
                          cudaStream_t s) {
-  dim3 grid(B, n_mod);
+  const int zsplit = (B * n_mod >= 592) ? 1 : ((L + 31) / 32 > 4 ? 4 : (L + 31) / 32);
+  dim3 grid(B, n_mod, zsplit);
   launch_k(vla_attn_kernel, dim3(grid), dim3(256), 0, s, q, kv, ctx, B, L, q_shared);
   RVB_CUDA(cudaGetLastError());
 }

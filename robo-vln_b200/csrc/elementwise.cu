@@ -576,17 +576,34 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 
 // mean over the L tokens of each (modality, batch row) group: x [n_mod*B*L, D] ->
 // out[b*out_pitch + mod*mod_stride + d]   (cross_pooler, seq2seq_highlevel_cma.py:114-115,209-210)
-__global__ void token_mean_kernel(const h16* __restrict__ x, int B, int L, int D, h16* __restrict__ out,
-                                  long long out_pitch, long long mod_stride) {
+__global__ void __launch_bounds__(256) token_mean_kernel(const h16* __restrict__ x, int B, int L, int D,
+                                                         h16* __restrict__ out, long long out_pitch,
+                                                         long long mod_stride) {
   RVB_PDL_PROLOGUE();
+  // one CTA per (modality, batch row); D == 256: lane v owns channels [8v, 8v+8), warp w sums
+  // rows w, w+8, ...; partials are folded in warp order (deterministic)
+  __shared__ float part[8][256];
   const int g = blockIdx.x;
   const int mod = g / B, b = g % B;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float acc = 0.0f;
-    const h16* p = x + static_cast<long long>(g) * L * D + d;
-    for (int l = 0; l < L; ++l) acc += from_h16(p[static_cast<long long>(l) * D]);
-    out[b * out_pitch + mod * mod_stride + d] = to_h16(acc / static_cast<float>(L));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+  const h16* p = x + static_cast<long long>(g) * L * D + lane * 8;
+  for (int l = warp; l < L; l += 8) {
+    float f[8];
+    load8(p + static_cast<long long>(l) * D, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[warp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int d = threadIdx.x;
+  float s = 0.0f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += part[w][d];
+  out[b * out_pitch + mod * mod_stride + d] = to_h16(s / static_cast<float>(L));
 }
 
 __global__ void sub_task_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ table, int B,
@@ -612,6 +629,63 @@ __global__ void heads_linear_kernel(const float* __restrict__ y, int M, int K, c
   for (int k = lane; k < K; k += 32) acc = fmaf(y[static_cast<long long>(m) * K + k], w[static_cast<long long>(o) * K + k], acc);
   acc = warp_sum(acc);
   if (lane == 0) out[static_cast<long long>(m) * n_out + o] = acc + b[o];
+}
+
+// Policy heads, one warp per row m (K == 512):
+//   outA[m][0..nA) = y[m] . wA^T + bA          (hi: sub-goal logits; lo: linear/angular velocity)
+//   outB[m][0..nB) = y[m] . wB^T + bB          (lo: stop logit; optional)
+//   amax[m]        = argmax over group A        (hi -> lo hand-off, hierarchical_trainer.py:1098; optional)
+//   emb_out[m][0..32) = emb[amax[m]]            (lo's sub_task_embedding of that sub-goal; optional)
+constexpr int HEADS_MAX = 5;
+__global__ void __launch_bounds__(256) heads_fused_kernel(const float* __restrict__ y, int M, int K,
+                                                          const float* __restrict__ wA, const float* __restrict__ bA, int nA,
+                                                          float* __restrict__ outA, const float* __restrict__ wB,
+                                                          const float* __restrict__ bB, int nB, float* __restrict__ outB,
+                                                          long long* __restrict__ amax, const float* __restrict__ emb,
+                                                          h16* __restrict__ emb_out, long long emb_pitch) {
+  RVB_PDL_PROLOGUE();
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  // K == 512: lane owns k = 4 lane + 128 i.  All loads of the row and of every weight row are
+  // issued before the first reduction (one memory round trip instead of one per output).
+  const float4* yr = reinterpret_cast<const float4*>(y + static_cast<long long>(m) * K) + lane;
+  float4 yv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) yv[i] = yr[32 * i];
+  const int n_tot = nA + nB;
+  float acc[HEADS_MAX];
+#pragma unroll
+  for (int o = 0; o < HEADS_MAX; ++o) {
+    acc[o] = 0.0f;
+    if (o < n_tot) {
+      const float4* w = reinterpret_cast<const float4*>(o < nA ? wA + static_cast<long long>(o) * K
+                                                               : wB + static_cast<long long>(o - nA) * K) + lane;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 wv = __ldg(w + 32 * i);
+        acc[o] = fmaf(yv[i].x, wv.x, acc[o]); acc[o] = fmaf(yv[i].y, wv.y, acc[o]);
+        acc[o] = fmaf(yv[i].z, wv.z, acc[o]); acc[o] = fmaf(yv[i].w, wv.w, acc[o]);
+      }
+    }
+  }
+  int best = 0;
+  float bv = 0.0f;
+#pragma unroll
+  for (int o = 0; o < HEADS_MAX; ++o) {
+    if (o < n_tot) {
+      const bool a = o < nA;
+      const float v = warp_sum(acc[o]) + (a ? bA[o] : bB[o - nA]);
+      if (a) {
+        if (lane == 0) outA[static_cast<long long>(m) * nA + o] = v;
+        if (o == 0 || v > bv) { bv = v; best = o; }
+      } else if (lane == 0) {
+        outB[static_cast<long long>(m) * nB + (o - nA)] = v;
+      }
+    }
+  }
+  if (amax != nullptr && lane == 0) amax[m] = best;
+  if (emb != nullptr) emb_out[m * emb_pitch + lane] = to_h16(emb[best * 32 + lane]);
 }
 
 __global__ void argmax_rows_kernel(const float* __restrict__ x, int M, int n, long long* __restrict__ out) {
@@ -753,6 +827,7 @@ void layernorm_rows(const float* x, int M, int D, const float* g, const float* b
 
 void token_mean(const h16* x, int n_mod, int B, int L, int D, h16* out, int64_t out_pitch, int64_t mod_stride,
                 cudaStream_t s) {
+  RVB_CHECK(D == 256, "token_mean: D must be 256");
   launch_k(token_mean_kernel, dim3(n_mod * B), dim3(256), 0, s, x, B, L, D, out, out_pitch, mod_stride);
   RVB_CUDA(cudaGetLastError());
 }
@@ -767,6 +842,17 @@ void heads_linear(const float* y, int M, int K, const float* w, const float* b, 
                   cudaStream_t s) {
   const long long warps = static_cast<long long>(M) * n_out;
   launch_k(heads_linear_kernel, dim3(static_cast<int>((warps * 32 + 255) / 256)), dim3(256), 0, s, y, M, K, w, b, n_out, out);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void heads_fused(const float* y, int M, int K, const float* wA, const float* bA, int nA, float* outA, const float* wB,
+                 const float* bB, int nB, float* outB, int64_t* amax, const float* emb, h16* emb_out, int64_t emb_pitch,
+                 cudaStream_t s) {
+  RVB_CHECK(nA >= 1 && nB >= 0 && nA + nB <= HEADS_MAX && K == 512 && (nB == 0 || (wB != nullptr && outB != nullptr)),
+            "heads_fused: bad groups");
+  RVB_CHECK(emb == nullptr || (nA <= 5 && emb_out != nullptr), "heads_fused: embedding table has 5 rows");
+  launch_k(heads_fused_kernel, dim3((M * 32 + 255) / 256), dim3(256), 0, s, y, M, K, wA, bA, nA, outA, wB, bB, nB, outB,
+           reinterpret_cast<long long*>(amax), emb, emb_out, static_cast<long long>(emb_pitch));
   RVB_CUDA(cudaGetLastError());
 }
 

@@ -454,7 +454,13 @@ void Engine::plan_hi_tail(Stage& pre, Stage& st) {
     });
     const float* lw = Wf("hi.linear.w", {4, 512});
     const float* lb = Wf("hi.linear.b", {4});
-    st.push_back([this, lw, lb, B](cudaStream_t s) { heads_linear(y_hi_, B, 512, lw, lb, 4, args_.logits, s); return 1; });
+    st.push_back([this, lw, lb, B](cudaStream_t s) {
+      // policy step: logits + argmax + lo's sub-task embedding of the chosen sub-goal in one launch
+      const bool pol = policy_sg_ != nullptr;
+      heads_fused(y_hi_, B, 512, lw, lb, 4, args_.logits, nullptr, nullptr, 0, nullptr, policy_sg_,
+                  pol ? Wf("lo.sub_emb", {5, 32}) : nullptr, pol ? lo_in_ + 384 : nullptr, 416, s);
+      return 1;
+    });
   }
 }
 
@@ -474,7 +480,11 @@ void Engine::plan_lo_tail(Stage& st) {
                                    ACT_RELU, lo_in_ + 128, 416, 0));
   {
     const float* tbl = Wf("lo.sub_emb", {5, 32});
-    st.push_back([this, tbl, B](cudaStream_t s) { sub_task_embed(args_.sub_goal, tbl, B, lo_in_ + 384, 416, s); return 1; });
+    st.push_back([this, tbl, B](cudaStream_t s) {
+      if (policy_sg_ != nullptr) return 0;   // already written by the hi head (forward_policy)
+      sub_task_embed(args_.sub_goal, tbl, B, lo_in_ + 384, 416, s);
+      return 1;
+    });
   }
   add_gemm(st, linear(lo_in_, B, 416, 416, Wb("lo.lstm.wih", {2048, 416}), 2048, Wf("lo.lstm.b", {2048}), ACT_NONE, gx_lo_,
                       2048, 1));
@@ -487,8 +497,10 @@ void Engine::plan_lo_tail(Stage& st) {
   const float* lb = Wf("lo.linear.b", {2});
   const float* sw = Wf("lo.stop.w", {1, 512});
   const float* sb = Wf("lo.stop.b", {1});
-  st.push_back([this, lw, lb, B](cudaStream_t s) { heads_linear(y_lo_, B, 512, lw, lb, 2, args_.actions, s); return 1; });
-  st.push_back([this, sw, sb, B](cudaStream_t s) { heads_linear(y_lo_, B, 512, sw, sb, 1, args_.stop, s); return 1; });
+  st.push_back([this, lw, lb, sw, sb, B](cudaStream_t s) {
+    heads_fused(y_lo_, B, 512, lw, lb, 2, args_.actions, sw, sb, 1, args_.stop, nullptr, nullptr, nullptr, 0, s);
+    return 1;
+  });
 }
 
 // ---------------------------------------------------------------------------------------
@@ -663,14 +675,18 @@ void Engine::forward_policy(cudaStream_t s) {
   RVB_CHECK(planned_ && have_hi_ && have_lo_, "forward_policy needs both models");
   RVB_CHECK(lo_shares_trunks_, "forward_policy requires lo to share hi's frozen trunks");
   int64_t* sg = args_.sub_goal_out != nullptr ? args_.sub_goal_out : subgoal_buf_;
-  forward_hi(s);
-  const int n_hi = launches_;
-  const int B = shp_.B;
-  const float* logits = args_.logits;
-  argmax_rows(logits, B, 4, sg, s);
-  args_.sub_goal = sg;
-  forward_lo(true, s);
-  launches_ += n_hi + 1;
+  policy_sg_ = sg;
+  try {
+    forward_hi(s);
+    const int n_hi = launches_;
+    args_.sub_goal = sg;
+    forward_lo(true, s);
+    launches_ += n_hi;
+  } catch (...) {
+    policy_sg_ = nullptr;
+    throw;
+  }
+  policy_sg_ = nullptr;
 }
 
 std::vector<OpTiming> Engine::profile_policy(cudaStream_t s) {
@@ -696,12 +712,11 @@ std::vector<OpTiming> Engine::profile_policy(cudaStream_t s) {
       out.push_back({op.name, 0.0, op.flops});
     }
   };
+  policy_sg_ = sg;
   for (auto* st : order) run_timed(*st);
-  argmax_rows(args_.logits, shp_.B, 4, sg, s);
-  RVB_CUDA(cudaEventRecord(prof_events_[ei++], s));
-  out.push_back({"argmax", 0.0, 0.0});
   args_.sub_goal = sg;
   run_timed(st_lo_tail_);
+  policy_sg_ = nullptr;
   RVB_CUDA(cudaStreamSynchronize(s));
   for (size_t i = 0; i < out.size(); ++i) {
     float ms = 0.f;

@@ -83,6 +83,8 @@ class Engine {
   bool get_buffer(const std::string& name, void** ptr, int* dtype, std::vector<int64_t>* shape) const;
 
   RunArgs args_;
+  // forward_policy only: the hi head also writes argmax -> sub-goal ids and lo's sub-task embedding
+  int64_t* policy_sg_ = nullptr;
   int64_t launches_ = 0;
   bool multi_stream_ = false;
   std::function<void(cudaStream_t)> before_rgb_;   // enqueued right before the RGB trunk (host-entry upload)

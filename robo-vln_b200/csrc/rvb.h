@@ -165,6 +165,9 @@ void token_mean(const h16* x, int n_mod, int B, int L, int D, h16* out, int64_t 
                 cudaStream_t s);
 void sub_task_embed(const int64_t* ids, const float* table, int B, h16* out, int64_t out_pitch, cudaStream_t s);
 void heads_linear(const float* y, int M, int K, const float* w, const float* b, int n_out, float* out, cudaStream_t s);
+void heads_fused(const float* y, int M, int K, const float* wA, const float* bA, int nA, float* outA, const float* wB,
+                 const float* bB, int nB, float* outB, int64_t* amax, const float* emb, h16* emb_out, int64_t emb_pitch,
+                 cudaStream_t s);
 void argmax_rows(const float* x, int M, int n, int64_t* out, cudaStream_t s);
 void sinusoid_table(float* pe, int L, int D, cudaStream_t s);
 
