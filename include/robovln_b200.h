@@ -152,6 +152,10 @@ int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in
  * written by rvb_rgb_pad_convert, W is the OUTPUT width, KW must be 1 and Cin 64 (8 px x 8 ch per
  * filter row), weights [Cout, KH*64]. */
 int rvb_rgb_pad_convert(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream);
+/* Packed stem (window == 2, what the engine runs): zero-padded ROW-PAIR-INTERLEAVED image [NB, (H+6)/2, Wp, 2, 4]
+ * (H even); the conv takes H = (H+6)/2 row pairs, W = OUTPUT width, in_pitch 8, KH = 4 (row pairs), KW 1, stride 2,
+ * Cin 64, win_row_pitch = Wp*8, weights [Cout, 4*64] with k = (r/2)*64 + s*8 + (r%2)*4 + c. */
+int rvb_rgb_pad_convert4(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream);
 int rvb_groupnorm(const void* x_bf16, float* stats /* [NB,G,2] zeroed by the call */, const float* gamma,
                   const float* beta, int NB, int HW, int C, int G, int relu, const void* res_bf16,
                   void* out_bf16, int64_t out_pitch, void* stream);

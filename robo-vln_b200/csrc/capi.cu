@@ -296,6 +296,10 @@ int rvb_rgb_pad_convert(const float* rgb, void* out_h16, int NB, int H, int W, i
   return guarded([&] { rgb_pad_convert(rgb, B16(out_h16), NB, H, W, Wp, S(stream)); });
 }
 
+int rvb_rgb_pad_convert4(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream) {
+  return guarded([&] { rgb_pad_convert4(rgb, B16(out_h16), NB, H, W, Wp, S(stream)); });
+}
+
 int rvb_depth_stem(const float* depth, const float* w, void* out_bf16, int NB, int H, int W, void* stream) {
   return guarded([&] { depth_stem_conv(depth, w, B16(out_bf16), NB, H, W, S(stream)); });
 }

@@ -96,6 +96,33 @@ __global__ void __launch_bounds__(256) rgb_pad_convert_kernel(const float* __res
   }
 }
 
+// Packed variant for the two-filter-rows-per-K-block stem: row-pair interleaved [NB, (H+6)/2, Wp, 2, 4]
+// (for every pixel column: row 2t then row 2t+1, 4 channels each with channel 3 zero).  One thread per
+// (row pair, pixel): 24 B read, 16 B written.
+__global__ void __launch_bounds__(256) rgb_pad_convert4_kernel(const float* __restrict__ rgb, h16* __restrict__ out,
+                                                               int NB, int H, int W, int Hh, int Wp) {
+  RVB_PDL_PROLOGUE();
+  const long long total = static_cast<long long>(NB) * Hh * Wp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xp = static_cast<int>(i % Wp);
+    const int tp = static_cast<int>((i / Wp) % Hh);
+    const int img = static_cast<int>(i / (static_cast<long long>(Wp) * Hh));
+    const int x = xp - 3;
+    uint32_t q[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      const int y = tp * 2 + r2 - 3;
+      if (x >= 0 && x < W && y >= 0 && y < H) {
+        const float* src = rgb + ((static_cast<long long>(img) * H + y) * W + x) * 3;
+        q[2 * r2] = pack_h2(__ldg(src) / 255.0f, __ldg(src + 1) / 255.0f);   // true division, as the reference
+        q[2 * r2 + 1] = pack_h2(__ldg(src + 2) / 255.0f, 0.0f);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(q[0], q[1], q[2], q[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 max pooling, NHWC h16
 // ---------------------------------------------------------------------------------------
@@ -736,6 +763,13 @@ void rgb_pad_convert(const float* rgb, h16* out, int NB, int H, int W, int Wp, c
   RVB_CHECK(Wp >= W + 6, "rgb_pad_convert: padded width too small");
   const long long total = static_cast<long long>(NB) * (H + 6) * Wp;
   launch_k(rgb_pad_convert_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, rgb, out, NB, H, W, H + 6, Wp);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void rgb_pad_convert4(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s) {
+  RVB_CHECK(Wp >= W + 6 && H % 2 == 0, "rgb_pad_convert4: padded width too small / odd height");
+  const long long total = static_cast<long long>(NB) * ((H + 6) / 2) * Wp;
+  launch_k(rgb_pad_convert4_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, rgb, out, NB, H, W, (H + 6) / 2, Wp);
   RVB_CUDA(cudaGetLastError());
 }
 

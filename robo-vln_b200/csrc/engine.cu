@@ -114,18 +114,18 @@ void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
   const int B = shp_.B, H = shp_.rgb_h, W = shp_.rgb_w;
   const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;   // conv1 7x7 s2 p3
   const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1; // maxpool 3x3 s2 p1
-  // stem: zero-padded NHW8 image -> 7x7 s2 conv on the tensor cores in window mode (7 K blocks,
-  // one per filter row) -> maxpool
+  // stem: zero-padded row-pair-interleaved image -> 7x7 s2 conv on the tensor cores in packed window
+  // mode (4 K blocks, two filter rows each) -> maxpool
   const int Hp = H + 6, Wp = W + 6;
-  h16* padded = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * Hp * Wp * 8 * 2));
+  h16* padded = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * Hp * Wp * 4 * 2));
   h16* stem = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 64 * 2));
   h16* x = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 64 * 2));
   if (!dry_) {
-    st.push_back([this, padded, B, H, W, Wp](cudaStream_t s) { rgb_pad_convert(args_.rgb, padded, B, H, W, Wp, s); return 1; });
+    st.push_back([this, padded, B, H, W, Wp](cudaStream_t s) { rgb_pad_convert4(args_.rgb, padded, B, H, W, Wp, s); return 1; });
     ConvGemm g;
-    g.in = padded; g.NB = B; g.H = Hp; g.W = W1; g.Cin = 64; g.in_pitch = 8;
-    g.window = 1; g.win_row_pitch = static_cast<int64_t>(Wp) * 8;
-    g.w = Wb(ns + ".rgb.stem.w", {64, 7 * 64}); g.Cout = 64; g.KH = 7; g.KW = 1; g.stride = 2; g.pad = 0;
+    g.in = padded; g.NB = B; g.H = Hp / 2; g.W = W1; g.Cin = 64; g.in_pitch = 8;
+    g.window = 2; g.win_row_pitch = static_cast<int64_t>(Wp) * 8;
+    g.w = Wb(ns + ".rgb.stem.w", {64, 4 * 64}); g.Cout = 64; g.KH = 4; g.KW = 1; g.stride = 2; g.pad = 0;
     g.bias = Wf(ns + ".rgb.stem.b", {64}); g.act = ACT_RELU; g.out = stem; g.ldc = 64;
     add_gemm(st, g);
     st.push_back([stem, x, B, H1, W1](cudaStream_t s) { maxpool3x3s2(stem, x, B, H1, W1, 64, s); return 1; });

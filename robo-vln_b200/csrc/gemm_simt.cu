@@ -27,7 +27,14 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   const int img = static_cast<int>(m / (static_cast<long long>(p.Wo) * p.Ho));
   const long long Ktot = static_cast<long long>(p.KH) * p.KW * p.Cin;
   float acc = 0.0f;
-  if (p.window) {
+  if (p.window == 2) {   // packed stem: K block kb = row pair ho + kb, 64 contiguous elements (8 px x 2 rows x 4 ch)
+    for (int kb = 0; kb < p.KH; ++kb) {
+      const h16* a = p.in + (static_cast<long long>(img) * p.H + ho + kb) * p.win_row_pitch +
+                     static_cast<long long>(wo) * p.stride * 8;
+      const h16* b = p.w + n * Ktot + static_cast<long long>(kb) * p.Cin;
+      for (int c = 0; c < p.Cin; ++c) acc = fmaf(from_h16(a[c]), from_h16(b[c]), acc);
+    }
+  } else if (p.window) {
     for (int r = 0; r < p.KH; ++r) {
       const h16* a = p.in + (static_cast<long long>(img) * p.H + ho * p.stride + r) * p.win_row_pitch +
                      static_cast<long long>(wo) * p.stride * 8;

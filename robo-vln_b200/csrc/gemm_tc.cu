@@ -206,6 +206,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + C::B_STAGE_BYTES);
           if (p.plain) {
             tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, mt * BLOCK_M, 0, 0);
+          } else if (p.window2) {
+            tma_load_4d(sa, &tmA, &full_bar[stage], 0, 0, h0 + tap, img);   // row pair h0 + tap = filter rows 2 tap, 2 tap + 1
           } else {
             const int r = tap / p.KW;
             const int s = tap - r * p.KW;
@@ -363,7 +365,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int half = 0; half < 2; ++half) {
               uint32_t v[32];
               __syncwarp();
-              tmem_ld_32x32(taddr + c0 + half * 32, v);
+              if (!(p.dbg & 4)) tmem_ld_32x32(taddr + c0 + half * 32, v);
+              else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+              }
               uint4 rv[4];
               if (p.res_tma) {
 #pragma unroll
@@ -392,7 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   t = unpack_h2(rv[j].w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
                 }
               }
-              epilogue_math(f, p, n + half * 32, p.res_tma ? nullptr : res_row);
+              if (!(p.dbg & 2)) epilogue_math(f, p, n + half * 32, p.res_tma ? nullptr : res_row);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 q;
@@ -409,7 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // plain GEMM: the output box is 32 rows, so every warp stores its own quarter of the
             // tile as soon as it is staged -- no cross-warp barrier, the eight warps run decoupled
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.dbg & 1)) {
               tma_store_4d(&tmC, stage_buf + quad * 4096, n, mt * BLOCK_M + quad * 32, 0, 0);
               tma_store_commit();
             }
@@ -631,7 +637,7 @@ bool use_simt_gemm() {
 
 void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   RVB_CHECK(g.in != nullptr && g.w != nullptr && g.out != nullptr, "gemm: null operand");
-  RVB_CHECK(g.Cin % 8 == 0 && g.in_pitch % 8 == 0, "gemm: Cin / pitch must be multiples of 8");
+  RVB_CHECK(g.Cin % 8 == 0 && (g.window == 2 || g.in_pitch % 8 == 0), "gemm: Cin / pitch must be multiples of 8");
   RVB_CHECK(g.window || g.in_pitch >= g.Cin, "gemm: pixel pitch smaller than Cin");
   RVB_CHECK((reinterpret_cast<uintptr_t>(g.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
             "gemm: operands must be 16-byte aligned");
@@ -666,6 +672,14 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   p.ldc = g.ldc;
   p.out_f32 = g.out_f32;
   p.tma_store = use_direct_epilogue() ? 0 : 1;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = std::getenv("ROBOVLN_EPI_DEBUG");
+      dbg = e ? std::atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
 
   const uint32_t ones[4] = {1, 1, 1, 1};
   const uint64_t pitchB = static_cast<uint64_t>(g.in_pitch) * 2;
@@ -699,7 +713,18 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
       p.tile_rows = p.nb * P;
       p.m_tiles = (g.NB + p.nb - 1) / p.nb;
     }
-    if (g.window) {
+    if (g.window == 2) {
+      // packed stem: element (k, wo, t, n) lives at n*H*rowpair + t*rowpair + wo*(stride px * 8) + k, k < 64
+      RVB_CHECK(g.KH == 4 && g.KW == 1 && g.pad == 0 && g.Cin == BLOCK_K && g.win_row_pitch % 8 == 0,
+                "packed window conv: bad geometry");
+      RVB_CHECK(static_cast<int64_t>(Wo - 1) * g.stride * 8 + BLOCK_K <= g.win_row_pitch, "packed window conv: row too short");
+      const uint64_t rowB = static_cast<uint64_t>(g.win_row_pitch) * 2;
+      const uint64_t dims[4] = {BLOCK_K, static_cast<uint64_t>(Wo), static_cast<uint64_t>(g.H), static_cast<uint64_t>(g.NB)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(g.stride) * 8 * 2, rowB, rowB * g.H};
+      const uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(Wo), static_cast<uint32_t>(p.th), static_cast<uint32_t>(p.nb)};
+      encode_map(&plan->tmA, kH16Type, g.in, 4, dims, strides, box, ones);
+      p.window2 = 1;
+    } else if (g.window) {
       // overlapping-window view of a zero-padded NHW8 image: element (k, wo, h, n) lives at
       // n*H*row + h*row + wo*(stride*8) + k; each K block is one filter ROW (KW folded into k).
       RVB_CHECK(g.KW == 1 && g.pad == 0 && g.Cin == BLOCK_K && g.win_row_pitch % 8 == 0, "window conv: bad geometry");

@@ -79,10 +79,14 @@ struct ConvGemm {
   int out_f32 = 0;
   // "window" mode (RGB stem): `in` is a zero-padded [NB, H, win_row_pitch/8, 8] image, KW is folded
   // into the K dimension (Cin = 64 = 8 pixels x 8 channels per filter row), W is the OUTPUT width.
+  // window == 2 (packed stem): `in` is a zero-padded, ROW-PAIR-INTERLEAVED image [NB, H, win_row_pitch/8, 2, 4]
+  // (H = padded rows / 2; per pixel column: row 2t then row 2t+1, 4 channels each), so one 64-element window
+  // = 8 pixels x 2 rows x 4 channels holds TWO filter rows: KH = 4 row pairs for the 7 filter rows (the 8th
+  // has zero weights), k = s*8 + (r%2)*4 + c.  The window steps `stride` (2) pixels in W and ONE row pair in H.
   int window = 0;
   int64_t win_row_pitch = 0;     // elements per padded input row
   // derived
-  int Ho() const { return (H + 2 * pad - KH) / stride + 1; }
+  int Ho() const { return window == 2 ? H - 3 : (H + 2 * pad - KH) / stride + 1; }
   int Wo() const { return window ? W : (W + 2 * pad - KW) / stride + 1; }
   int64_t M() const { return static_cast<int64_t>(NB) * Ho() * Wo(); }
   bool plain() const { return !window && KH == 1 && KW == 1 && stride == 1 && pad == 0; }
@@ -112,7 +116,9 @@ struct GemmTcParams {
   int out_f32;
   int tma_store;     // 1: smem-staged TMA store epilogue, 0: direct global stores (validation)
   int res_tma;       // 1: residual chunks prefetched by TMA into per-warp smem slices
+  int window2;       // 1: packed stem (rows advance by one row PAIR per output row: A row coord h0 + tap)
   int nstages;       // pipeline stages in use (fewer when the residual slices take their place)
+  int dbg;           // timing experiments only (ROBOVLN_EPI_DEBUG bit mask; results are wrong when set)
 };
 
 struct GemmTcPlan {
@@ -140,6 +146,7 @@ bool use_simt_gemm();
 // elementwise.cu
 void rgb_stem_im2col(const float* rgb, h16* out, int NB, int H, int W, int Kpitch, cudaStream_t s);
 void rgb_pad_convert(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s);
+void rgb_pad_convert4(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s);   // row-pair interleaved (packed stem)
 void maxpool3x3s2(const h16* in, h16* out, int NB, int H, int W, int C, cudaStream_t s);
 void depth_stem_conv(const float* depth, const float* w, h16* out, int NB, int H, int W, cudaStream_t s);
 void gn_stats(const h16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s);

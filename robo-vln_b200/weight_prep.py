@@ -7,7 +7,7 @@ features where the reference flattens NCHW "channel-major" ones
 (seq2seq_highlevel_cma.py:92-100 depth_linear; resnet_encoders.py:58-62 visual_fc).
 
 Engine tensor names (``ns`` is "hi" or "lo"):
-  {ns}.rgb.stem.{w,b}                     h16 [64,448] (7 filter rows x 64-wide window block), f32 [64]
+  {ns}.rgb.stem.{w,b}                     h16 [64,256] (4 K blocks x two 32-wide filter rows), f32 [64]
   {ns}.rgb.l{1-4}.{blk}.{c1,c2,c3,ds}.{w,b}
   {ns}.depth.stem.w f32 [32,49]; {ns}.depth.stem.gn.{w,b}
   {ns}.depth.l{1-4}.{blk}.{c1,c2,c3,ds}.w ; .gn{1,2,3}.{w,b} ; .dsgn.{w,b}
@@ -60,6 +60,18 @@ def fold_bn(conv_w: torch.Tensor, g, b, mean, var, eps: float = 1e-5):
     return conv_w.float() * scale.view(-1, 1, 1, 1), b.float() - mean.float() * scale
 
 
+def stem_packed_weights(w: torch.Tensor) -> torch.Tensor:
+    """[64,3,7,7] (O,C,R,S) -> [64, 4*64]: K block kb holds filter rows 2kb and 2kb+1 as the packed window-mode
+    A operand reads the padded row-pair-interleaved image: k = kb*64 + s*8 + (r%2)*4 + c for r < 7, s < 7,
+    c < 3; zeros elsewhere (4th channel, 8th pixel of the window, the 8th filter row)."""
+    o = w.shape[0]
+    wk = torch.zeros((o, 4, 8, 2, 4), dtype=torch.float32, device=w.device)   # [O, kb, s(8), r2, c(4)]
+    wr = torch.zeros((o, 8, 8, 4), dtype=torch.float32, device=w.device)      # [O, r(8), s(8), c(4)]
+    wr[:, :7, :7, :3] = w.float().permute(0, 2, 3, 1)                          # [O, R, S, C]
+    wk[:] = wr.view(o, 4, 2, 8, 4).permute(0, 1, 3, 2, 4)
+    return wk.reshape(o, 4 * 64)
+
+
 def stem_window_weights(w: torch.Tensor) -> torch.Tensor:
     """[64,3,7,7] (O,C,R,S) -> [64, 7*64]: one 64-wide K block per filter row r, laid out as the
     window-mode A operand reads the padded NHW8 image: k = s*8 + c for s < 7, c < 3, zeros
@@ -78,7 +90,7 @@ def prep_rgb_trunk(sd: Dict[str, torch.Tensor], ns: str, dev) -> Dict[str, torch
         return (sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"], sd[prefix + ".running_var"])
 
     w, b = fold_bn(sd[p + "conv1.weight"], *bn(p + "bn1"))
-    out[f"{ns}.rgb.stem.w"] = _bf(stem_window_weights(w), dev)
+    out[f"{ns}.rgb.stem.w"] = _bf(stem_packed_weights(w), dev)
     out[f"{ns}.rgb.stem.b"] = _f32(b, dev)
     for li, (nb, _s) in enumerate(_STAGES):
         for blk in range(nb):

@@ -68,6 +68,24 @@ def rgb_stem(rgb, w_win, bias, dtype="fp16", impl=0):
     return out, padded
 
 
+def rgb_stem_packed(rgb, w_pk, bias, dtype="fp16", impl=0):
+    """RGB stem as the engine runs it: row-pair-interleaved pad/convert pre-pass, then the packed window-mode conv (two
+    filter rows per 64-wide K block).  rgb [NB,H,W,3] f32, w_pk [64, 256] h16
+    (weight_prep.stem_packed_weights) -> [NB*Ho*Wo, 64]."""
+    NB, H, W, _ = rgb.shape
+    Hp, Wp = H + 6, W + 6
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    inter = torch.full((NB, Hp // 2, Wp, 2, 4), 3.0, dtype=H16[dtype], device=rgb.device)
+    check(lib(dtype).rvb_rgb_pad_convert4(P(rgb), P(inter), NB, H, W, Wp, stream()), "rvb_rgb_pad_convert4", dtype)
+    out = torch.zeros((NB * Ho * Wo, 64), dtype=H16[dtype], device=rgb.device)
+    rc = lib(dtype).rvb_conv_gemm(P(inter), NB, Hp // 2, Wo, 64, 8, P(w_pk), 64, 4, 1, 2, 0, P(bias), None, 0, 0, 1,
+                                  P(out), 64, 0, 0, impl, 2, Wp * 8, stream())
+    check(rc, "rvb_conv_gemm(packed window)", dtype)
+    torch.cuda.synchronize()
+    padded = inter.permute(0, 1, 3, 2, 4).reshape(NB, Hp, Wp, 4)      # back to plain NHW4 for inspection
+    return out, padded
+
+
 def conv_ref(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows=0, act=0):
     """fp32 torch reference on the same 16-bit-rounded operands."""
     NB, H, W, Cin = x.shape

@@ -171,6 +171,37 @@ def test_rgb_stem_window_conv(hw, dtype):
     assert rel_err(simt, ref) < OUT_TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hw", [(256, 256), (224, 224), (128, 160)])
+def test_rgb_stem_packed_window_conv(hw, dtype):
+    """The stem the engine runs: row-pair-interleaved padded image, overlapping-window TMA boxes that put TWO
+    filter rows in every 64-wide K block (4 K blocks instead of 7), against torch's conv2d on the /255 image."""
+    from robovln_b200.weight_prep import stem_packed_weights
+    from tests.gpu_util import H16, OUT_TOL, rel_err, rgb_stem_packed
+
+    H, W = hw
+    NB = 3
+    g = torch.Generator(device="cuda")
+    g.manual_seed(22)
+    rgb = torch.randint(0, 256, (NB, H, W, 3), generator=g, device="cuda").float()
+    w = torch.randn((64, 3, 7, 7), generator=g, device="cuda") * (2.0 / 147) ** 0.5
+    bias = torch.randn((64,), generator=g, device="cuda") * 0.2
+    w_pk = stem_packed_weights(w).to(H16[dtype]).contiguous()
+    out, padded = rgb_stem_packed(rgb, w_pk, bias, dtype)
+    img = (rgb / 255.0).to(H16[dtype]).float()
+    assert torch.equal(padded[:, 3:H + 3, 3:W + 3, :3].float(), img)
+    assert float(padded[..., 3:].float().abs().max()) == 0.0
+    assert float(padded[:, :3].float().abs().max()) == 0.0 and float(padded[:, :, W + 3:].float().abs().max()) == 0.0
+    w_q = w_pk.float().view(64, 4, 8, 2, 4).permute(0, 1, 3, 2, 4).reshape(64, 8, 8, 4)[:, :7, :7, :3]
+    w_q = w_q.permute(0, 3, 1, 2).contiguous()                                                   # rounded weights, OIHW
+    ref = torch.relu(torch.nn.functional.conv2d(img.permute(0, 3, 1, 2), w_q, bias, stride=2, padding=3))
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, 64)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < OUT_TOL[dtype]
+    simt, _ = rgb_stem_packed(rgb, w_pk, bias, dtype, impl=1)
+    assert rel_err(simt, ref) < OUT_TOL[dtype]
+
+
 def test_output_column_slice_and_pitch():
     """GEMM epilogues write straight into column slices of the LSTM input (ldc > N)."""
     from tests.gpu_util import OUT_TOL, conv_gemm, conv_ref, rel_err

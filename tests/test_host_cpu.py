@@ -104,12 +104,12 @@ def test_weight_prep_numerics():
     t.update(WP.prep_depth_trunk(sd, "hi", "cpu"))
     t.update(WP.prep_bert(sd, "cpu"))
     t.update(WP.prep_hi_tail(sd, "cpu"))
-    assert t["hi.rgb.stem.w"].shape == (64, 448) and t["hi.rgb.stem.w"].dtype == torch.float16   # default build
-    sw = t["hi.rgb.stem.w"].float().view(64, 7, 8, 8)             # [o, filter row, pixel-in-window, channel]
-    assert torch.all(sw[:, :, 7] == 0) and torch.all(sw[:, :, :, 3:] == 0)
+    assert t["hi.rgb.stem.w"].shape == (64, 256) and t["hi.rgb.stem.w"].dtype == torch.float16   # default build
+    sw = t["hi.rgb.stem.w"].float().view(64, 4, 8, 2, 4).permute(0, 1, 3, 2, 4).reshape(64, 8, 8, 4)   # [o, r (8th = 0), s, c]
+    assert torch.all(sw[:, :, 7] == 0) and torch.all(sw[:, :, :, 3:] == 0) and torch.all(sw[:, 7] == 0)
     wf, _ = WP.fold_bn(sd["rgb_encoder.cnn.conv1.weight"], sd["rgb_encoder.cnn.bn1.weight"], sd["rgb_encoder.cnn.bn1.bias"],
                        sd["rgb_encoder.cnn.bn1.running_mean"], sd["rgb_encoder.cnn.bn1.running_var"])
-    assert float((sw[9, 2, 5, 1] - wf[9, 1, 2, 5]).abs()) < 2e-3   # [o, c, r, s] -> block r, k = s*8 + c
+    assert float((sw[9, 2, 5, 1] - wf[9, 1, 2, 5]).abs()) < 2e-3   # [o, c, r, s] -> k = (r//2)*64 + s*8 + (r%2)*4 + c
     assert t["hi.rgb.l4.0.c2.w"].shape == (512, 9 * 512) and t["hi.depth.comp.w"].shape == (128, 9 * 1024)
     assert t["hi.bert.3.qkv.w"].shape == (2304, 768) and t["hi.vla.fc_kv.w"].shape == (512, 256)
     assert t["hi.lstm.b"].dtype == torch.float32
