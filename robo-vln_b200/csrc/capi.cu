@@ -115,7 +115,7 @@ int hcm_forward_policy(hcm_engine* e, const float* rgb, const float* depth, cons
     a.hc_hi_in = hc_hi_in; a.hc_lo_in = hc_lo_in; a.hc_hi_out = hc_hi_out; a.hc_lo_out = hc_lo_out;
     a.logits = logits; a.actions = actions; a.stop = stop_logit; a.sub_goal_out = sub_goal_out;
     e->eng.args_ = a;
-    e->eng.forward_policy(S(stream));
+    e->eng.forward_policy_graphed(S(stream));
   });
 }
 

@@ -520,6 +520,7 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
   RVB_CHECK(dry_ || (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
   arena_off_ = 0;
   arena_cap_ = bytes;
+  drop_graphs();
   gemms_.clear();
   for (Stage* s : {&st_rgb_, &st_depth_, &st_rgb_lo_, &st_depth_lo_, &st_bert_, &st_pre_, &st_hi_tail_, &st_lo_tail_,
                    &st_cm_only_, &st_rgb_post_hi_, &st_depth_post_hi_, &st_bert_post_, &st_rgb_post_lo_, &st_depth_post_lo_})
@@ -572,6 +573,9 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
     if (!streams_ready_) {
       RVB_CUDA(cudaStreamCreateWithFlags(&side_[0], cudaStreamNonBlocking));
       RVB_CUDA(cudaStreamCreateWithFlags(&side_[1], cudaStreamNonBlocking));
+      RVB_CUDA(cudaStreamCreateWithFlags(&capture_, cudaStreamNonBlocking));
+      RVB_CUDA(cudaStreamCreateWithFlags(&upload_, cudaStreamNonBlocking));
+      RVB_CUDA(cudaEventCreateWithFlags(&ev_upload_, cudaEventDisableTiming));
       for (auto& ev : events_) RVB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       streams_ready_ = true;
     }
@@ -596,17 +600,19 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool 
   // per-stream op lists: the encoder followed by the tail ops that consume only that encoder
   std::vector<const Op*> rgb, dep, bert;
   auto append = [](std::vector<const Op*>& v, const Stage& st) { for (const Op& op : st) v.push_back(&op); };
-  append(rgb, (lo_weights && !st_rgb_lo_.empty()) ? st_rgb_lo_ : st_rgb_);
-  append(dep, (lo_weights && !st_depth_lo_.empty()) ? st_depth_lo_ : st_depth_);
+  const bool do_rgb = (enc_mask_ & 1) != 0, do_dep = (enc_mask_ & 2) != 0;
+  with_bert = with_bert && (enc_mask_ & 4) != 0;
+  if (do_rgb) append(rgb, (lo_weights && !st_rgb_lo_.empty()) ? st_rgb_lo_ : st_rgb_);
+  if (do_dep) append(dep, (lo_weights && !st_depth_lo_.empty()) ? st_depth_lo_ : st_depth_);
   if (with_bert) append(bert, st_bert_);
   if (posts_hi) {
-    append(rgb, st_rgb_post_hi_);
-    append(dep, st_depth_post_hi_);
+    if (do_rgb) append(rgb, st_rgb_post_hi_);
+    if (do_dep) append(dep, st_depth_post_hi_);
     if (with_bert) append(bert, st_bert_post_);
   }
   if (posts_lo) {
-    append(rgb, st_rgb_post_lo_);
-    append(dep, st_depth_post_lo_);
+    if (do_rgb) append(rgb, st_rgb_post_lo_);
+    if (do_dep) append(dep, st_depth_post_lo_);
   }
   if (!multi) {
     if (before_rgb_) before_rgb_(s);
@@ -619,14 +625,16 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool 
   // launches ROUND-ROBIN (one RGB op, one BERT op, three of the many tiny depth ops per turn) so
   // that every stream has work queued within the first microseconds of the call; issuing stage
   // after stage would leave the GPU with only the depth trunk's 160 tiny kernels for ~1 ms.
-  RVB_CUDA(cudaEventRecord(events_[0], s));
-  RVB_CUDA(cudaStreamWaitEvent(side_[0], events_[0], 0));
-  if (with_bert) RVB_CUDA(cudaStreamWaitEvent(side_[1], events_[0], 0));
-  if (before_rgb_) before_rgb_(s);   // host entry: the (large) RGB upload overlaps depth trunk + BERT
+  if (!dep.empty() || !bert.empty()) RVB_CUDA(cudaEventRecord(events_[0], s));
+  if (!dep.empty()) RVB_CUDA(cudaStreamWaitEvent(side_[0], events_[0], 0));
+  if (!bert.empty()) RVB_CUDA(cudaStreamWaitEvent(side_[1], events_[0], 0));
+  if (before_rgb_ && !rgb.empty()) before_rgb_(s);   // host entry: the (large) RGB upload overlaps depth trunk + BERT
   size_t ir = 0, id = 0, ib = 0;
   size_t nb = bert.size();
   // timing experiments only (results are wrong): ROBOVLN_SKIP=rgb|depth|bert drops a stage
   static const char* skip = std::getenv("ROBOVLN_SKIP");
+  static const char* pdl_depth_env = std::getenv("ROBOVLN_PDL_DEPTH");
+  const int pdl_depth = (pdl_depth_env != nullptr && std::strcmp(pdl_depth_env, "1") == 0) ? 1 : -1;
   if (skip != nullptr) {
     if (std::strstr(skip, "rgb")) ir = rgb.size();
     if (std::strstr(skip, "depth")) id = dep.size();
@@ -635,11 +643,15 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool 
   while (ir < rgb.size() || id < dep.size() || ib < nb) {
     if (ir < rgb.size()) launches_ += (*rgb[ir++])(s);
     if (ib < nb) launches_ += (*bert[ib++])(side_[1]);
+    g_pdl_override = pdl_depth;
     for (int k = 0; k < 3 && id < dep.size(); ++k) launches_ += (*dep[id++])(side_[0]);
+    g_pdl_override = -1;
   }
-  RVB_CUDA(cudaEventRecord(events_[1], side_[0]));
-  RVB_CUDA(cudaStreamWaitEvent(s, events_[1], 0));
-  if (with_bert) {
+  if (!dep.empty()) {
+    RVB_CUDA(cudaEventRecord(events_[1], side_[0]));
+    RVB_CUDA(cudaStreamWaitEvent(s, events_[1], 0));
+  }
+  if (!bert.empty()) {
     RVB_CUDA(cudaEventRecord(events_[2], side_[1]));
     RVB_CUDA(cudaStreamWaitEvent(s, events_[2], 0));
   }
@@ -689,6 +701,92 @@ void Engine::forward_policy(cudaStream_t s) {
   policy_sg_ = nullptr;
 }
 
+void Engine::drop_graphs() {
+  for (auto& g : graphs_) cudaGraphExecDestroy(g.exec);
+  graphs_.clear();
+  if (host_graphs_.g1 != nullptr) cudaGraphExecDestroy(host_graphs_.g1);
+  if (host_graphs_.g2a != nullptr) cudaGraphExecDestroy(host_graphs_.g2a);
+  if (host_graphs_.g2b != nullptr) cudaGraphExecDestroy(host_graphs_.g2b);
+  host_graphs_ = HostGraphs();
+  eager_runs_ = 0;
+}
+
+void Engine::forward_policy_graphed(cudaStream_t s) {
+  static const char* env = std::getenv("ROBOVLN_GRAPH");
+  const bool enabled = !(env != nullptr && std::strcmp(env, "0") == 0) && multi_stream_;
+  if (!enabled) {
+    forward_policy(s);
+    return;
+  }
+  RVB_CHECK(planned_ && have_hi_ && have_lo_ && lo_shares_trunks_, "forward_policy needs a planned hi+lo engine with shared trunks");
+  const RunArgs user = args_;
+  const int B = shp_.B, N = shp_.N;
+  // the graph writes engine-owned buffers; the caller's (fresh every call) get small device copies
+  args_.logits = logits_buf_; args_.actions = act_buf_; args_.stop = stop_buf_;
+  args_.hc_hi_out = hc_hi_buf_; args_.hc_lo_out = hc_lo_buf_; args_.sub_goal_out = subgoal_buf_;
+  auto copy_out = [&]() {
+    if (user.logits == logits_buf_) return;   // host entry: results are read from the engine's buffers directly
+    const size_t hc_b = 2ull * N * 512 * 4;
+    RVB_CUDA(cudaMemcpyAsync(user.logits, logits_buf_, static_cast<size_t>(B) * 16, cudaMemcpyDeviceToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(user.actions, act_buf_, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(user.stop, stop_buf_, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(user.hc_hi_out, hc_hi_buf_, hc_b, cudaMemcpyDeviceToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(user.hc_lo_out, hc_lo_buf_, hc_b, cudaMemcpyDeviceToDevice, s));
+    if (user.sub_goal_out != nullptr)
+      RVB_CUDA(cudaMemcpyAsync(user.sub_goal_out, subgoal_buf_, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, s));
+  };
+  RVB_CHECK(user.hc_hi_in != hc_hi_buf_ && user.hc_lo_in != hc_lo_buf_, "hidden state in/out must not alias");
+  if (eager_runs_ < 1) {   // first call after planning runs eagerly: one-time kernel attribute setup is not capturable
+    forward_policy(s);
+    ++eager_runs_;
+    copy_out();
+    args_ = user;
+    return;
+  }
+  const void* key[8] = {user.rgb, user.depth, user.instr_f32, user.instr_i64, user.masks,
+                        reinterpret_cast<const void*>(static_cast<uintptr_t>(user.mask_stride)), user.hc_hi_in, user.hc_lo_in};
+  GraphEntry* hit = nullptr;
+  for (auto& g : graphs_)
+    if (std::memcmp(g.key, key, sizeof(key)) == 0) hit = &g;
+  if (hit == nullptr) {
+    if (graphs_.size() >= 8) {   // evict the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < graphs_.size(); ++i)
+        if (graphs_[i].last_use < graphs_[lru].last_use) lru = i;
+      cudaGraphExecDestroy(graphs_[lru].exec);
+      graphs_.erase(graphs_.begin() + lru);
+    }
+    // capture on an engine-owned stream (the caller's may be the legacy default stream, which cannot be
+    // captured); the instantiated graph is then launched on the caller's stream
+    cudaGraph_t graph = nullptr;
+    RVB_CUDA(cudaStreamBeginCapture(capture_, cudaStreamCaptureModeThreadLocal));
+    try {
+      forward_policy(capture_);
+    } catch (...) {
+      cudaStreamEndCapture(capture_, &graph);
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      args_ = user;
+      throw;
+    }
+    RVB_CUDA(cudaStreamEndCapture(capture_, &graph));
+    GraphEntry e;
+    std::memcpy(e.key, key, sizeof(key));
+    e.launches = launches_;
+    e.last_use = 0;
+    cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    RVB_CUDA(ie);
+    graphs_.push_back(e);
+    hit = &graphs_.back();
+  }
+  hit->last_use = ++graph_tick_;
+  RVB_CUDA(cudaGraphLaunch(hit->exec, s));
+  launches_ = hit->launches;
+  trunks_valid_ = true;
+  copy_out();
+  args_ = user;
+}
+
 std::vector<OpTiming> Engine::profile_policy(cudaStream_t s) {
   RVB_CHECK(planned_ && have_hi_ && have_lo_ && lo_shares_trunks_, "profile_policy needs a planned hi+lo engine");
   int64_t* sg = args_.sub_goal_out != nullptr ? args_.sub_goal_out : subgoal_buf_;
@@ -736,32 +834,93 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
   const size_t dep_b = static_cast<size_t>(B) * shp_.depth_h * shp_.depth_w * 4;
   const size_t ins_b = static_cast<size_t>(shp_.instr_rows) * shp_.L * 4;
   const size_t hc_b = 2ull * N * 512 * 4;
-  // small uploads first; the 50 MB RGB upload is issued right before the RGB trunk so that the
-  // depth trunk and BERT (side streams) run underneath it
-  float* stage_rgb = stage_rgb_;
-  before_rgb_ = [stage_rgb, rgb, rgb_b](cudaStream_t st) {
-    RVB_CUDA(cudaMemcpyAsync(stage_rgb, rgb, rgb_b, cudaMemcpyHostToDevice, st));
-  };
-  RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, s));
-  RVB_CUDA(cudaMemcpyAsync(stage_instr_, instr, ins_b, cudaMemcpyHostToDevice, s));
-  RVB_CUDA(cudaMemcpyAsync(stage_masks_, masks, static_cast<size_t>(B) * 2 * 4, cudaMemcpyHostToDevice, s));
-  RVB_CUDA(cudaMemcpyAsync(stage_hc_hi_, hc_hi_in, hc_b, cudaMemcpyHostToDevice, s));
-  RVB_CUDA(cudaMemcpyAsync(stage_hc_lo_, hc_lo_in, hc_b, cudaMemcpyHostToDevice, s));
   RunArgs a;
   a.rgb = stage_rgb_; a.depth = stage_depth_; a.instr_f32 = stage_instr_; a.instr_i64 = nullptr;
   a.masks = stage_masks_; a.mask_stride = 2;
   a.hc_hi_in = stage_hc_hi_; a.hc_lo_in = stage_hc_lo_;
   a.hc_hi_out = hc_hi_buf_; a.hc_lo_out = hc_lo_buf_;
   a.logits = logits_buf_; a.actions = act_buf_; a.stop = stop_buf_;
-  a.sub_goal_out = nullptr;
+  a.sub_goal_out = subgoal_buf_;
   args_ = a;
-  try {
-    forward_policy(s);
-  } catch (...) {
+  auto small_uploads = [&]() {
+    RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(stage_instr_, instr, ins_b, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(stage_masks_, masks, static_cast<size_t>(B) * 2 * 4, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(stage_hc_hi_, hc_hi_in, hc_b, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(stage_hc_lo_, hc_lo_in, hc_b, cudaMemcpyHostToDevice, s));
+  };
+  static const char* genv = std::getenv("ROBOVLN_GRAPH");
+  const bool graphs = !(genv != nullptr && std::strcmp(genv, "0") == 0) && multi_stream_ && have_hi_ && have_lo_ &&
+                      lo_shares_trunks_;
+  if (!graphs || eager_runs_ < 1) {
+    // eager: small uploads first; the 50 MB RGB upload is issued right before the RGB trunk so that the
+    // depth trunk and BERT (side streams) run underneath it
+    small_uploads();
+    float* stage_rgb = stage_rgb_;
+    before_rgb_ = [stage_rgb, rgb, rgb_b](cudaStream_t st) {
+      RVB_CUDA(cudaMemcpyAsync(stage_rgb, rgb, rgb_b, cudaMemcpyHostToDevice, st));
+    };
+    try {
+      forward_policy(s);
+    } catch (...) {
+      before_rgb_ = nullptr;
+      throw;
+    }
     before_rgb_ = nullptr;
-    throw;
+    ++eager_runs_;
+  } else {
+    // Three graphs over the fixed staging buffers: G1 = depth trunk + BERT (+ their single-encoder
+    // consumers), G2a = RGB trunk (+ consumers), G2b = hi tail -> lo tail.  G1 starts as soon as the small
+    // uploads have landed and runs on its own stream underneath the RGB upload; G2a follows the upload.
+    if (!host_graphs_.valid) {
+      auto capture = [&](cudaGraphExec_t* exec, const std::function<void(cudaStream_t)>& body) {
+        cudaGraph_t graph = nullptr;
+        RVB_CUDA(cudaStreamBeginCapture(capture_, cudaStreamCaptureModeThreadLocal));
+        try {
+          body(capture_);
+        } catch (...) {
+          cudaStreamEndCapture(capture_, &graph);
+          if (graph != nullptr) cudaGraphDestroy(graph);
+          enc_mask_ = 7;
+          policy_sg_ = nullptr;
+          throw;
+        }
+        RVB_CUDA(cudaStreamEndCapture(capture_, &graph));
+        cudaError_t ie = cudaGraphInstantiate(exec, graph, 0);
+        cudaGraphDestroy(graph);
+        RVB_CUDA(ie);
+      };
+      int64_t n = 0;
+      launches_ = 0;
+      enc_mask_ = 6;
+      capture(&host_graphs_.g1, [&](cudaStream_t c) { run_encoders(true, false, c, true, true); });
+      enc_mask_ = 1;
+      capture(&host_graphs_.g2a, [&](cudaStream_t c) { run_encoders(true, false, c, true, true); });
+      enc_mask_ = 7;
+      n = launches_;
+      capture(&host_graphs_.g2b, [&](cudaStream_t c) {
+        policy_sg_ = subgoal_buf_;
+        n += run(st_hi_tail_, c);
+        args_.sub_goal = subgoal_buf_;
+        n += run(st_lo_tail_, c);
+        policy_sg_ = nullptr;
+      });
+      host_graphs_.launches = n + static_cast<int64_t>(st_pre_.size());
+      host_graphs_.valid = true;
+    }
+    small_uploads();
+    run(st_pre_, s);
+    RVB_CUDA(cudaEventRecord(events_[3], s));
+    RVB_CUDA(cudaStreamWaitEvent(upload_, events_[3], 0));
+    RVB_CUDA(cudaGraphLaunch(host_graphs_.g1, upload_));
+    RVB_CUDA(cudaEventRecord(ev_upload_, upload_));
+    RVB_CUDA(cudaMemcpyAsync(stage_rgb_, rgb, rgb_b, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaGraphLaunch(host_graphs_.g2a, s));
+    RVB_CUDA(cudaStreamWaitEvent(s, ev_upload_, 0));
+    RVB_CUDA(cudaGraphLaunch(host_graphs_.g2b, s));
+    launches_ = host_graphs_.launches;
+    trunks_valid_ = true;
   }
-  before_rgb_ = nullptr;
   RVB_CUDA(cudaMemcpyAsync(logits, logits_buf_, static_cast<size_t>(B) * 4 * 4, cudaMemcpyDeviceToHost, s));
   RVB_CUDA(cudaMemcpyAsync(actions, act_buf_, static_cast<size_t>(B) * 2 * 4, cudaMemcpyDeviceToHost, s));
   RVB_CUDA(cudaMemcpyAsync(stop, stop_buf_, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
@@ -803,9 +962,13 @@ bool Engine::get_buffer(const std::string& name, void** ptr, int* dtype, std::ve
 }
 
 Engine::~Engine() {
+  drop_graphs();
   if (streams_ready_) {
     cudaStreamDestroy(side_[0]);
     cudaStreamDestroy(side_[1]);
+    cudaStreamDestroy(capture_);
+    cudaStreamDestroy(upload_);
+    cudaEventDestroy(ev_upload_);
     for (auto& ev : events_) cudaEventDestroy(ev);
   }
 }

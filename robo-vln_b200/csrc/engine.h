@@ -69,6 +69,9 @@ class Engine {
   void forward_hi(cudaStream_t s);
   void forward_lo(bool reuse_trunks, cudaStream_t s);
   void forward_policy(cudaStream_t s);
+  // forward_policy replayed from a CUDA graph (captured once per distinct set of input pointers; outputs go
+  // through engine-owned buffers and are copied to the caller's).  ROBOVLN_GRAPH=0 disables.
+  void forward_policy_graphed(cudaStream_t s);
   void forward_policy_host(const float* rgb, const float* depth, const float* instr, const float* masks,
                            const float* hc_hi_in, const float* hc_lo_in, float* logits, float* actions, float* stop,
                            float* hc_hi_out, float* hc_lo_out, cudaStream_t s);
@@ -134,9 +137,28 @@ class Engine {
   float *stage_rgb_ = nullptr, *stage_depth_ = nullptr, *stage_instr_ = nullptr, *stage_masks_ = nullptr,
         *stage_hc_hi_ = nullptr, *stage_hc_lo_ = nullptr;
 
+  struct GraphEntry {
+    const void* key[8];
+    cudaGraphExec_t exec;
+    int64_t launches;
+    uint64_t last_use;
+  };
+  std::vector<GraphEntry> graphs_;
+  struct HostGraphs {
+    cudaGraphExec_t g1 = nullptr, g2a = nullptr, g2b = nullptr;
+    int64_t launches = 0;
+    bool valid = false;
+  } host_graphs_;
+  int enc_mask_ = 7;             // run_encoders: 1 = RGB, 2 = depth, 4 = BERT branches (graph capture of subsets)
+  uint64_t graph_tick_ = 0;
+  int eager_runs_ = 0;           // eager forward_policy calls since the last plan (kernels' one-time setup)
+  void drop_graphs();
   bool trunks_valid_ = false;
   bool streams_ready_ = false;
   cudaStream_t side_[2] = {nullptr, nullptr};
+  cudaStream_t upload_ = nullptr;    // host entry: the RGB frame upload runs here, under the depth trunk and BERT
+  cudaEvent_t ev_upload_ = nullptr;
+  cudaStream_t capture_ = nullptr;   // graph capture happens here (the caller's stream may be the legacy default stream)
   cudaEvent_t events_[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> prof_events_;
 };

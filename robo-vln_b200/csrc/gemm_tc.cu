@@ -607,7 +607,10 @@ bool use_direct_epilogue() {
 
 }  // namespace
 
+thread_local int g_pdl_override = -1;
+
 bool use_pdl() {
+  if (g_pdl_override >= 0) return g_pdl_override == 1;
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("ROBOVLN_PDL");

@@ -38,6 +38,7 @@ struct Error : public std::runtime_error {
 // library calls griddepcontrol.wait before touching data a predecessor may still be writing.
 // ROBOVLN_PDL=0 launches plainly (validation).
 bool use_pdl();
+extern thread_local int g_pdl_override;   // -1: environment default; 0 / 1: forced for the launches that follow
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg;

@@ -147,6 +147,48 @@ def test_lo_without_trunk_reuse_and_policy_entry(models):
     assert hi.runtime().launches() > 100
 
 
+def test_graph_replay_matches_eager(models):
+    """HcmPolicy.act / act_host replay a captured CUDA graph from the second call with the same input
+    pointers on; replays must reproduce the eager (first) call bit for bit, follow NEW input values
+    written into the same tensors, and fall back to a fresh capture for new tensors."""
+    import robovln_b200 as R
+    from oracle import weights as W
+
+    hi, lo, _, _ = models
+    pol = R.HcmPolicy(hi, lo)
+    dev = "cuda"
+    a = W.make_inputs(B=3, L=16, N=3, rgb_hw=256, seed=21, mask_zero_rows=(1,))
+    b = W.make_inputs(B=3, L=16, N=3, rgb_hw=256, seed=22, mask_zero_rows=())
+    keys = ("rgb", "depth", "instruction", "hidden_hi", "hidden_lo", "masks")
+    ta = {k: a[k].to(dev) for k in keys}
+
+    def run(t):
+        out = pol.act({k: t[k] for k in ("rgb", "depth", "instruction")}, t["hidden_hi"], t["hidden_lo"], t["masks"])
+        torch.cuda.synchronize()
+        return [o.clone() for o in out]
+
+    eager = run(ta)                      # first call after planning: eager
+    for _ in range(3):                   # captured, then replayed
+        for x, y in zip(run(ta), eager):
+            assert torch.equal(x, y)
+    tb = {k: b[k].to(dev) for k in keys}
+    ref_b = run(tb)                      # new pointers: new capture
+    for k in keys:                       # new VALUES behind the first graph's pointers
+        ta[k].copy_(tb[k])
+    for x, y in zip(run(ta), ref_b):
+        assert torch.equal(x, y)
+    assert not all(torch.equal(x, y) for x, y in zip(ref_b, eager))
+    # host entry: eager on the first call for its staging buffers, graph afterwards
+    host = {k: a[k].pin_memory() for k in keys}
+    outs = []
+    for _ in range(3):
+        o = pol.act_host(host["rgb"], host["depth"], host["instruction"], host["masks"], host["hidden_hi"], host["hidden_lo"])
+        outs.append({k: v.clone() for k, v in o.items()})
+    for o in outs:
+        assert torch.equal(o["logits"], eager[0].cpu()) and torch.equal(o["actions"], eager[1].cpu())
+        assert torch.equal(o["hidden_hi"], eager[3].cpu()) and torch.equal(o["hidden_lo"], eager[4].cpu())
+
+
 def test_bf16_build_end_to_end(golden_dir):
     """librobovln_b200_bf16.so through the same modules (ROBOVLN_DTYPE=bf16).  bf16 rounding
     (8-bit significand) amplified by the 54-layer GroupNorm trunk and 12 BERT layers reaches
