@@ -575,6 +575,9 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
       RVB_CUDA(cudaStreamCreateWithFlags(&side_[1], cudaStreamNonBlocking));
       RVB_CUDA(cudaStreamCreateWithFlags(&capture_, cudaStreamNonBlocking));
       RVB_CUDA(cudaStreamCreateWithFlags(&upload_, cudaStreamNonBlocking));
+      RVB_CUDA(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
+      RVB_CUDA(cudaEventCreateWithFlags(&ev_aux_[0], cudaEventDisableTiming));
+      RVB_CUDA(cudaEventCreateWithFlags(&ev_aux_[1], cudaEventDisableTiming));
       RVB_CUDA(cudaEventCreateWithFlags(&ev_upload_, cudaEventDisableTiming));
       for (auto& ev : events_) RVB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       streams_ready_ = true;
@@ -705,6 +708,7 @@ void Engine::drop_graphs() {
   for (auto& g : graphs_) cudaGraphExecDestroy(g.exec);
   graphs_.clear();
   if (host_graphs_.g1 != nullptr) cudaGraphExecDestroy(host_graphs_.g1);
+  if (host_graphs_.g1b != nullptr) cudaGraphExecDestroy(host_graphs_.g1b);
   if (host_graphs_.g2a != nullptr) cudaGraphExecDestroy(host_graphs_.g2a);
   if (host_graphs_.g2b != nullptr) cudaGraphExecDestroy(host_graphs_.g2b);
   host_graphs_ = HostGraphs();
@@ -869,9 +873,9 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
     before_rgb_ = nullptr;
     ++eager_runs_;
   } else {
-    // Three graphs over the fixed staging buffers: G1 = depth trunk + BERT (+ their single-encoder
-    // consumers), G2a = RGB trunk (+ consumers), G2b = hi tail -> lo tail.  G1 starts as soon as the small
-    // uploads have landed and runs on its own stream underneath the RGB upload; G2a follows the upload.
+    // Four graphs over the fixed staging buffers: G1b = BERT, G1 = depth trunk, G2a = RGB trunk (each with
+    // its single-encoder consumers), G2b = hi tail -> lo tail.  Every encoder graph starts as soon as ITS
+    // input has landed, on its own stream, underneath the uploads that follow.
     if (!host_graphs_.valid) {
       auto capture = [&](cudaGraphExec_t* exec, const std::function<void(cudaStream_t)>& body) {
         cudaGraph_t graph = nullptr;
@@ -892,7 +896,9 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
       };
       int64_t n = 0;
       launches_ = 0;
-      enc_mask_ = 6;
+      enc_mask_ = 4;
+      capture(&host_graphs_.g1b, [&](cudaStream_t c) { run_encoders(true, false, c, true, true); });
+      enc_mask_ = 2;
       capture(&host_graphs_.g1, [&](cudaStream_t c) { run_encoders(true, false, c, true, true); });
       enc_mask_ = 1;
       capture(&host_graphs_.g2a, [&](cudaStream_t c) { run_encoders(true, false, c, true, true); });
@@ -908,15 +914,25 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
       host_graphs_.launches = n + static_cast<int64_t>(st_pre_.size());
       host_graphs_.valid = true;
     }
-    small_uploads();
-    run(st_pre_, s);
+    // uploads in the order the encoders can start: instruction (tiny) -> BERT, depth -> depth trunk, RGB -> RGB trunk
+    RVB_CUDA(cudaMemcpyAsync(stage_instr_, instr, ins_b, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(stage_masks_, masks, static_cast<size_t>(B) * 2 * 4, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(stage_hc_hi_, hc_hi_in, hc_b, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(stage_hc_lo_, hc_lo_in, hc_b, cudaMemcpyHostToDevice, s));
     RVB_CUDA(cudaEventRecord(events_[3], s));
     RVB_CUDA(cudaStreamWaitEvent(upload_, events_[3], 0));
-    RVB_CUDA(cudaGraphLaunch(host_graphs_.g1, upload_));
+    RVB_CUDA(cudaGraphLaunch(host_graphs_.g1b, upload_));
     RVB_CUDA(cudaEventRecord(ev_upload_, upload_));
+    run(st_pre_, s);
+    RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, s));
+    RVB_CUDA(cudaEventRecord(ev_aux_[0], s));
+    RVB_CUDA(cudaStreamWaitEvent(aux_, ev_aux_[0], 0));
+    RVB_CUDA(cudaGraphLaunch(host_graphs_.g1, aux_));
+    RVB_CUDA(cudaEventRecord(ev_aux_[1], aux_));
     RVB_CUDA(cudaMemcpyAsync(stage_rgb_, rgb, rgb_b, cudaMemcpyHostToDevice, s));
     RVB_CUDA(cudaGraphLaunch(host_graphs_.g2a, s));
     RVB_CUDA(cudaStreamWaitEvent(s, ev_upload_, 0));
+    RVB_CUDA(cudaStreamWaitEvent(s, ev_aux_[1], 0));
     RVB_CUDA(cudaGraphLaunch(host_graphs_.g2b, s));
     launches_ = host_graphs_.launches;
     trunks_valid_ = true;
@@ -968,6 +984,9 @@ Engine::~Engine() {
     cudaStreamDestroy(side_[1]);
     cudaStreamDestroy(capture_);
     cudaStreamDestroy(upload_);
+    cudaStreamDestroy(aux_);
+    cudaEventDestroy(ev_aux_[0]);
+    cudaEventDestroy(ev_aux_[1]);
     cudaEventDestroy(ev_upload_);
     for (auto& ev : events_) cudaEventDestroy(ev);
   }

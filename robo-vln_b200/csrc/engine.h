@@ -145,7 +145,7 @@ class Engine {
   };
   std::vector<GraphEntry> graphs_;
   struct HostGraphs {
-    cudaGraphExec_t g1 = nullptr, g2a = nullptr, g2b = nullptr;
+    cudaGraphExec_t g1 = nullptr, g1b = nullptr, g2a = nullptr, g2b = nullptr;
     int64_t launches = 0;
     bool valid = false;
   } host_graphs_;
@@ -158,6 +158,8 @@ class Engine {
   cudaStream_t side_[2] = {nullptr, nullptr};
   cudaStream_t upload_ = nullptr;    // host entry: the RGB frame upload runs here, under the depth trunk and BERT
   cudaEvent_t ev_upload_ = nullptr;
+  cudaStream_t aux_ = nullptr;       // host entry: depth-trunk graph
+  cudaEvent_t ev_aux_[2] = {nullptr, nullptr};
   cudaStream_t capture_ = nullptr;   // graph capture happens here (the caller's stream may be the legacy default stream)
   cudaEvent_t events_[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> prof_events_;
