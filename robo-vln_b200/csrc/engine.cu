@@ -10,6 +10,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -571,11 +572,20 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
   const size_t need = arena_off_ + 1024;
   if (!dry_) {
     if (!streams_ready_) {
-      RVB_CUDA(cudaStreamCreateWithFlags(&side_[0], cudaStreamNonBlocking));
-      RVB_CUDA(cudaStreamCreateWithFlags(&side_[1], cudaStreamNonBlocking));
+      // The depth trunk is a long chain of tiny kernels: at equal priority it is starved by the SM-filling
+      // GEMMs of the other two encoders and ends up running alone at the end of the step (measured: 1 ms of
+      // the RGB stream waiting for it).  Highest priority for its stream, BERT next, RGB (caller's stream) last.
+      int prio_lo = 0, prio_hi = 0;
+      RVB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      static const char* penv = std::getenv("ROBOVLN_PRIORITIES");
+      const bool prio = !(penv != nullptr && std::strcmp(penv, "0") == 0);
+      const int p_depth = prio ? prio_hi : prio_lo;
+      const int p_bert = prio ? std::min(prio_lo, prio_hi + 1) : prio_lo;
+      RVB_CUDA(cudaStreamCreateWithPriority(&side_[0], cudaStreamNonBlocking, p_depth));
+      RVB_CUDA(cudaStreamCreateWithPriority(&side_[1], cudaStreamNonBlocking, p_bert));
       RVB_CUDA(cudaStreamCreateWithFlags(&capture_, cudaStreamNonBlocking));
       RVB_CUDA(cudaStreamCreateWithFlags(&upload_, cudaStreamNonBlocking));
-      RVB_CUDA(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
+      RVB_CUDA(cudaStreamCreateWithPriority(&aux_, cudaStreamNonBlocking, p_depth));
       RVB_CUDA(cudaEventCreateWithFlags(&ev_aux_[0], cudaEventDisableTiming));
       RVB_CUDA(cudaEventCreateWithFlags(&ev_aux_[1], cudaEventDisableTiming));
       RVB_CUDA(cudaEventCreateWithFlags(&ev_upload_, cudaEventDisableTiming));
@@ -636,19 +646,15 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool 
   size_t nb = bert.size();
   // timing experiments only (results are wrong): ROBOVLN_SKIP=rgb|depth|bert drops a stage
   static const char* skip = std::getenv("ROBOVLN_SKIP");
-  static const char* pdl_depth_env = std::getenv("ROBOVLN_PDL_DEPTH");
-  const int pdl_depth = (pdl_depth_env != nullptr && std::strcmp(pdl_depth_env, "1") == 0) ? 1 : -1;
   if (skip != nullptr) {
     if (std::strstr(skip, "rgb")) ir = rgb.size();
     if (std::strstr(skip, "depth")) id = dep.size();
     if (std::strstr(skip, "bert")) nb = 0;
   }
   while (ir < rgb.size() || id < dep.size() || ib < nb) {
-    if (ir < rgb.size()) launches_ += (*rgb[ir++])(s);
-    if (ib < nb) launches_ += (*bert[ib++])(side_[1]);
-    g_pdl_override = pdl_depth;
-    for (int k = 0; k < 3 && id < dep.size(); ++k) launches_ += (*dep[id++])(side_[0]);
-    g_pdl_override = -1;
+    if (ir < rgb.size()) { launches_ += (*rgb[ir])(s); tl_mark(0, &rgb[ir]->name, s); ++ir; }
+    if (ib < nb) { launches_ += (*bert[ib])(side_[1]); tl_mark(2, &bert[ib]->name, side_[1]); ++ib; }
+    for (int k = 0; k < 3 && id < dep.size(); ++k) { launches_ += (*dep[id])(side_[0]); tl_mark(1, &dep[id]->name, side_[0]); ++id; }
   }
   if (!dep.empty()) {
     RVB_CUDA(cudaEventRecord(events_[1], side_[0]));
@@ -662,12 +668,23 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool 
 
 void Engine::forward_hi(cudaStream_t s) {
   RVB_CHECK(planned_ && have_hi_, "forward_hi: engine not planned or hi weights missing");
+  static const char* tlp = std::getenv("ROBOVLN_TIMELINE");
+  tl_path_ = tlp;
+  if (tl_path_ != nullptr) {
+    if (tl_start_ == nullptr) RVB_CUDA(cudaEventCreate(&tl_start_));
+    RVB_CUDA(cudaEventRecord(tl_start_, s));
+  }
   RVB_CHECK(args_.rgb && args_.depth && (args_.instr_f32 || args_.instr_i64) && args_.masks && args_.hc_hi_in &&
                 args_.hc_hi_out && args_.logits, "forward_hi: null argument");
   launches_ = 0;
   launches_ += run(st_pre_, s);
   run_encoders(true, false, s, true, have_lo_ && lo_shares_trunks_);
-  launches_ += run(st_hi_tail_, s);
+  if (tl_path_ != nullptr) {
+    for (const Op& op : st_hi_tail_) { launches_ += op(s); tl_mark(0, &op.name, s); }
+    tl_flush(s);
+  } else {
+    launches_ += run(st_hi_tail_, s);
+  }
   trunks_valid_ = true;
 }
 
@@ -702,6 +719,29 @@ void Engine::forward_policy(cudaStream_t s) {
     throw;
   }
   policy_sg_ = nullptr;
+}
+
+void Engine::tl_mark(int stream_id, const std::string* name, cudaStream_t st) {
+  if (tl_path_ == nullptr) return;
+  cudaEvent_t ev;
+  RVB_CUDA(cudaEventCreate(&ev));
+  RVB_CUDA(cudaEventRecord(ev, st));
+  tl_.push_back({stream_id, name, ev});
+}
+
+void Engine::tl_flush(cudaStream_t s) {
+  if (tl_path_ == nullptr || tl_.empty()) return;
+  RVB_CUDA(cudaStreamSynchronize(s));
+  FILE* f = std::fopen(tl_path_, "a");
+  if (f != nullptr) std::fprintf(f, "# step\n");
+  for (auto& r : tl_) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, tl_start_, r.ev);
+    if (f != nullptr) std::fprintf(f, "%d,%.1f,%s\n", r.stream, ms * 1e3, r.name != nullptr ? r.name->c_str() : "-");
+    cudaEventDestroy(r.ev);
+  }
+  if (f != nullptr) std::fclose(f);
+  tl_.clear();
 }
 
 void Engine::drop_graphs() {

@@ -153,6 +153,14 @@ class Engine {
   uint64_t graph_tick_ = 0;
   int eager_runs_ = 0;           // eager forward_policy calls since the last plan (kernels' one-time setup)
   void drop_graphs();
+  // ROBOVLN_TIMELINE=path: eager multi-stream step with a timing event after every op of every stream; the
+  // completion time of each op (relative to the step's start) is appended to `path` (diagnostics only)
+  struct TlRec { int stream; const std::string* name; cudaEvent_t ev; };
+  std::vector<TlRec> tl_;
+  cudaEvent_t tl_start_ = nullptr;
+  const char* tl_path_ = nullptr;
+  void tl_mark(int stream_id, const std::string* name, cudaStream_t st);
+  void tl_flush(cudaStream_t s);
   bool trunks_valid_ = false;
   bool streams_ready_ = false;
   cudaStream_t side_[2] = {nullptr, nullptr};
