@@ -111,43 +111,27 @@ ConvGemm Engine::linear(const h16* in, int64_t M, int K, int64_t lda, const h16*
 // ---------------------------------------------------------------------------------------
 // RGB trunk: torchvision ResNet-50 v1.5, eval-mode BN folded into the conv weights + bias
 // ---------------------------------------------------------------------------------------
-void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
-  const int B = shp_.B, H = shp_.rgb_h, W = shp_.rgb_w;
-  const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;   // conv1 7x7 s2 p3
-  const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1; // maxpool 3x3 s2 p1
-  // stem: zero-padded row-pair-interleaved image -> 7x7 s2 conv on the tensor cores in packed window
-  // mode (4 K blocks, two filter rows each) -> maxpool
-  const int Hp = H + 6, Wp = W + 6;
-  h16* padded = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * Hp * Wp * 4 * 2));
-  h16* stem = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 64 * 2));
-  h16* x = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 64 * 2));
-  if (!dry_) {
-    st.push_back([this, padded, B, H, W, Wp](cudaStream_t s) { rgb_pad_convert4(args_.rgb, padded, B, H, W, Wp, s); return 1; });
-    ConvGemm g;
-    g.in = padded; g.NB = B; g.H = Hp / 2; g.W = W1; g.Cin = 64; g.in_pitch = 8;
-    g.window = 2; g.win_row_pitch = static_cast<int64_t>(Wp) * 8;
-    g.w = Wb(ns + ".rgb.stem.w", {64, 4 * 64}); g.Cout = 64; g.KH = 4; g.KW = 1; g.stride = 2; g.pad = 0;
-    g.bias = Wf(ns + ".rgb.stem.b", {64}); g.act = ACT_RELU; g.out = stem; g.ldc = 64;
-    add_gemm(st, g);
-    st.push_back([stem, x, B, H1, W1](cudaStream_t s) { maxpool3x3s2(stem, x, B, H1, W1, 64, s); return 1; });
-  }
-  int h = H2, w = W2, cin = 64;
+// Bottleneck stages [li_begin, li_end) of the RGB trunk on NB images starting at x [NB,h,w,cin]; the
+// last block writes to out_last when given.  Returns the output pointer and updates h, w, cin.
+h16* Engine::plan_rgb_blocks(const std::string& ns, Stage& st, h16* x, int NB, int& h, int& w, int& cin, int li_begin,
+                             int li_end, h16* out_last) {
   const int nblocks[4] = {3, 4, 6, 3};
-  for (int li = 0; li < 4; ++li) {
+  for (int li = li_begin; li < li_end; ++li) {
     const int mid = 64 << li, cout = mid * 4;
     for (int b = 0; b < nblocks[li]; ++b) {
       const int stride = (b == 0 && li > 0) ? 2 : 1;
       const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
       const std::string p = ns + ".rgb.l" + std::to_string(li + 1) + "." + std::to_string(b);
-      h16* t1 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * h * w * mid * 2));
-      h16* t2 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * mid * 2));
-      h16* out = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+      h16* t1 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(NB) * h * w * mid * 2));
+      h16* t2 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(NB) * ho * wo * mid * 2));
+      const bool last = (li == li_end - 1 && b == nblocks[li] - 1 && out_last != nullptr);
+      h16* out = last ? out_last : reinterpret_cast<h16*>(alloc(static_cast<size_t>(NB) * ho * wo * cout * 2));
       const h16* idt = x;
       if (b == 0) {
-        h16* ds = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * ho * wo * cout * 2));
+        h16* ds = reinterpret_cast<h16*>(alloc(static_cast<size_t>(NB) * ho * wo * cout * 2));
         if (!dry_) {
           ConvGemm g;
-          g.in = x; g.NB = B; g.H = h; g.W = w; g.Cin = cin; g.in_pitch = cin;
+          g.in = x; g.NB = NB; g.H = h; g.W = w; g.Cin = cin; g.in_pitch = cin;
           g.w = Wb(p + ".ds.w", {cout, cin}); g.Cout = cout; g.KH = g.KW = 1; g.stride = stride; g.pad = 0;
           g.bias = Wf(p + ".ds.b", {cout}); g.act = ACT_NONE; g.out = ds; g.ldc = cout;
           add_gemm(st, g);
@@ -155,19 +139,68 @@ void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
         idt = ds;
       }
       if (!dry_) {
-        add_gemm(st, linear(x, static_cast<int64_t>(B) * h * w, cin, cin, Wb(p + ".c1.w", {mid, cin}), mid,
+        add_gemm(st, linear(x, static_cast<int64_t>(NB) * h * w, cin, cin, Wb(p + ".c1.w", {mid, cin}), mid,
                             Wf(p + ".c1.b", {mid}), ACT_RELU, t1, mid, 0));
         ConvGemm g;
-        g.in = t1; g.NB = B; g.H = h; g.W = w; g.Cin = mid; g.in_pitch = mid;
+        g.in = t1; g.NB = NB; g.H = h; g.W = w; g.Cin = mid; g.in_pitch = mid;
         g.w = Wb(p + ".c2.w", {mid, 9 * mid}); g.Cout = mid; g.KH = g.KW = 3; g.stride = stride; g.pad = 1;
         g.bias = Wf(p + ".c2.b", {mid}); g.act = ACT_RELU; g.out = t2; g.ldc = mid;
         add_gemm(st, g);
-        add_gemm(st, linear(t2, static_cast<int64_t>(B) * ho * wo, mid, mid, Wb(p + ".c3.w", {cout, mid}), cout,
+        add_gemm(st, linear(t2, static_cast<int64_t>(NB) * ho * wo, mid, mid, Wb(p + ".c3.w", {cout, mid}), cout,
                             Wf(p + ".c3.b", {cout}), ACT_RELU, out, cout, 0, idt, cout, 0));
       }
       x = out; h = ho; w = wo; cin = cout;
     }
   }
+  return x;
+}
+
+void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
+  const int B = shp_.B, H = shp_.rgb_h, W = shp_.rgb_w;
+  const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;   // conv1 7x7 s2 p3
+  const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1; // maxpool 3x3 s2 p1
+  const int Hp = H + 6, Wp = W + 6;
+  // The high-resolution front of the trunk (stem, layer1, layer2) streams hundreds of MB per layer at
+  // batch 64 -- far more than the 126 MB L2.  It is therefore planned per SUB-BATCH of B/q images, depth
+  // first, through one set of scratch buffers that every sub-batch reuses: the working set of a sub-batch
+  // stays L2-resident from layer to layer and the scratch lines are overwritten before they are ever
+  // written back.  layer3/layer4 (small activations, weight-heavy) run on the whole batch.
+  static const char* senv = std::getenv("ROBOVLN_RGB_SPLIT");
+  int q = senv != nullptr ? std::atoi(senv) : 1;
+  if (q < 1 || B % q != 0) q = 1;
+  const int NBs = B / q;
+  const int h3 = ((H2 + 2 - 3) / 2 + 1), w3 = ((W2 + 2 - 3) / 2 + 1);   // layer2 output resolution
+  h16* l2out = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * h3 * w3 * 512 * 2));
+  const size_t mark = arena_off_;
+  size_t high = mark;
+  int h = H2, w = W2, cin = 64;
+  for (int sb = 0; sb < q; ++sb) {
+    arena_off_ = mark;   // same scratch addresses for every sub-batch
+    // stem: zero-padded row-pair-interleaved image -> 7x7 s2 conv on the tensor cores in packed window
+    // mode (4 K blocks, two filter rows each) -> maxpool
+    h16* padded = reinterpret_cast<h16*>(alloc(static_cast<size_t>(NBs) * Hp * Wp * 4 * 2));
+    h16* stem = reinterpret_cast<h16*>(alloc(static_cast<size_t>(NBs) * H1 * W1 * 64 * 2));
+    h16* x = reinterpret_cast<h16*>(alloc(static_cast<size_t>(NBs) * H2 * W2 * 64 * 2));
+    if (!dry_) {
+      const size_t in_off = static_cast<size_t>(sb) * NBs * H * W * 3;
+      st.push_back([this, padded, NBs, H, W, Wp, in_off](cudaStream_t s) {
+        rgb_pad_convert4(args_.rgb + in_off, padded, NBs, H, W, Wp, s);
+        return 1;
+      });
+      ConvGemm g;
+      g.in = padded; g.NB = NBs; g.H = Hp / 2; g.W = W1; g.Cin = 64; g.in_pitch = 8;
+      g.window = 2; g.win_row_pitch = static_cast<int64_t>(Wp) * 8;
+      g.w = Wb(ns + ".rgb.stem.w", {64, 4 * 64}); g.Cout = 64; g.KH = 4; g.KW = 1; g.stride = 2; g.pad = 0;
+      g.bias = Wf(ns + ".rgb.stem.b", {64}); g.act = ACT_RELU; g.out = stem; g.ldc = 64;
+      add_gemm(st, g);
+      st.push_back([stem, x, NBs, H1, W1](cudaStream_t s) { maxpool3x3s2(stem, x, NBs, H1, W1, 64, s); return 1; });
+    }
+    h = H2; w = W2; cin = 64;
+    plan_rgb_blocks(ns, st, x, NBs, h, w, cin, 0, 2, l2out + static_cast<size_t>(sb) * NBs * h3 * w3 * 512);
+    high = std::max(high, arena_off_);
+  }
+  arena_off_ = high;
+  h16* x = plan_rgb_blocks(ns, st, l2out, B, h, w, cin, 2, 4, nullptr);
   rgb_feat_ = x; rgb_fh_ = h; rgb_fw_ = w;
   if (!dry_) {
     h16* feat = x;

@@ -110,6 +110,8 @@ class Engine {
                          void* out, int64_t ldc, int out_f32, const h16* res = nullptr, int64_t ldr = 0,
                          int res_rows = 0);
   void plan_rgb_trunk(const std::string& ns, Stage& st);
+  h16* plan_rgb_blocks(const std::string& ns, Stage& st, h16* x, int NB, int& h, int& w, int& cin, int li_begin, int li_end,
+                       h16* out_last);
   void plan_depth_trunk(const std::string& ns, Stage& st);
   void plan_bert(Stage& st);
   void plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch);
