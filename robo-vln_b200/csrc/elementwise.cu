@@ -353,7 +353,26 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const GnApplyDev 
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.0f;
-    for (int p = prow; p < a.HW; p += rows_per_iter) {
+    // four 16-byte loads in flight per thread: one CTA streams up to 256 KB here, and with a single
+    // outstanding load per thread the pass ran at a few GB/s per SM
+    int p = prow;
+    for (; p + 3 * rows_per_iter < a.HW; p += 4 * rows_per_iter) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p + u * rows_per_iter) * a.C));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = unpack_h2(w[j]);
+          s[2 * j] += t.x; q[2 * j] = fmaf(t.x, t.x, q[2 * j]);
+          s[2 * j + 1] += t.y; q[2 * j + 1] = fmaf(t.y, t.y, q[2 * j + 1]);
+        }
+      }
+    }
+    for (; p < a.HW; p += rows_per_iter) {
       float f[8];
       load8(base + static_cast<long long>(p) * a.C, f);
 #pragma unroll
@@ -402,30 +421,39 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const GnApplyDev 
   }
   // pass 2
   const long long pix0 = static_cast<long long>(img) * a.HW;
-  for (int i = threadIdx.x; i < a.HW * cv; i += blockDim.x) {
-    const int v = i % cv;
-    const long long pix = pix0 + i / cv;
-    const int c0 = v * 8;
-    float f[8];
-    load8(a.x + pix * a.C + c0, f);
+  // (slot, prow) mapping as in pass 1: this thread's 8 channels are fixed, so its scale/shift live in
+  // registers; two pixels per iteration keep 2-4 loads in flight
+  const int c0 = slot * 8;
+  float scx[8], shx[8], scr[8], shr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc_x[c0 + j], sh_x[c0 + j]);
-    if (a.res_mode == 1) {
-      float r[8];
-      load8(a.res + pix * a.C + c0, r);
+  for (int j = 0; j < 8; ++j) {
+    scx[j] = sc_x[c0 + j]; shx[j] = sh_x[c0 + j];
+    scr[j] = (a.res_mode == 2) ? sc_r[c0 + j] : 1.0f;
+    shr[j] = (a.res_mode == 2) ? sh_r[c0 + j] : 0.0f;
+  }
+  for (int p0 = prow; p0 < a.HW; p0 += 2 * rows_per_iter) {
+    float f[2][8], r[2][8];
+    bool ok[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
-    } else if (a.res_mode == 2) {
-      float r[8];
-      load8(a.res + pix * a.C + c0, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += fmaf(r[j], sc_r[c0 + j], sh_r[c0 + j]);
+    for (int u = 0; u < 2; ++u) {
+      const int p = p0 + u * rows_per_iter;
+      ok[u] = p < a.HW;
+      if (ok[u]) {
+        load8(a.x + (pix0 + p) * a.C + c0, f[u]);
+        if (a.res_mode != 0) load8(a.res + (pix0 + p) * a.C + c0, r[u]);
+      }
     }
-    if (a.relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(f[u][j], scx[j], shx[j]);
+        if (a.res_mode != 0) v += fmaf(r[u][j], scr[j], shr[j]);
+        f[u][j] = a.relu ? fmaxf(v, 0.0f) : v;
+      }
+      store8(a.out + (pix0 + p0 + u * rows_per_iter) * a.out_pitch + c0, f[u]);
     }
-    store8(a.out + pix * a.out_pitch + c0, f);
   }
 }
 
