@@ -189,15 +189,27 @@ __global__ void __launch_bounds__(256) depth_stem_kernel(const float* __restrict
     rows[i] = v;
   }
   __syncthreads();
+  // thread = (channel, group of 4 consecutive output columns): per filter row the 13 inputs the four
+  // sliding windows share are read once and each weight feeds 4 FMAs (0.7 shared loads per FMA instead of 2)
   const int ch = threadIdx.x & 31;
-  for (int wo = threadIdx.x >> 5; wo < Wo; wo += blockDim.x >> 5) {
-    float acc = 0.0f;
+  for (int wg = threadIdx.x >> 5; wg * 4 < Wo; wg += blockDim.x >> 5) {
+    const int wo0 = wg * 4;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
+      float x[13];
 #pragma unroll
-      for (int s = 0; s < 7; ++s) acc = fmaf(rows[r * RW + 2 * wo + s], ws[(r * 7 + s) * 32 + ch], acc);
+      for (int i = 0; i < 13; ++i) x[i] = (2 * wo0 + i < RW) ? rows[r * RW + 2 * wo0 + i] : 0.0f;
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const float wv = ws[(r * 7 + s) * 32 + ch];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(x[2 * j + s], wv, acc[j]);
+      }
     }
-    out[((static_cast<long long>(img) * Ho + ho) * Wo + wo) * 32 + ch] = to_h16(acc);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (wo0 + j < Wo) out[((static_cast<long long>(img) * Ho + ho) * Wo + wo0 + j) * 32 + ch] = to_h16(acc[j]);
   }
 }
 
