@@ -151,6 +151,12 @@ int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in
 /* window != 0 ("window mode", the RGB stem): `in` is the zero-padded [NB,H,win_row_pitch/8,8] image
  * written by rvb_rgb_pad_convert, W is the OUTPUT width, KW must be 1 and Cin 64 (8 px x 8 ch per
  * filter row), weights [Cout, KH*64]. */
+/* GEMM with LayerNorm folded into the store: out[M,N] (h16) = LN(act(A[M,K] . W[N,K]^T + bias + res[m % res_rows]))
+ * * gamma + beta (+ pe[m % pe_rows]); N in {256, 512, 768}; statistics in fp32 over the fp32 accumulators
+ * (BertSelfOutput / BertOutput, modeling_bert; transformer.py:38-43,111-126,262-281). */
+int rvb_gemm_ln(const void* a_h16, int64_t M, int K, const void* w_h16, int N, const float* bias, const void* res_h16,
+                int res_rows, int act, const float* gamma, const float* beta, float eps, const float* pe, int pe_rows,
+                void* out_h16, void* stream);
 int rvb_rgb_pad_convert(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream);
 /* Packed stem (window == 2, what the engine runs): zero-padded ROW-PAIR-INTERLEAVED image [NB, (H+6)/2, Wp, 2, 4]
  * (H even); the conv takes H = (H+6)/2 row pairs, W = OUTPUT width, in_pitch 8, KH = 4 (row pairs), KW 1, stride 2,

@@ -249,6 +249,22 @@ int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in
   });
 }
 
+int rvb_gemm_ln(const void* a_h16, int64_t M, int K, const void* w_h16, int N, const float* bias, const void* res_h16,
+                int res_rows, int act, const float* gamma, const float* beta, float eps, const float* pe, int pe_rows,
+                void* out_h16, void* stream) {
+  return guarded([&] {
+    ConvGemm g;
+    g.in = B16(a_h16); g.NB = 1; g.H = 1; g.W = static_cast<int>(M); g.Cin = K; g.in_pitch = K;
+    g.w = B16(w_h16); g.Cout = N; g.KH = g.KW = 1; g.stride = 1; g.pad = 0;
+    g.bias = bias; g.res = B16(res_h16); g.ldr = N; g.res_rows = res_rows; g.act = act;
+    g.out = out_h16; g.ldc = N; g.out_f32 = 0;
+    g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.ln_pe = pe; g.ln_pe_rows = pe_rows > 0 ? pe_rows : 1;
+    GemmTcPlan plan;
+    gemm_tc_make_plan(g, &plan, 0);
+    gemm_tc_launch(plan, S(stream));
+  });
+}
+
 int rvb_groupnorm(const void* x_bf16, float* stats, const float* gamma, const float* beta, int NB, int HW, int C, int G,
                   int relu, const void* res_bf16, void* out_bf16, int64_t out_pitch, void* stream) {
   return guarded([&] {

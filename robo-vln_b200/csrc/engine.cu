@@ -108,6 +108,26 @@ ConvGemm Engine::linear(const h16* in, int64_t M, int K, int64_t lda, const h16*
   return g;
 }
 
+// LayerNorm folded into the producing GEMM's store (gemm_tc.cu, LN epilogue).  ROBOVLN_LN_FUSED = 0: never,
+// 1 (default): where one CTA holds the whole row (N = 256: the four LayerNorms of the cross-modal block),
+// 2: also BERT's N = 768 LayerNorms (3-CTA clusters exchanging row statistics over DSMEM; measured slower than
+// GEMM + LayerNorm kernel inside the three-stream step: cluster launches wait for three free SMs in one GPC).
+static int ln_fused_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_LN_FUSED");
+    v = (e != nullptr) ? std::atoi(e) : 1;
+  }
+  return v;
+}
+static bool use_ln_fused() { return ln_fused_level() >= 1; }
+static bool use_ln_fused_bert() { return ln_fused_level() >= 2; }
+
+static ConvGemm with_ln(ConvGemm g, const float* gamma, const float* beta, float eps, const float* pe = nullptr, int pe_rows = 1) {
+  g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.ln_pe = pe; g.ln_pe_rows = pe_rows;
+  return g;
+}
+
 // ---------------------------------------------------------------------------------------
 // RGB trunk: torchvision ResNet-50 v1.5, eval-mode BN folded into the conv weights + bias
 // ---------------------------------------------------------------------------------------
@@ -352,9 +372,14 @@ void Engine::plan_bert(Stage& st) {
     add_gemm(st, linear(xa, M, 768, 768, Wb(p + ".qkv.w", {2304, 768}), 2304, Wf(p + ".qkv.b", {2304}), ACT_NONE, qkv,
                         2304, 0));
     st.push_back([qkv, ctx, R, L](cudaStream_t s) { bert_self_attention(qkv, ctx, R, L, 12, s); return 1; });
-    add_gemm(st, linear(ctx, M, 768, 768, Wb(p + ".ao.w", {768, 768}), 768, Wf(p + ".ao.b", {768}), ACT_NONE, y, 768, 1,
-                        xa, 768, 0));
-    {
+    if (use_ln_fused_bert()) {
+      // attention output projection + residual + LayerNorm in one launch (3-CTA clusters share the row statistics)
+      add_gemm(st, with_ln(linear(ctx, M, 768, 768, Wb(p + ".ao.w", {768, 768}), 768, Wf(p + ".ao.b", {768}), ACT_NONE, xb,
+                                  768, 0, xa, 768, 0),
+                           Wf(p + ".ln1.w", {768}), Wf(p + ".ln1.b", {768}), 1e-12f));
+    } else {
+      add_gemm(st, linear(ctx, M, 768, 768, Wb(p + ".ao.w", {768, 768}), 768, Wf(p + ".ao.b", {768}), ACT_NONE, y, 768, 1,
+                          xa, 768, 0));
       const float* g = Wf(p + ".ln1.w", {768});
       const float* b = Wf(p + ".ln1.b", {768});
       st.push_back([y, M, g, b, xb](cudaStream_t s) {
@@ -364,9 +389,13 @@ void Engine::plan_bert(Stage& st) {
     }
     add_gemm(st, linear(xb, M, 768, 768, Wb(p + ".ff1.w", {3072, 768}), 3072, Wf(p + ".ff1.b", {3072}), ACT_GELU, hbuf,
                         3072, 0));
-    add_gemm(st, linear(hbuf, M, 3072, 3072, Wb(p + ".ff2.w", {768, 3072}), 768, Wf(p + ".ff2.b", {768}), ACT_NONE, y,
-                        768, 1, xb, 768, 0));
-    {
+    if (use_ln_fused_bert()) {
+      add_gemm(st, with_ln(linear(hbuf, M, 3072, 3072, Wb(p + ".ff2.w", {768, 3072}), 768, Wf(p + ".ff2.b", {768}), ACT_NONE,
+                                  xa, 768, 0, xb, 768, 0),
+                           Wf(p + ".ln2.w", {768}), Wf(p + ".ln2.b", {768}), 1e-12f));
+    } else {
+      add_gemm(st, linear(hbuf, M, 3072, 3072, Wb(p + ".ff2.w", {768, 3072}), 768, Wf(p + ".ff2.b", {768}), ACT_NONE, y,
+                          768, 1, xb, 768, 0));
       const float* g = Wf(p + ".ln2.w", {768});
       const float* b = Wf(p + ".ln2.b", {768});
       st.push_back([y, M, g, b, xa](cudaStream_t s) {
@@ -403,26 +432,40 @@ void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16*
   const float* ln0b = Wf(p + ".ln0.b", {256});
   // query side (shared by both modalities; depends on BERT only -> stage stq)
   stq.push_back([pe, L](cudaStream_t s) { sinusoid_table(pe, L, 256, s); return 1; });
-  add_gemm(stq, linear(bert, MQ, 768, 768, Wb(p + ".ins_fc.w", {256, 768}), 256, Wf(p + ".ins_fc.b", {256}), ACT_RELU,
-                       f32q, 256, 1));
-  stq.push_back([f32q, MQ, ln0w, ln0b, pe, L, Q0](cudaStream_t s) {
-    layernorm_rows(f32q, static_cast<int>(MQ), 256, ln0w, ln0b, 1e-5f, pe, L, Q0, s);
-    return 1;
-  });
+  if (use_ln_fused()) {
+    add_gemm(stq, with_ln(linear(bert, MQ, 768, 768, Wb(p + ".ins_fc.w", {256, 768}), 256, Wf(p + ".ins_fc.b", {256}),
+                                 ACT_RELU, Q0, 256, 0), ln0w, ln0b, 1e-5f, pe, L));
+  } else {
+    add_gemm(stq, linear(bert, MQ, 768, 768, Wb(p + ".ins_fc.w", {256, 768}), 256, Wf(p + ".ins_fc.b", {256}), ACT_RELU,
+                         f32q, 256, 1));
+    stq.push_back([f32q, MQ, ln0w, ln0b, pe, L, Q0](cudaStream_t s) {
+      layernorm_rows(f32q, static_cast<int>(MQ), 256, ln0w, ln0b, 1e-5f, pe, L, Q0, s);
+      return 1;
+    });
+  }
   add_gemm(stq, linear(Q0, MQ, 256, 256, Wb(p + ".fc_q.w", {256, 256}), 256, Wf(p + ".fc_q.b", {256}), ACT_NONE, qq, 256, 0));
   // key/value side
-  add_gemm(st, linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
-                      f32a, 256, 1));
-  st.push_back([f32a, MV, ln0w, ln0b, vis](cudaStream_t s) {
-    layernorm_rows(f32a, static_cast<int>(MV), 256, ln0w, ln0b, 1e-5f, nullptr, 1, vis, s);
-    return 1;
-  });
+  if (use_ln_fused()) {
+    add_gemm(st, with_ln(linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
+                                vis, 256, 0), ln0w, ln0b, 1e-5f));
+  } else {
+    add_gemm(st, linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
+                        f32a, 256, 1));
+    st.push_back([f32a, MV, ln0w, ln0b, vis](cudaStream_t s) {
+      layernorm_rows(f32a, static_cast<int>(MV), 256, ln0w, ln0b, 1e-5f, nullptr, 1, vis, s);
+      return 1;
+    });
+  }
   add_gemm(st, linear(vis, MV, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}), ACT_NONE, kv, 512, 0));
   const int q_shared = (R == 1) ? 1 : 0;
   st.push_back([qq, kv, ctx, B, L, q_shared](cudaStream_t s) { vla_cross_attention(qq, kv, ctx, B, L, 2, q_shared, s); return 1; });
-  add_gemm(st, linear(ctx, MX, 256, 256, Wb(p + ".fc_o.w", {256, 256}), 256, Wf(p + ".fc_o.b", {256}), ACT_NONE, f32a, 256,
-                      1, Q0, 256, static_cast<int>(MQ)));
-  {
+  if (use_ln_fused()) {
+    add_gemm(st, with_ln(linear(ctx, MX, 256, 256, Wb(p + ".fc_o.w", {256, 256}), 256, Wf(p + ".fc_o.b", {256}), ACT_NONE, X,
+                                256, 0, Q0, 256, static_cast<int>(MQ)),
+                         Wf(p + ".ln1.w", {256}), Wf(p + ".ln1.b", {256}), 1e-5f));
+  } else {
+    add_gemm(st, linear(ctx, MX, 256, 256, Wb(p + ".fc_o.w", {256, 256}), 256, Wf(p + ".fc_o.b", {256}), ACT_NONE, f32a, 256,
+                        1, Q0, 256, static_cast<int>(MQ)));
     const float* g = Wf(p + ".ln1.w", {256});
     const float* b = Wf(p + ".ln1.b", {256});
     st.push_back([f32a, MX, g, b, X](cudaStream_t s) {
@@ -431,9 +474,13 @@ void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16*
     });
   }
   add_gemm(st, linear(X, MX, 256, 256, Wb(p + ".fc1.w", {1024, 256}), 1024, Wf(p + ".fc1.b", {1024}), ACT_RELU, hff, 1024, 0));
-  add_gemm(st, linear(hff, MX, 1024, 1024, Wb(p + ".fc2.w", {256, 1024}), 256, Wf(p + ".fc2.b", {256}), ACT_NONE, f32a,
-                      256, 1, X, 256, 0));
-  {
+  if (use_ln_fused()) {
+    add_gemm(st, with_ln(linear(hff, MX, 1024, 1024, Wb(p + ".fc2.w", {256, 1024}), 256, Wf(p + ".fc2.b", {256}), ACT_NONE, Y,
+                                256, 0, X, 256, 0),
+                         Wf(p + ".ln2.w", {256}), Wf(p + ".ln2.b", {256}), 1e-5f));
+  } else {
+    add_gemm(st, linear(hff, MX, 1024, 1024, Wb(p + ".fc2.w", {256, 1024}), 256, Wf(p + ".fc2.b", {256}), ACT_NONE, f32a,
+                        256, 1, X, 256, 0));
     const float* g = Wf(p + ".ln2.w", {256});
     const float* b = Wf(p + ".ln2.b", {256});
     st.push_back([f32a, MX, g, b, Y](cudaStream_t s) {

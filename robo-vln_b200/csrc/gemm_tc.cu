@@ -95,7 +95,7 @@ RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, cons
   }
 }
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -104,8 +104,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int STAGES = C::STAGES;       // ring capacity; p.nstages (<= STAGES) are in use
   const int nstages = p.nstages;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;   // 0 = leader of the pair
-  const int unit = (CTAS == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int num_units = (CTAS == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // LayerNorm mode (CTAS == 1): the n_tiles CTAs of one 128-row block form a cluster; CTA `ln_rank` owns
+  // column tile ln_rank and all CTAs of a cluster walk the same sequence of row blocks
+  const int ncl = LN ? p.n_tiles : 1;
+  const uint32_t ln_rank = (ncl > 1) ? cluster_ctarank() : 0u;
+  const int unit = (CTAS == 2) ? static_cast<int>(blockIdx.x >> 1)
+                   : (ncl > 1 ? static_cast<int>(blockIdx.x / ncl) * p.n_tiles + static_cast<int>(ln_rank)
+                              : static_cast<int>(blockIdx.x));
+  const int num_units = (CTAS == 2) ? static_cast<int>(gridDim.x >> 1)
+                        : (ncl > 1 ? static_cast<int>(gridDim.x / ncl) * p.n_tiles : static_cast<int>(gridDim.x));
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -119,6 +126,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* rbar_base = bars + 2 * STAGES + 5;   // [8] residual-slice barriers, one per epilogue warp
+  uint64_t* ln_bar = rbar_base + NUM_EPI_WARPS;  // [2] LayerNorm exchange: row sums / centred sums of squares
   // residual-prefetch mode: the pipeline runs with fewer stages and the B buffers of the unused
   // stages hold eight 4 KiB residual slices (32 rows x 128 B, one per epilogue warp)
   uint8_t* res_slices = smem_b + nstages * C::B_STAGE_BYTES;
@@ -139,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], NUM_EPI_WARPS * CTAS);  // one arrive per epilogue warp (of both CTAs)
+      if (LN) mbar_init(&ln_bar[i], static_cast<uint32_t>(ncl) * NUM_EPI_WARPS * 32);   // every epilogue thread of the cluster ([0] in use)
     }
     fence_barrier_init();
   }
@@ -148,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (CTAS == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA
+  if (CTAS == 2 || ncl > 1) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above overlapped the previous kernel's tail; its outputs (our A operand and
@@ -300,6 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nt_ = tile_ % p.n_tiles;
       return nt_ * BN + ch_ * 64 < p.N;
     };
+    int ln_tile_count = 0;
     if (p.res_tma && lane == 0 && chunk_exists(unit, group)) issue_res(unit, group);
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int mu = tile / p.n_tiles;
@@ -318,17 +328,154 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
-
       const h16* res_row = nullptr;
       if (p.res != nullptr && row_ok) {
         const long long rr = (p.res_rows > 0) ? (m % p.res_rows) : m;
         res_row = p.res + rr * p.ldr;
       }
+      // LayerNorm mode: this thread's 128 residual values are fetched while the MMAs of the tile still run
+      uint4 rres[LN ? 16 : 1];
+      const bool have_res = LN && res_row != nullptr;
+      if constexpr (LN) {
+        if (have_res) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              rres[cc * 8 + j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + group * 64 + cc * 128) + j);
+        }
+      }
 
-      if (p.tma_store) {
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+      if constexpr (LN) {
+        // ---------------- LayerNorm folded into the store ----------------
+        // This thread owns output row `row_in_tile`; its warp group covers column chunks group, group + 2 of
+        // this CTA's 256 columns.  Pass 1 adds bias / residual / activation, writes the values back to TMEM
+        // and accumulates (sum, sum of squares) in fp32; the partials of the 2 groups x ncl CTAs are pushed
+        // into every CTA of the cluster (DSMEM) and folded in a fixed order -> mean, rstd (one exchange).
+        // Pass 2 normalises, applies gamma / beta (+ positional table) and stores through TMA.
+        float2* ln_buf = reinterpret_cast<float2*>(smem_a + nstages * A_STAGE_BYTES);   // [2 parity][ncl][2 group][128]
+        const int par = ln_tile_count & 1;
+        auto ln_slot = [&](int src, int grp) { return ln_buf + (((par * ncl + src) * 2 + grp) * BLOCK_M); };
+        // pass 1
+        float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = group * 64 + cc * 128;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr + c0 + half * 32, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (have_res) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 r4 = rres[(cc * 2 + half) * 4 + j];
+                float2 t;
+                t = unpack_h2(r4.x); f[8 * j] += t.x; f[8 * j + 1] += t.y;
+                t = unpack_h2(r4.y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
+                t = unpack_h2(r4.z); f[8 * j + 4] += t.x; f[8 * j + 5] += t.y;
+                t = unpack_h2(r4.w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
+              }
+            }
+            epilogue_math(f, p, n0 + c0 + half * 32, nullptr);   // bias + activation
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sum += f[j];
+              sq = fmaf(f[j], f[j], sq);
+              v[j] = __float_as_uint(f[j]);
+            }
+            tmem_st_32x32(taddr + c0 + half * 32, v);
+          }
+        }
+        tmem_st_wait();
+        // exchange (sum, sumsq)
+        {
+          float2* mine = ln_slot(static_cast<int>(ln_rank), group) + row_in_tile;
+          if (ncl == 1) {
+            *mine = make_float2(sum, sq);
+            mbar_arrive(&ln_bar[0]);
+            mbar_wait(&ln_bar[0], static_cast<uint32_t>(par));
+          } else {
+            const uint32_t a_data = smem_u32(mine), a_bar = smem_u32(&ln_bar[0]);
+            for (int r = 0; r < ncl; ++r) {
+              const uint32_t ra = mapa_u32(a_data, static_cast<uint32_t>(r));
+              asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(ra), "f"(sum), "f"(sq) : "memory");
+              mbar_arrive_release_cluster(mapa_u32(a_bar, static_cast<uint32_t>(r)));
+            }
+            mbar_wait_acquire_cluster(&ln_bar[0], static_cast<uint32_t>(par));
+          }
+        }
+        float tsum = 0.0f, tsq = 0.0f;
+        for (int r = 0; r < ncl; ++r) {
+          const float2 a0 = ln_slot(r, 0)[row_in_tile], a1 = ln_slot(r, 1)[row_in_tile];
+          tsum += a0.x + a1.x;
+          tsq += a0.y + a1.y;
+        }
+        const float inv_n = 1.0f / static_cast<float>(p.N);
+        const float mean = tsum * inv_n;
+        const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.0f) + p.ln_eps);
+        // pass 2
+        const float* pe_row = (p.ln_pe != nullptr && row_ok) ? p.ln_pe + static_cast<long long>(m % p.ln_pe_rows) * p.N : nullptr;
+#pragma unroll 1
+        for (int c0 = group * 64; c0 < BN; c0 += 128) {
+          const int n = n0 + c0;
+          if (store_pending) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_32x32(taddr + c0 + half * 32, v);
+            tmem_ld_wait();
+            float f[32];
+            const int nn = n + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + nn + j));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + nn + j));
+              f[j] = (__uint_as_float(v[j]) - mean) * rstd * g4.x + b4.x;
+              f[j + 1] = (__uint_as_float(v[j + 1]) - mean) * rstd * g4.y + b4.y;
+              f[j + 2] = (__uint_as_float(v[j + 2]) - mean) * rstd * g4.z + b4.z;
+              f[j + 3] = (__uint_as_float(v[j + 3]) - mean) * rstd * g4.w + b4.w;
+              if (pe_row != nullptr) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(pe_row + nn + j));
+                f[j] += p4.x; f[j + 1] += p4.y; f[j + 2] += p4.z; f[j + 3] += p4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_h2(f[8 * j], f[8 * j + 1]);
+              q.y = pack_h2(f[8 * j + 2], f[8 * j + 3]);
+              q.z = pack_h2(f[8 * j + 4], f[8 * j + 5]);
+              q.w = pack_h2(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(my_row + (((half * 4 + j) ^ sw) << 4)) = q;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmC, stage_buf + quad * 4096, n, mt * BLOCK_M + quad * 32, 0, 0);
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
+        ++ln_tile_count;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      if (!LN && p.tma_store) {
 #pragma unroll 1
         for (int ch = group; ch < n_chunks; ch += 2) {
           const int c0 = ch * chunk_cols;
@@ -435,7 +582,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (CTAS == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
           else mbar_arrive(&tempty_bar[acc]);
         }
-      } else {
+      } else if (!LN) {
         // direct global stores (validation path, ROBOVLN_EPILOGUE=direct): 32-column chunks
 #pragma unroll 1
         for (int c0 = group * 32; c0 < BN; c0 += 64) {
@@ -489,7 +636,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (CTAS == 2) cluster_sync_all();   // the peer may still be using this CTA's barriers / TMEM half
+  if (CTAS == 2 || ncl > 1) cluster_sync_all();   // the peer may still be using this CTA's barriers / TMEM half / smem
   if (warp == 1) {
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
@@ -545,12 +692,12 @@ void encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int 
 
 constexpr CUtensorMapDataType kH16Type = RVB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, bool LN = false>
 void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   using C = Cfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CTAS, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -561,9 +708,10 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (CTAS == 2) {
+  const int cluster_x = (CTAS == 2) ? 2 : (LN ? plan.p.n_tiles : 1);
+  if (cluster_x > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = CTAS;
+    attr[na].val.clusterDim.x = cluster_x;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
@@ -575,7 +723,7 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS, LN>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
 }
 
 bool use_pair_mma() {
@@ -675,6 +823,16 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   p.ldc = g.ldc;
   p.out_f32 = g.out_f32;
   p.tma_store = use_direct_epilogue() ? 0 : 1;
+  const bool ln = g.ln_gamma != nullptr;
+  if (ln) {
+    RVB_CHECK(g.plain() && !g.out_f32 && g.ln_beta != nullptr && g.Cout % 256 == 0 && g.Cout <= 768 && p.tma_store,
+              "gemm: LayerNorm epilogue needs a plain GEMM with h16 output and Cout in {256, 512, 768}");
+    RVB_CHECK((reinterpret_cast<uintptr_t>(g.ln_gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.ln_beta) & 15) == 0 &&
+                  (g.ln_pe == nullptr || (reinterpret_cast<uintptr_t>(g.ln_pe) & 15) == 0), "gemm: LayerNorm parameter alignment");
+    p.ln = 1; p.ln_eps = g.ln_eps; p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_pe = g.ln_pe;
+    p.ln_pe_rows = g.ln_pe_rows > 0 ? g.ln_pe_rows : 1;
+    force_bn = 256;   // one full 256-column tile per CTA, 1-CTA form
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -817,12 +975,13 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   }
 
   // residual prefetch through TMA (plain GEMM, 16-bit output, one residual row per output row)
-  p.res_tma = (p.tma_store && p.plain && !g.out_f32 && g.res != nullptr && g.res_rows == 0 && use_res_tma()) ? 1 : 0;
+  p.res_tma = (p.tma_store && p.plain && !g.out_f32 && g.res != nullptr && g.res_rows == 0 && use_res_tma() && !ln) ? 1 : 0;
   {
     const int b_stage = (best_bn / best_ctas) * BLOCK_K * 2;
     const int max_stages = std::min(8, SMEM_STAGE_BUDGET / (A_STAGE_BYTES + b_stage));
     // the residual slices (32 KiB) live in the B buffers of the stages given up
     p.nstages = p.res_tma ? max_stages - (32768 + b_stage - 1) / b_stage : max_stages;
+    if (ln) p.nstages = max_stages - 1;   // the A buffer of the stage given up holds the statistics exchange (12 KB)
     RVB_CHECK(p.nstages >= 2, "gemm: too few pipeline stages");
   }
   if (p.res_tma) {
@@ -837,6 +996,7 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
 
   const long long units = static_cast<long long>((p.m_tiles + best_ctas - 1) / best_ctas) * p.n_tiles;
   plan->grid = static_cast<int>(std::min<long long>(units, sms / best_ctas)) * best_ctas;
+  if (ln) plan->grid = std::min(p.m_tiles, sms / p.n_tiles) * p.n_tiles;   // whole clusters of n_tiles CTAs
   plan->valid = true;
 }
 
@@ -849,6 +1009,11 @@ void gemm_tc_launch(const GemmTcPlan& plan, cudaStream_t stream) {
   if (plan.ctas == 2) {
     RVB_CHECK(plan.BN == 256, "gemm: the CTA-pair kernel is built for BN = 256");
     launch_bn<256, 2>(plan, stream);
+    return;
+  }
+  if (plan.p.ln) {
+    RVB_CHECK(plan.BN == 256 && plan.ctas == 1, "gemm: the LayerNorm epilogue is built for the 1-CTA BN = 256 form");
+    launch_bn<256, 1, true>(plan, stream);
     return;
   }
   switch (plan.BN) {

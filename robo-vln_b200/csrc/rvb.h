@@ -78,6 +78,14 @@ struct ConvGemm {
   void* out = nullptr;           // h16 or f32, [M, ldc]
   int64_t ldc = 0;
   int out_f32 = 0;
+  // LayerNorm folded into the store (plain GEMM, h16 output, Cout in {256, 512, 768}):
+  //   out = LN(act(acc + bias + res)) * ln_gamma + ln_beta (+ ln_pe[m % ln_pe_rows])
+  // The Cout/256 CTAs that hold one 128-row block form a cluster and exchange row statistics over DSMEM.
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 0.0f;
+  const float* ln_pe = nullptr;  // [ln_pe_rows, Cout] fp32 added after the norm, or null
+  int ln_pe_rows = 1;
   // "window" mode (RGB stem): `in` is a zero-padded [NB, H, win_row_pitch/8, 8] image, KW is folded
   // into the K dimension (Cin = 64 = 8 pixels x 8 channels per filter row), W is the OUTPUT width.
   // window == 2 (packed stem): `in` is a zero-padded, ROW-PAIR-INTERLEAVED image [NB, H, win_row_pitch/8, 2, 4]
@@ -118,6 +126,12 @@ struct GemmTcParams {
   int tma_store;     // 1: smem-staged TMA store epilogue, 0: direct global stores (validation)
   int res_tma;       // 1: residual chunks prefetched by TMA into per-warp smem slices
   int window2;       // 1: packed stem (rows advance by one row PAIR per output row: A row coord h0 + tap)
+  int ln;            // 1: LayerNorm epilogue; the n_tiles CTAs of a 128-row block are one cluster
+  float ln_eps;
+  const float* ln_gamma;
+  const float* ln_beta;
+  const float* ln_pe;
+  int ln_pe_rows;
   int nstages;       // pipeline stages in use (fewer when the residual slices take their place)
   int dbg;           // timing experiments only (ROBOVLN_EPI_DEBUG bit mask; results are wrong when set)
 };

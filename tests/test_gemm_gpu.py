@@ -202,6 +202,40 @@ def test_rgb_stem_packed_window_conv(hw, dtype):
     assert rel_err(simt, ref) < OUT_TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,K,N,res_rows,act,pe_rows", [(5120, 768, 768, 0, 0, 0), (1000, 3072, 768, 0, 0, 0),
+                                                        (640, 768, 256, -1, 1, 80), (2048, 256, 256, 1024, 0, 0),
+                                                        (300, 1024, 256, 0, 0, 0), (128 * 60, 256, 512, 0, 1, 0)])
+def test_gemm_layernorm_epilogue(M, K, N, res_rows, act, pe_rows, dtype):
+    """LayerNorm folded into the GEMM store (row statistics exchanged between the N/256 CTAs of a cluster over
+    DSMEM) against torch: LN(act(A W^T + bias + res)) * gamma + beta (+ pe).  res_rows -1 = no residual."""
+    import ctypes
+
+    from tests.gpu_util import H16, OUT_TOL, P, check, lib, rel_err, stream
+
+    a = _mk((M, K), 1.0, 31, dtype)
+    w = _mk((N, K), K ** -0.5, 32, dtype)
+    bias = _mk((N,), 0.3, 33, "f32")
+    gamma = _mk((N,), 0.2, 34, "f32") + 1.0
+    beta = _mk((N,), 0.2, 35, "f32")
+    res = None if res_rows < 0 else _mk((res_rows if res_rows > 0 else M, N), 1.0, 36, dtype)
+    pe = _mk((pe_rows, N), 0.5, 37, "f32") if pe_rows > 0 else None
+    out = torch.zeros((M, N), dtype=H16[dtype], device="cuda")
+    for eps in (1e-12, 1e-5):
+        check(lib(dtype).rvb_gemm_ln(P(a), M, K, P(w), N, P(bias), P(res), max(res_rows, 0), act, P(gamma), P(beta),
+                                     ctypes.c_float(eps), P(pe), pe_rows, P(out), stream()), "rvb_gemm_ln", dtype)
+        torch.cuda.synchronize()
+        y = a.float() @ w.float().t() + bias
+        if res is not None:
+            y = y + res.float()[torch.arange(M, device="cuda") % res.shape[0]]
+        if act == 1:
+            y = torch.relu(y)
+        ref = torch.nn.functional.layer_norm(y, (N,), gamma, beta, eps)
+        if pe is not None:
+            ref = ref + pe[torch.arange(M, device="cuda") % pe_rows]
+        assert rel_err(out, ref) < OUT_TOL[dtype]
+
+
 def test_output_column_slice_and_pitch():
     """GEMM epilogues write straight into column slices of the LSTM input (ldc > N)."""
     from tests.gpu_util import OUT_TOL, conv_gemm, conv_ref, rel_err
