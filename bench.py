@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -259,10 +259,19 @@ def run_b200(args):
     n_gemm = sum(1 for o in ops if o["flops"] > 0)
     all_ms = sum(o["ms"] for o in ops)
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp):          # dram__bytes_read.sum + dram__bytes_write.sum per gemm_tc launch, from the committed ncu pass
+        try:
+            traffic = float(json.load(open(tp))["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM), %d launches/step" % n_gemm,
         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-        "peak_source": "%s, sustained bf16 (kernel timed inside the step)" % peaks["source"], "traffic": None,
+        "peak_source": "%s, sustained bf16 (kernel timed inside the step)" % peaks["source"], "traffic": traffic,
+        "traffic_note": "average DRAM bytes per gemm_tc launch (ncu, profiles/r01_gemm_traffic.json); 'achieved' is FLOP/s "
+                        "(tensor-bound kernel), average FLOPs per launch = flops_per_step / launches",
         "flops_per_step": gemm_fl, "ms_per_step_in_kernel": gemm_ms, "kernel_share_of_step": gemm_ms / all_ms if all_ms else None,
         "step_frac_of_tensor_peak": value / world * GFLOP_PER_OBS * 1e9 / (peaks["bf16_tflops"] * 1e12),
         "single_stream_step_ms": all_ms,
@@ -303,8 +312,8 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)      # ~0.8 s per timed region: enough nvidia-smi clock samples
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="environments per GPU")
     ap.add_argument("--seq-len", type=int, default=80)
