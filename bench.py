@@ -312,6 +312,106 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_cross_modal(args):
+    """BASELINE.json configs[2]: cross-modal attention block only, rollout-shaped batch of 128 environments."""
+    import torch
+
+    import robovln_b200 as R
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, L = 128, args.seq_len
+    policy = R.HcmPolicy().share_frozen_trunks().to(dev).eval()
+    rt = policy._runtime()
+    g = torch.Generator().manual_seed(3)
+    sets = [(torch.randn((B, L, 768), generator=g).to(dev, rt.h16), torch.randn((B, 16, 256), generator=g).to(dev, rt.h16),
+             torch.randn((B, 16, 256), generator=g).to(dev, rt.h16)) for _ in range(3)]
+    for i in range(max(args.warmup, 3)):
+        out = rt.cross_modal(*sets[i % 3])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = rt.cross_modal(*sets[i % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    flops = B * 0.246e9 * 1.0      # SURVEY.md 8(d): 0.288 GFLOP/obs, 0.246 with the query side shared by both modalities
+    peaks = _peaks()
+    print(json.dumps({
+        "metric": "cross_modal_obs_per_sec", "value": B / (ms * 1e-3), "unit": "obs/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": rt.dtype_name, "data": "synthetic",
+        "config": {"workload": "cfg3: Visual_Ling_Attn x2 + token mean-pool only, 128 environments, L=%d, 16 visual cells" % L,
+                   "launches": int(rt.launches())},
+        "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                     "note": "31.5 GFLOP per call in %d launches: launch/latency bound (27 us at peak)" % int(rt.launches())},
+        "outputs_finite": bool(torch.isfinite(out.float()).all().item()),
+    }), flush=True)
+
+
+def run_train(args):
+    """BASELINE.json configs[4]: DAgger inner loop on a 64-step trajectory (N=1, T=64, one shared instruction):
+    hi forward + CE + backward, lo forward + MSE + BCE-with-logits + backward (hierarchical_trainer.py:498-553),
+    frozen encoders on the engine, trainable tail under autograd, dropout as the reference (p=0.25)."""
+    import torch
+    import torch.nn.functional as F
+
+    import robovln_b200 as R
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    T, L = args.batch, args.seq_len
+    policy = R.HcmPolicy().share_frozen_trunks().to(dev)
+    hi, lo = policy.high_level, policy.low_level
+    hi.train()
+    lo.train()
+    g = torch.Generator().manual_seed(5)
+    rgb = torch.randint(0, 256, (T, 256, 256, 3), generator=g).float().to(dev)
+    depth = torch.rand((T, 256, 256, 1), generator=g).to(dev)
+    ids = torch.randint(1000, 30522, (1, L), generator=g).float().to(dev)
+    masks = torch.ones((T, 2), device=dev)
+    masks[0] = 0.0
+    tgt_hi = torch.randint(0, 4, (T,), generator=g).to(dev)
+    tgt_act = torch.rand((T, 2), generator=g).to(dev)
+    tgt_stop = (torch.rand((T, 1), generator=g) > 0.9).float().to(dev)
+    sub = torch.randint(0, 5, (T,), generator=g).to(dev)
+    params = [p for m in (hi, lo) for p in m.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        obs = {"rgb": rgb, "depth": depth, "instruction": ids}
+        logits, _ = hi((obs, torch.zeros((2, 1, 512), device=dev), None, masks))
+        F.cross_entropy(logits, tgt_hi, ignore_index=-1).backward()
+        act, stop, _ = lo((obs, torch.zeros((2, 1, 512), device=dev), None, masks, sub))
+        (F.mse_loss(act, tgt_act) + F.binary_cross_entropy_with_logits(stop, tgt_stop)).backward()
+        opt.step()
+        hi.notify_weights_updated()
+        lo.notify_weights_updated()
+        return logits
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    obs_s = T / (ms * 1e-3)
+    print(json.dumps({
+        "metric": "dagger_step_tokens_and_pixels_per_sec", "value": obs_s * (L + 2 * 256 * 256), "unit": "tokens+pixels/s",
+        "obs_per_sec": obs_s, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "dtype": hi.runtime().dtype_name, "data": "synthetic",
+        "config": {"workload": "cfg5: DAgger inner loop, trajectory T=%d (N=1), shared %d-token instruction, hi fwd+CE+bwd, "
+                               "lo fwd+MSE+BCE+bwd, AdamW step; frozen encoders on the engine, trainable tail in torch autograd" % (T, L)},
+        "outputs_finite": bool(torch.isfinite(out).all().item()),
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,9 +423,15 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=4)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
+    ap.add_argument("--workload", default="policy", choices=["policy", "cross_modal", "train"],
+                    help="policy = BASELINE.json metric (default, the contract line); cross_modal = configs[2]; train = configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cross_modal":
+        run_cross_modal(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_b200(args)
 

@@ -344,6 +344,25 @@ class HcmRuntime:
                                                    _ptr(out["hidden_lo"]), self._stream()), "hcm_forward_policy_host")
         return out
 
+    def cross_modal(self, bert: torch.Tensor, rgb_spatial: torch.Tensor, depth_spatial: torch.Tensor) -> torch.Tensor:
+        """Visual_Ling_Attn for both modalities + token mean-pool on caller tensors (BASELINE.json configs[2]):
+        bert [1|B, L, 768], rgb_spatial / depth_spatial [B, 16, 256] (the rgb_kv / depth_kv outputs, cell-major)
+        -> [B, 512] = (ins_rgb_att | ins_depth_att), transformer.py:262-281 + seq2seq_highlevel_cma.py:200-210."""
+        B, L, rows = rgb_spatial.shape[0], bert.shape[1], bert.shape[0]
+        if rows not in (1, B) or tuple(rgb_spatial.shape[1:]) != (16, 256) or tuple(depth_spatial.shape) != tuple(rgb_spatial.shape):
+            raise ValueError("cross_modal: bert [1|B,L,768], rgb/depth spatial [B,16,256]")
+        hw = (self._shape_key[4], self._shape_key[5]) if self._shape_key else ((256, 256), (256, 256))
+        self.ensure_plan(B, B, L, rows, hw[0], hw[1])
+        b16 = bert.to(self.device, self.h16).contiguous()
+        r16 = rgb_spatial.to(self.device, self.h16).contiguous()
+        d16 = depth_spatial.to(self.device, self.h16).contiguous()
+        out = torch.empty((B, 512), dtype=self.h16, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_run_cross_modal(self.handle, _ptr(b16), _ptr(r16), _ptr(d16), _ptr(out), self._stream()),
+                  "hcm_run_cross_modal")
+        self._keep = (b16, r16, d16)
+        return out
+
     def get_buffer(self, name: str) -> torch.Tensor:
         """Copy of an internal stage buffer (parity tests)."""
         ptr = ctypes.c_void_p()

@@ -147,6 +147,26 @@ def test_lo_without_trunk_reuse_and_policy_entry(models):
     assert hi.runtime().launches() > 100
 
 
+@pytest.mark.parametrize("B,L,shared", [(5, 20, False), (128, 80, False), (6, 33, True)])
+def test_cross_modal_stage_against_oracle(B, L, shared, models):
+    """BASELINE.json configs[2]: the cross-modal block alone (both modalities, LayerNorms folded into the GEMM
+    stores, token mean-pool) on caller tensors against the oracle's Visual_Ling_Attn restatement."""
+    from oracle import hcm_oracle as O
+
+    hi, _, sd_hi, _ = models
+    g = torch.Generator().manual_seed(100 + B)
+    bert = torch.randn((1 if shared else B, L, 768), generator=g)
+    rgb_sp = torch.randn((B, 16, 256), generator=g)
+    dep_sp = torch.randn((B, 16, 256), generator=g)
+    out = hi.runtime().cross_modal(bert, rgb_sp, dep_sp).float().cpu()
+    h = hi.runtime().h16
+    bq, rq, dq = (t.to(h).float() for t in (bert, rgb_sp, dep_sp))          # the stage consumes 16-bit inputs
+    with torch.no_grad():
+        ins = bq.expand(B, L, 768)
+        ref = torch.cat([O.visual_ling_attn(sd_hi, ins, rq).mean(dim=1), O.visual_ling_attn(sd_hi, ins, dq).mean(dim=1)], dim=1)
+    _out(out, ref, "cross_modal pooled", tol=1e-2)
+
+
 def test_graph_replay_matches_eager(models):
     """HcmPolicy.act / act_host replay a captured CUDA graph from the second call with the same input
     pointers on; replays must reproduce the eager (first) call bit for bit, follow NEW input values
