@@ -386,9 +386,7 @@ def run_train(args):
         F.cross_entropy(logits, tgt_hi, ignore_index=-1).backward()
         act, stop, _ = lo((obs, torch.zeros((2, 1, 512), device=dev), None, masks, sub))
         (F.mse_loss(act, tgt_act) + F.binary_cross_entropy_with_logits(stop, tgt_stop)).backward()
-        opt.step()
-        hi.notify_weights_updated()
-        lo.notify_weights_updated()
+        opt.step()       # the engine runs only the FROZEN encoders in train mode: no re-pack of its weights per step
         return logits
 
     for _ in range(max(args.warmup, 3)):

@@ -63,25 +63,27 @@ def visual_ling_attn(m, ins: torch.Tensor, vis: torch.Tensor, p_drop: float, tra
 
 
 def lstm_state_encoder(rnn, x: torch.Tensor, hidden: torch.Tensor, masks: torch.Tensor):
-    """rnn = module.state_encoder.rnn (parameter container); x [T*N, I], hidden [2,N,H], masks [T*N]."""
-    b = rnn.bias_ih_l0 + rnn.bias_hh_l0
+    """rnn = module.state_encoder.rnn (parameter container); x [T*N, I], hidden [2,N,H], masks [T*N].
+    RNNStateEncoder.seq_forward (rnn_state_encoder.py:85-136): the trajectory is cut at t = 0 and at every step
+    where any environment is reset, (h, c) are multiplied by the masks of the segment's first step, and each
+    segment is ONE fused LSTM call (torch's native/cuDNN kernel, differentiable) instead of a Python loop of
+    T cell updates -- 64 steps of forward + backward were 20 of the 42 ms of a DAgger step."""
     N, H = hidden.shape[1], hidden.shape[2]
     T = x.shape[0] // N
-    gx = (F.linear(x, rnn.weight_ih_l0) + b).view(T, N, 4 * H)
     m = masks.view(T, N)
-    flags = [True] + [bool(v) for v in (m[1:] == 0.0).any(dim=1).tolist()] if T > 1 else [True]
-    h, c = hidden[0], hidden[1]
+    starts = [0] + ([t + 1 for t, v in enumerate((m[1:] == 0.0).any(dim=1).tolist()) if v] if T > 1 else [])
+    xs = x.view(T, N, -1)
+    weights = [rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0]
+    h, c = hidden[0:1], hidden[1:2]
     outs = []
-    for t in range(T):
-        if flags[t]:
-            h = h * m[t].view(N, 1)
-            c = c * m[t].view(N, 1)
-        g = gx[t] + F.linear(h, rnn.weight_hh_l0)
-        i, f, gg, o = g.chunk(4, dim=1)
-        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
-        h = torch.sigmoid(o) * torch.tanh(c)
-        outs.append(h)
-    return torch.stack(outs, 0).view(T * N, H), torch.stack([h, c], 0)
+    for i, t0 in enumerate(starts):
+        t1 = starts[i + 1] if i + 1 < len(starts) else T
+        mk = m[t0].view(1, N, 1)
+        # train flag: cuDNN keeps its reserve space for backward only in "training" mode (no dropout here)
+        out, h, c = torch._VF.lstm(xs[t0:t1], (h * mk, c * mk), weights, True, 1, 0.0, torch.is_grad_enabled(), False, False)
+        outs.append(out)
+    y = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+    return y.reshape(T * N, H), torch.cat([h, c], 0)
 
 
 def hi_tail(mod, rgb_feat, depth_feat, bert, hidden, masks, p_drop: float = 0.25):
