@@ -204,7 +204,7 @@ def visual_ling_attn(sd: SD, ins: torch.Tensor, vis: torch.Tensor, prefix: str =
     lnw, lnb = sd[prefix + "layer_norm.weight"], sd[prefix + "layer_norm.bias"]
     V = F.layer_norm(F.relu(F.linear(vis, sd[prefix + "vis_fc.weight"], sd[prefix + "vis_fc.bias"])), (d,), lnw, lnb, 1e-5)
     Q = F.layer_norm(F.relu(F.linear(ins, sd[prefix + "ins_fc.weight"], sd[prefix + "ins_fc.bias"])), (d,), lnw, lnb, 1e-5)
-    Q = Q + sinusoid_table(L, d).unsqueeze(0)
+    Q = Q + sinusoid_table(L, d).unsqueeze(0).to(Q.device)   # built on the CPU as the reference does (transformer.py:271-273)
     a = prefix + "layers.0.enc_att.attention."
     dk = d // h
     nk = V.shape[1]

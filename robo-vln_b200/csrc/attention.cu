@@ -56,14 +56,26 @@ __global__ void __launch_bounds__(256) bert_attn_kernel(const h16* __restrict__ 
 
   // stage Q, K, V head slices (zero-padded to LP rows)
   const h16* src = qkv + static_cast<long long>(row) * L * H3 + head * HD;
-  for (int i = threadIdx.x; i < LP * 8 * 3; i += blockDim.x) {
-    const int which = i / (LP * 8);
-    const int rem = i - which * LP * 8;
-    const int l = rem >> 3, v = rem & 7;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (l < L) val = *reinterpret_cast<const uint4*>(src + static_cast<long long>(l) * H3 + which * heads * HD + v * 8);
-    h16* dst = (which == 0 ? sQ : (which == 1 ? sK : sV)) + l * PITCH + v * 8;
-    *reinterpret_cast<uint4*>(dst) = val;
+  // four 16-byte loads in flight per thread (the staging is the latency-bound part of this kernel)
+  for (int i0 = threadIdx.x; i0 < LP * 8 * 3; i0 += 4 * blockDim.x) {
+    uint4 val[4];
+    h16* dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      val[u] = make_uint4(0, 0, 0, 0);
+      dst[u] = nullptr;
+      if (i < LP * 8 * 3) {
+        const int which = i / (LP * 8);
+        const int rem = i - which * LP * 8;
+        const int l = rem >> 3, v = rem & 7;
+        if (l < L) val[u] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(l) * H3 + which * heads * HD + v * 8));
+        dst[u] = (which == 0 ? sQ : (which == 1 ? sK : sV)) + l * PITCH + v * 8;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u] != nullptr) *reinterpret_cast<uint4*>(dst[u]) = val[u];
   }
   __syncthreads();
 
