@@ -157,6 +157,12 @@ int rvb_conv_gemm(const void* in_bf16, int NB, int H, int W, int Cin, int64_t in
 int rvb_gemm_ln(const void* a_h16, int64_t M, int K, const void* w_h16, int N, const float* bias, const void* res_h16,
                 int res_rows, int act, const float* gamma, const float* beta, float eps, const float* pe, int pe_rows,
                 void* out_h16, void* stream);
+/* Convolution (or 1x1 GEMM) with GroupNorm folded into the store, for output maps of 16 or 64 pixels per sample:
+ * out = relu?(GroupNorm_groups(conv(in, w)) * gamma + beta + res)  (habitat_baselines/rl/ddppo/policy/resnet.py:65-77,
+ * layers 3-4 of the depth trunk).  Cout/groups in {8,16,32,64}. */
+int rvb_conv_gemm_gn(const void* in_h16, int NB, int H, int W, int Cin, const void* w_h16, int Cout, int KH, int stride,
+                     int pad, const float* gamma, const float* beta, int groups, int relu, const void* res_h16,
+                     void* out_h16, void* stream);
 int rvb_rgb_pad_convert(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream);
 /* Packed stem (window == 2, what the engine runs): zero-padded ROW-PAIR-INTERLEAVED image [NB, (H+6)/2, Wp, 2, 4]
  * (H even); the conv takes H = (H+6)/2 row pairs, W = OUTPUT width, in_pitch 8, KH = 4 (row pairs), KW 1, stride 2,

@@ -51,6 +51,8 @@ SYMBOLS = {
                               c_int, c_int64, c_void_p]),
     "rvb_gemm_ln": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                             c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    "rvb_conv_gemm_gn": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rvb_rgb_pad_convert": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rvb_rgb_pad_convert4": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rvb_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,

@@ -265,6 +265,22 @@ int rvb_gemm_ln(const void* a_h16, int64_t M, int K, const void* w_h16, int N, c
   });
 }
 
+int rvb_conv_gemm_gn(const void* in_h16, int NB, int H, int W, int Cin, const void* w_h16, int Cout, int KH, int stride,
+                     int pad, const float* gamma, const float* beta, int groups, int relu, const void* res_h16,
+                     void* out_h16, void* stream) {
+  return guarded([&] {
+    ConvGemm g;
+    g.in = B16(in_h16); g.NB = NB; g.H = H; g.W = W; g.Cin = Cin; g.in_pitch = Cin;
+    g.w = B16(w_h16); g.Cout = Cout; g.KH = g.KW = KH; g.stride = stride; g.pad = pad;
+    g.res = B16(res_h16); g.ldr = Cout; g.res_rows = 0; g.act = relu ? ACT_RELU : ACT_NONE;
+    g.out = out_h16; g.ldc = Cout; g.out_f32 = 0;
+    g.gn_gamma = gamma; g.gn_beta = beta; g.gn_groups = groups; g.gn_hw = g.Ho() * g.Wo();
+    GemmTcPlan plan;
+    gemm_tc_make_plan(g, &plan, 0);
+    gemm_tc_launch(plan, S(stream));
+  });
+}
+
 int rvb_groupnorm(const void* x_bf16, float* stats, const float* gamma, const float* beta, int NB, int HW, int C, int G,
                   int relu, const void* res_bf16, void* out_bf16, int64_t out_pitch, void* stream) {
   return guarded([&] {

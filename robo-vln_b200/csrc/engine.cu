@@ -249,6 +249,8 @@ void Engine::plan_depth_trunk(const std::string& ns, Stage& st) {
   const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1;
   constexpr int G = 16;
   gn_stats_used_ = 0;
+  static const char* gnenv = std::getenv("ROBOVLN_GN_EPILOGUE");
+  const bool gn_epilogue = !(gnenv != nullptr && std::strcmp(gnenv, "0") == 0);
   h16* raw0 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
   h16* a0 = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H1 * W1 * 32 * 2));
   h16* x = reinterpret_cast<h16*>(alloc(static_cast<size_t>(B) * H2 * W2 * 32 * 2));
@@ -299,21 +301,42 @@ void Engine::plan_depth_trunk(const std::string& ns, Stage& st) {
         sds = new_stats(G);
       }
       if (dry_) { x = out; h = ho; w = wo; cin = cout; continue; }
-      conv_gn(x, h, w, cin, p + ".c1.w", mid, 1, 1, r1, s1);
-      {
+      // Feature maps of <= 64 pixels (layers 3-4): every 128-row GEMM tile holds whole samples, so GroupNorm
+      // (+ ReLU, + plain residual) is folded into the conv's store (gemm_tc.cu, GN epilogue) -- no raw tensor,
+      // no GroupNorm launch.  The first block of a stage keeps the kernel for gn3 (two normalised branches).
+      auto conv_gn_fused = [&](const h16* in, int ih, int iw, int ci, const std::string& wname, int co, int k, int stride_,
+                               const std::string& gname, const h16* res, h16* dst) {
+        ConvGemm g;
+        g.in = in; g.NB = B; g.H = ih; g.W = iw; g.Cin = ci; g.in_pitch = ci;
+        g.w = Wb(wname, {co, k * k * ci}); g.Cout = co; g.KH = g.KW = k; g.stride = stride_; g.pad = (k == 3) ? 1 : 0;
+        g.act = ACT_RELU; g.out = dst; g.ldc = co;
+        g.res = res; g.ldr = co; g.res_rows = 0;
+        g.gn_gamma = Wf(gname + ".w", {co}); g.gn_beta = Wf(gname + ".b", {co}); g.gn_groups = G; g.gn_hw = g.Ho() * g.Wo();
+        add_gemm(st, g);
+      };
+      const bool fuse12_in = gn_epilogue && (h * w == 64 || h * w == 16);       // conv1 output lives at the input resolution
+      const bool fuse_out = gn_epilogue && (ho * wo == 64 || ho * wo == 16);     // conv2 / conv3 outputs
+      if (fuse12_in) {
+        conv_gn_fused(x, h, w, cin, p + ".c1.w", mid, 1, 1, p + ".gn1", nullptr, t1);
+      } else {
+        conv_gn(x, h, w, cin, p + ".c1.w", mid, 1, 1, r1, s1);
         GnApply a{r1, s1, Wf(p + ".gn1.w", {mid}), Wf(p + ".gn1.b", {mid}), B, h * w, mid, G, 1, 0,
                   nullptr, nullptr, nullptr, nullptr, t1, mid};
         st.push_back([a](cudaStream_t s) { gn_fused(a, s); return 1; });
       }
-      conv_gn(t1, h, w, mid, p + ".c2.w", mid, 3, stride, r2, s2);
-      {
+      if (fuse_out) {
+        conv_gn_fused(t1, h, w, mid, p + ".c2.w", mid, 3, stride, p + ".gn2", nullptr, t2);
+      } else {
+        conv_gn(t1, h, w, mid, p + ".c2.w", mid, 3, stride, r2, s2);
         GnApply a{r2, s2, Wf(p + ".gn2.w", {mid}), Wf(p + ".gn2.b", {mid}), B, ho * wo, mid, G, 1, 0,
                   nullptr, nullptr, nullptr, nullptr, t2, mid};
         st.push_back([a](cudaStream_t s) { gn_fused(a, s); return 1; });
       }
-      conv_gn(t2, ho, wo, mid, p + ".c3.w", cout, 1, 1, r3, s3);
-      if (b == 0) conv_gn(x, h, w, cin, p + ".ds.w", cout, 1, stride, rds, sds);
-      {
+      if (fuse_out && b != 0) {
+        conv_gn_fused(t2, ho, wo, mid, p + ".c3.w", cout, 1, 1, p + ".gn3", x, out);
+      } else {
+        conv_gn(t2, ho, wo, mid, p + ".c3.w", cout, 1, 1, r3, s3);
+        if (b == 0) conv_gn(x, h, w, cin, p + ".ds.w", cout, 1, stride, rds, sds);
         GnApply a{r3, s3, Wf(p + ".gn3.w", {cout}), Wf(p + ".gn3.b", {cout}), B, ho * wo, cout, G, 1,
                   b == 0 ? 2 : 1, b == 0 ? rds : x, sds,
                   b == 0 ? Wf(p + ".dsgn.w", {cout}) : nullptr, b == 0 ? Wf(p + ".dsgn.b", {cout}) : nullptr,

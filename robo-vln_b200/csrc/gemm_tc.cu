@@ -95,11 +95,13 @@ RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, cons
   }
 }
 
-template <int BN, int CTAS, bool LN>
+template <int BN, int CTAS, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const GemmTcParams p) {
+  constexpr bool LN = (EPI == 1);   // LayerNorm folded into the store
+  constexpr bool GN = (EPI == 2);   // GroupNorm folded into the store
   using C = Cfg<BN, CTAS>;
   constexpr int STAGES = C::STAGES;       // ring capacity; p.nstages (<= STAGES) are in use
   const int nstages = p.nstages;
@@ -115,6 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         : (ncl > 1 ? static_cast<int>(gridDim.x / ncl) * p.n_tiles : static_cast<int>(gridDim.x));
 
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float gn_x[GN ? 2 * 8 * 16 : 1];   // GroupNorm: (sum, sumsq) x 8 groups per epilogue warp, double-buffered
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
@@ -310,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       return nt_ * BN + ch_ * 64 < p.N;
     };
     int ln_tile_count = 0;
+    int gn_par = 0;
     if (p.res_tma && lane == 0 && chunk_exists(unit, group)) issue_res(unit, group);
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int mu = tile / p.n_tiles;
@@ -350,6 +354,146 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
+      if constexpr (GN) {
+        // ---------------- GroupNorm folded into the store ----------------
+        // The 128 rows of the tile are 128 / gn_hw whole samples and a 64-column chunk holds 64 / cpg whole
+        // groups, so the statistics of every (sample, group) of a chunk live in ONE epilogue group: per-thread
+        // sums over the group's columns, a segmented warp shuffle over the sample's rows and, for 64-pixel
+        // samples, one exchange between the two warps that share the sample.  Fixed order: bit-reproducible.
+        const int cpg = p.gn_cpg, hw = p.gn_hw;
+        const int ngrp = 64 / cpg;                       // groups per chunk: 8, 4, 2 or 1
+        const float inv_cnt = 1.0f / static_cast<float>(hw * cpg);
+        const int pair_bar = 3 + group * 2 + (quad >> 1);
+#pragma unroll 1
+        for (int ch = group; ch < n_chunks; ch += 2) {
+          const int c0 = ch * 64;
+          const int n = n0 + c0;
+          if (n >= p.N) break;
+          uint4 rres[8];
+          if (res_row != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rres[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n) + j);
+          }
+          uint32_t v[64];
+          __syncwarp();
+          {
+            uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+            tmem_ld_32x32(taddr + c0, v0);
+            tmem_ld_32x32(taddr + c0 + 32, v1);
+          }
+          tmem_ld_wait();
+          // per-thread sums per group (ngrp <= 8), then over the sample's rows
+          float gs[8], gq[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const float x = __uint_as_float(v[j]);
+            const int g = (cpg == 8) ? (j >> 3) : (cpg == 16) ? (j >> 4) : (cpg == 32) ? (j >> 5) : 0;
+#pragma unroll
+            for (int gg = 0; gg < 8; ++gg)
+              if (gg == g) { gs[gg] += x; gq[gg] = fmaf(x, x, gq[gg]); }
+          }
+          const int seg = hw < 32 ? hw : 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g < ngrp) {
+              for (int o = 1; o < seg; o <<= 1) {
+                gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
+                gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+              }
+            }
+          }
+          if (hw == 64) {   // the sample spans this warp and its neighbour (quad ^ 1) of the same epilogue group
+            float* mine = gn_x + ((gn_par * 8 + (warp - 2)) * 16);
+            float* other = gn_x + ((gn_par * 8 + ((warp - 2) ^ 1)) * 16);
+            if (lane == 0) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) { mine[2 * g] = gs[g]; mine[2 * g + 1] = gq[g]; }
+            }
+            named_bar_sync(pair_bar, 64);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              // fold in quad order so that both warps compute bit-identical totals
+              const float a = (quad & 1) ? other[2 * g] : gs[g], b = (quad & 1) ? gs[g] : other[2 * g];
+              const float c = (quad & 1) ? other[2 * g + 1] : gq[g], d = (quad & 1) ? gq[g] : other[2 * g + 1];
+              gs[g] = a + b;
+              gq[g] = c + d;
+            }
+            gn_par ^= 1;
+          }
+          float gmean[8], grstd[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            gmean[g] = gs[g] * inv_cnt;
+            grstd[g] = rsqrtf(fmaxf(gq[g] * inv_cnt - gmean[g] * gmean[g], 0.0f) + 1e-5f);
+          }
+          if (store_pending) {
+            if (p.plain) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            } else {
+              if (leader) tma_store_wait_read<0>();
+              named_bar_sync(1 + group, 128);
+            }
+          }
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; e += 4) {
+              const int j = j8 * 8 + e;
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + n + j));
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + n + j));
+              const float gam[4] = {g4.x, g4.y, g4.z, g4.w}, bet[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int jj = j + t;
+                const int g = (cpg == 8) ? (jj >> 3) : (cpg == 16) ? (jj >> 4) : (cpg == 32) ? (jj >> 5) : 0;
+                float mean = gmean[0], rstd = grstd[0];
+#pragma unroll
+                for (int gg = 1; gg < 8; ++gg)
+                  if (gg == g) { mean = gmean[gg]; rstd = grstd[gg]; }
+                f[e + t] = (__uint_as_float(v[jj]) - mean) * rstd * gam[t] + bet[t];
+              }
+            }
+            if (res_row != nullptr) {
+              const uint4 r4 = rres[j8];
+              float2 t;
+              t = unpack_h2(r4.x); f[0] += t.x; f[1] += t.y;
+              t = unpack_h2(r4.y); f[2] += t.x; f[3] += t.y;
+              t = unpack_h2(r4.z); f[4] += t.x; f[5] += t.y;
+              t = unpack_h2(r4.w); f[6] += t.x; f[7] += t.y;
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+            }
+            uint4 q;
+            q.x = pack_h2(f[0], f[1]); q.y = pack_h2(f[2], f[3]); q.z = pack_h2(f[4], f[5]); q.w = pack_h2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(my_row + ((j8 ^ sw) << 4)) = q;
+          }
+          fence_proxy_async();
+          if (p.plain) {
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmC, stage_buf + quad * 4096, n, mt * BLOCK_M + quad * 32, 0, 0);
+              tma_store_commit();
+            }
+          } else {
+            named_bar_sync(1 + group, 128);
+            if (leader) {
+              tma_store_4d(&tmC, stage_buf, n, 0, h0, img);
+              tma_store_commit();
+            }
+          }
+          store_pending = true;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
       if constexpr (LN) {
         // ---------------- LayerNorm folded into the store ----------------
         // This thread owns output row `row_in_tile`; its warp group covers column chunks group, group + 2 of
@@ -475,7 +619,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      if (!LN && p.tma_store) {
+      if (!LN && !GN && p.tma_store) {
 #pragma unroll 1
         for (int ch = group; ch < n_chunks; ch += 2) {
           const int c0 = ch * chunk_cols;
@@ -582,7 +726,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (CTAS == 2) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
           else mbar_arrive(&tempty_bar[acc]);
         }
-      } else if (!LN) {
+      } else if (!LN && !GN) {
         // direct global stores (validation path, ROBOVLN_EPILOGUE=direct): 32-column chunks
 #pragma unroll 1
         for (int c0 = group * 32; c0 < BN; c0 += 64) {
@@ -692,12 +836,12 @@ void encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int 
 
 constexpr CUtensorMapDataType kH16Type = RVB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
-template <int BN, int CTAS, bool LN = false>
+template <int BN, int CTAS, int EPI = 0>
 void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   using C = Cfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CTAS, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -708,7 +852,7 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  const int cluster_x = (CTAS == 2) ? 2 : (LN ? plan.p.n_tiles : 1);
+  const int cluster_x = (CTAS == 2) ? 2 : (EPI == 1 ? plan.p.n_tiles : 1);
   if (cluster_x > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = cluster_x;
@@ -723,7 +867,7 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS, LN>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS, EPI>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
 }
 
 bool use_pair_mma() {
@@ -823,6 +967,16 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   p.ldc = g.ldc;
   p.out_f32 = g.out_f32;
   p.tma_store = use_direct_epilogue() ? 0 : 1;
+  const bool gn = g.gn_gamma != nullptr;
+  if (gn) {
+    RVB_CHECK(!g.out_f32 && g.gn_beta != nullptr && g.gn_groups > 0 && g.Cout % g.gn_groups == 0 && p.tma_store && g.res_rows == 0 &&
+                  g.bias == nullptr && (g.act == ACT_NONE || g.act == ACT_RELU), "gemm: GroupNorm epilogue: unsupported combination");
+    const int cpg = g.Cout / g.gn_groups;
+    RVB_CHECK((cpg == 8 || cpg == 16 || cpg == 32 || cpg == 64) && (g.gn_hw == 16 || g.gn_hw == 64) && g.gn_hw == Ho * Wo,
+              "gemm: GroupNorm epilogue needs 8..64 channels per group and 16- or 64-pixel samples");
+    p.gn_hw = g.gn_hw; p.gn_cpg = cpg; p.gn_gamma = g.gn_gamma; p.gn_beta = g.gn_beta;
+    if (force_bn == 0) force_bn = (g.Cout >= 128 && g.Cout % 128 == 0) ? 128 : 64;
+  }
   const bool ln = g.ln_gamma != nullptr;
   if (ln) {
     RVB_CHECK(g.plain() && !g.out_f32 && g.ln_beta != nullptr && g.Cout % 256 == 0 && g.Cout <= 768 && p.tma_store,
@@ -975,7 +1129,7 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   }
 
   // residual prefetch through TMA (plain GEMM, 16-bit output, one residual row per output row)
-  p.res_tma = (p.tma_store && p.plain && !g.out_f32 && g.res != nullptr && g.res_rows == 0 && use_res_tma() && !ln) ? 1 : 0;
+  p.res_tma = (p.tma_store && p.plain && !g.out_f32 && g.res != nullptr && g.res_rows == 0 && use_res_tma() && !ln && !gn) ? 1 : 0;
   {
     const int b_stage = (best_bn / best_ctas) * BLOCK_K * 2;
     const int max_stages = std::min(8, SMEM_STAGE_BUDGET / (A_STAGE_BYTES + b_stage));
@@ -1013,7 +1167,13 @@ void gemm_tc_launch(const GemmTcPlan& plan, cudaStream_t stream) {
   }
   if (plan.p.ln) {
     RVB_CHECK(plan.BN == 256 && plan.ctas == 1, "gemm: the LayerNorm epilogue is built for the 1-CTA BN = 256 form");
-    launch_bn<256, 1, true>(plan, stream);
+    launch_bn<256, 1, 1>(plan, stream);
+    return;
+  }
+  if (plan.p.gn_hw != 0) {
+    RVB_CHECK(plan.ctas == 1 && (plan.BN == 64 || plan.BN == 128), "gemm: the GroupNorm epilogue is built for BN = 64 / 128");
+    if (plan.BN == 64) launch_bn<64, 1, 2>(plan, stream);
+    else launch_bn<128, 1, 2>(plan, stream);
     return;
   }
   switch (plan.BN) {

@@ -86,6 +86,13 @@ struct ConvGemm {
   float ln_eps = 0.0f;
   const float* ln_pe = nullptr;  // [ln_pe_rows, Cout] fp32 added after the norm, or null
   int ln_pe_rows = 1;
+  // GroupNorm folded into the store, for feature maps small enough that every 128-row M tile holds WHOLE
+  // samples (gn_hw = H*W of the output in {16, 64}) and every N tile whole groups:
+  //   out = relu?( GN_groups(acc) * gn_gamma + gn_beta + res )     (res: plain h16 residual, optional)
+  const float* gn_gamma = nullptr;
+  const float* gn_beta = nullptr;
+  int gn_groups = 0;
+  int gn_hw = 0;
   // "window" mode (RGB stem): `in` is a zero-padded [NB, H, win_row_pitch/8, 8] image, KW is folded
   // into the K dimension (Cin = 64 = 8 pixels x 8 channels per filter row), W is the OUTPUT width.
   // window == 2 (packed stem): `in` is a zero-padded, ROW-PAIR-INTERLEAVED image [NB, H, win_row_pitch/8, 2, 4]
@@ -126,6 +133,9 @@ struct GemmTcParams {
   int tma_store;     // 1: smem-staged TMA store epilogue, 0: direct global stores (validation)
   int res_tma;       // 1: residual chunks prefetched by TMA into per-warp smem slices
   int window2;       // 1: packed stem (rows advance by one row PAIR per output row: A row coord h0 + tap)
+  int gn_hw, gn_cpg; // GroupNorm epilogue: pixels per sample (16 / 64), channels per group (8 .. 64); 0 = off
+  const float* gn_gamma;
+  const float* gn_beta;
   int ln;            // 1: LayerNorm epilogue; the n_tiles CTAs of a 128-row block are one cluster
   float ln_eps;
   const float* ln_gamma;

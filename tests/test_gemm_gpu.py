@@ -236,6 +236,44 @@ def test_gemm_layernorm_epilogue(M, K, N, res_rows, act, pe_rows, dtype):
         assert rel_err(out, ref) < OUT_TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("NB,HW,Cin,Cout,K,stride,res,relu", [
+    (6, 8, 256, 128, 1, 1, False, True),      # layer3 conv1: 64-pixel samples, 8 channels per group, BN = 128
+    (6, 8, 128, 128, 3, 1, False, True),      # layer3 conv2 (3x3)
+    (5, 8, 128, 512, 1, 1, True, True),       # layer3 conv3 + residual: 32 channels per group
+    (4, 16, 128, 128, 3, 2, False, True),     # layer3 block 0 conv2, stride 2: 16x16 -> 8x8
+    (19, 4, 512, 256, 1, 1, False, True),     # layer4 conv1: 16-pixel samples, 16 channels per group, ragged last tile
+    (16, 4, 256, 256, 3, 1, False, False),    # layer4 conv2 (3x3), no ReLU
+    (9, 4, 256, 1024, 1, 1, True, True),      # layer4 conv3 + residual: 64 channels per group
+])
+def test_conv_groupnorm_epilogue(NB, HW, Cin, Cout, K, stride, res, relu, dtype):
+    """GroupNorm(16) folded into the conv GEMM's store (depth trunk layers 3-4) against torch."""
+    from tests.gpu_util import H16, OUT_TOL, P, check, lib, rel_err, stream
+
+    x = _mk((NB, HW, HW, Cin), 1.0, 41, dtype)
+    w = _mk((Cout, K * K * Cin), (K * K * Cin) ** -0.5, 42, dtype)
+    gamma = _mk((Cout,), 0.3, 43, "f32") + 1.0
+    beta = _mk((Cout,), 0.3, 44, "f32")
+    Ho = (HW + 2 * (K // 2) - K) // stride + 1
+    r = _mk((NB * Ho * Ho, Cout), 1.0, 45, dtype) if res else None
+    out = torch.zeros((NB * Ho * Ho, Cout), dtype=H16[dtype], device="cuda")
+    outs = []
+    for _ in range(2):
+        check(lib(dtype).rvb_conv_gemm_gn(P(x), NB, HW, HW, Cin, P(w), Cout, K, stride, K // 2, P(gamma), P(beta), 16, int(relu),
+                                          P(r), P(out), stream()), "rvb_conv_gemm_gn", dtype)
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1])          # fixed-order statistics: bit-reproducible
+    w4 = w.float().view(Cout, K, K, Cin).permute(0, 3, 1, 2).contiguous()
+    y = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w4, None, stride=stride, padding=K // 2)
+    y = torch.nn.functional.group_norm(y, 16, gamma, beta, 1e-5).permute(0, 2, 3, 1).reshape(-1, Cout)
+    if r is not None:
+        y = y + r.float()
+    if relu:
+        y = torch.relu(y)
+    assert rel_err(out, y) < OUT_TOL[dtype]
+
+
 def test_output_column_slice_and_pitch():
     """GEMM epilogues write straight into column slices of the LSTM input (ldc > N)."""
     from tests.gpu_util import OUT_TOL, conv_gemm, conv_ref, rel_err
