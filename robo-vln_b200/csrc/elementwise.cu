@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(256) bert_embed_ln_kernel(const long long* __r
 // LayerNorm over fp32 rows (the producing GEMM already added bias and residual), optional
 // additive table (sinusoid PE, transformer.py:271-274) AFTER the norm; h16 out.
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int M,
+__global__ void __launch_bounds__(128) layernorm_rows_kernel(const float* __restrict__ x, int M,
                                                              const float* __restrict__ g,
                                                              const float* __restrict__ b, float eps,
                                                              const float* __restrict__ pe, int pe_rows,
@@ -892,9 +892,11 @@ void bert_embed_ln(const int64_t* ids_i64, const float* ids_f32, int id_rows, in
 
 void layernorm_rows(const float* x, int M, int D, const float* g, const float* b, float eps, const float* pe,
                     int pe_rows, h16* out, cudaStream_t s) {
-  const int blocks = static_cast<int>((static_cast<long long>(M) * 32 + 255) / 256);
-  if (D == 768) launch_k(layernorm_rows_kernel<6>, dim3(blocks), dim3(256), 0, s, x, M, g, b, eps, pe, pe_rows, out);
-  else if (D == 256) launch_k(layernorm_rows_kernel<2>, dim3(blocks), dim3(256), 0, s, x, M, g, b, eps, pe, pe_rows, out);
+  // 128-thread CTAs without shared memory: 8 K registers each, so they fit NEXT TO a resident GEMM CTA
+  // (320 threads x 160 registers, ~226 KB of shared memory) instead of waiting for a whole free SM
+  const int blocks = static_cast<int>((static_cast<long long>(M) * 32 + 127) / 128);
+  if (D == 768) launch_k(layernorm_rows_kernel<6>, dim3(blocks), dim3(128), 0, s, x, M, g, b, eps, pe, pe_rows, out);
+  else if (D == 256) launch_k(layernorm_rows_kernel<2>, dim3(blocks), dim3(128), 0, s, x, M, g, b, eps, pe, pe_rows, out);
   else RVB_CHECK(false, "layernorm: D must be 256 or 768");
   RVB_CUDA(cudaGetLastError());
 }
