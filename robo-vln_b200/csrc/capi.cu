@@ -259,6 +259,23 @@ int rvb_gemm_ln(const void* a_h16, int64_t M, int K, const void* w_h16, int N, c
     g.bias = bias; g.res = B16(res_h16); g.ldr = N; g.res_rows = res_rows; g.act = act;
     g.out = out_h16; g.ldc = N; g.out_f32 = 0;
     g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.ln_pe = pe; g.ln_pe_rows = pe_rows > 0 ? pe_rows : 1;
+    // ROBOVLN_LN_XCHG=global: exchange the row statistics of N > 256 through global memory instead of a cluster
+    static const char* xe = std::getenv("ROBOVLN_LN_XCHG");
+    if (xe != nullptr && std::strcmp(xe, "global") == 0 && N > 256) {
+      static uint8_t* scratch = nullptr;
+      const size_t m_tiles = static_cast<size_t>((M + 127) / 128);
+      const size_t ws_bytes = m_tiles * 3 * 256 * 8, cap = size_t(64) << 20;
+      RVB_CHECK(ws_bytes + m_tiles * 16 + 256 <= cap, "rvb_gemm_ln: M too large for the test scratch");
+      if (scratch == nullptr) {
+        RVB_CUDA(cudaMalloc(&scratch, cap));
+        RVB_CUDA(cudaMemset(scratch, 0, cap));
+      }
+      g.ln_ws = scratch + (size_t(1) << 20);        // counters live in the first MiB
+      g.ln_cnt = reinterpret_cast<int*>(scratch);
+      // the engine gives every plan its own (monotonic, never reset) counters; this shared test scratch serves
+      // calls with different N / M, so it is re-zeroed in stream order before every launch
+      RVB_CUDA(cudaMemsetAsync(scratch, 0, m_tiles * 16, S(stream)));
+    }
     GemmTcPlan plan;
     gemm_tc_make_plan(g, &plan, 0);
     gemm_tc_launch(plan, S(stream));

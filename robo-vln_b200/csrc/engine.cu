@@ -122,6 +122,7 @@ static int ln_fused_level() {
 }
 static bool use_ln_fused() { return ln_fused_level() >= 1; }
 static bool use_ln_fused_bert() { return ln_fused_level() >= 2; }
+static bool use_ln_global_exchange() { return ln_fused_level() >= 3; }   // BERT: statistics through global memory, no clusters
 
 static ConvGemm with_ln(ConvGemm g, const float* gamma, const float* beta, float eps, const float* pe = nullptr, int pe_rows = 1) {
   g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.ln_pe = pe; g.ln_pe_rows = pe_rows;
@@ -376,6 +377,24 @@ void Engine::plan_bert(Stage& st) {
   float* y = reinterpret_cast<float*>(alloc(M * 768 * 4));
   h16* hbuf = reinterpret_cast<h16*>(alloc(M * 3072 * 2));
   bert_out_ = xa;
+  // LayerNorm-in-GEMM with the global-memory exchange: per GEMM plan, partial (sum, sumsq) of every row from each
+  // of the 3 column tiles x 2 warp groups, and one monotonic counter per (row block, lane quadrant)
+  const int64_t m_tiles = (M + 127) / 128;
+  const size_t ws_bytes = static_cast<size_t>(m_tiles) * 3 * 256 * 8, cnt_bytes = static_cast<size_t>(m_tiles) * 4 * 4;
+  uint8_t* ln_scratch = nullptr;
+  if (use_ln_global_exchange()) {
+    ln_scratch = reinterpret_cast<uint8_t*>(alloc(24 * (ws_bytes + cnt_bytes + 1024)));
+    if (!dry_) RVB_CUDA(cudaMemset(ln_scratch, 0, 24 * (ws_bytes + cnt_bytes + 1024)));
+  }
+  int ln_plan_idx = 0;
+  auto with_xchg = [&](ConvGemm g) {
+    if (ln_scratch != nullptr) {
+      uint8_t* base = ln_scratch + static_cast<size_t>(ln_plan_idx++) * (ws_bytes + cnt_bytes + 1024);
+      g.ln_ws = base;
+      g.ln_cnt = reinterpret_cast<int*>(base + ((ws_bytes + 255) & ~size_t(255)));
+    }
+    return g;
+  };
   if (dry_) return;
   {
     const float* word = Wf("hi.bert.word", {});
@@ -397,9 +416,9 @@ void Engine::plan_bert(Stage& st) {
     st.push_back([qkv, ctx, R, L](cudaStream_t s) { bert_self_attention(qkv, ctx, R, L, 12, s); return 1; });
     if (use_ln_fused_bert()) {
       // attention output projection + residual + LayerNorm in one launch (3-CTA clusters share the row statistics)
-      add_gemm(st, with_ln(linear(ctx, M, 768, 768, Wb(p + ".ao.w", {768, 768}), 768, Wf(p + ".ao.b", {768}), ACT_NONE, xb,
-                                  768, 0, xa, 768, 0),
-                           Wf(p + ".ln1.w", {768}), Wf(p + ".ln1.b", {768}), 1e-12f));
+      add_gemm(st, with_xchg(with_ln(linear(ctx, M, 768, 768, Wb(p + ".ao.w", {768, 768}), 768, Wf(p + ".ao.b", {768}), ACT_NONE, xb,
+                                            768, 0, xa, 768, 0),
+                                     Wf(p + ".ln1.w", {768}), Wf(p + ".ln1.b", {768}), 1e-12f)));
     } else {
       add_gemm(st, linear(ctx, M, 768, 768, Wb(p + ".ao.w", {768, 768}), 768, Wf(p + ".ao.b", {768}), ACT_NONE, y, 768, 1,
                           xa, 768, 0));
@@ -413,9 +432,9 @@ void Engine::plan_bert(Stage& st) {
     add_gemm(st, linear(xb, M, 768, 768, Wb(p + ".ff1.w", {3072, 768}), 3072, Wf(p + ".ff1.b", {3072}), ACT_GELU, hbuf,
                         3072, 0));
     if (use_ln_fused_bert()) {
-      add_gemm(st, with_ln(linear(hbuf, M, 3072, 3072, Wb(p + ".ff2.w", {768, 3072}), 768, Wf(p + ".ff2.b", {768}), ACT_NONE,
-                                  xa, 768, 0, xb, 768, 0),
-                           Wf(p + ".ln2.w", {768}), Wf(p + ".ln2.b", {768}), 1e-12f));
+      add_gemm(st, with_xchg(with_ln(linear(hbuf, M, 3072, 3072, Wb(p + ".ff2.w", {768, 3072}), 768, Wf(p + ".ff2.b", {768}), ACT_NONE,
+                                            xa, 768, 0, xb, 768, 0),
+                                     Wf(p + ".ln2.w", {768}), Wf(p + ".ln2.b", {768}), 1e-12f)));
     } else {
       add_gemm(st, linear(hbuf, M, 3072, 3072, Wb(p + ".ff2.w", {768, 3072}), 768, Wf(p + ".ff2.b", {768}), ACT_NONE, y,
                           768, 1, xb, 768, 0));

@@ -108,7 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;   // 0 = leader of the pair
   // LayerNorm mode (CTAS == 1): the n_tiles CTAs of one 128-row block form a cluster; CTA `ln_rank` owns
   // column tile ln_rank and all CTAs of a cluster walk the same sequence of row blocks
-  const int ncl = LN ? p.n_tiles : 1;
+  const int ncl = (LN && !p.ln_xchg) ? p.n_tiles : 1;   // cluster size (DSMEM exchange); 1 for the global-memory exchange
   const uint32_t ln_rank = (ncl > 1) ? cluster_ctarank() : 0u;
   const int unit = (CTAS == 2) ? static_cast<int>(blockIdx.x >> 1)
                    : (ncl > 1 ? static_cast<int>(blockIdx.x / ncl) * p.n_tiles + static_cast<int>(ln_rank)
@@ -541,7 +541,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tmem_st_wait();
         // exchange (sum, sumsq)
-        {
+        float tsum = 0.0f, tsq = 0.0f;
+        if (p.ln_xchg) {
+          // independent CTAs: partials through global memory (L2), completion through a monotonic counter per
+          // (row block, lane quadrant) that the 2 x n_tiles warps owning these 32 rows increment once per launch
+          const int nex = p.n_tiles;
+          float2* ws = reinterpret_cast<float2*>(p.ln_ws);
+          __stcg(ws + ((static_cast<size_t>(mu) * nex + nt) * 2 + group) * BLOCK_M + row_in_tile, make_float2(sum, sq));
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) {
+            int* cnt = p.ln_cnt + mu * 4 + quad;
+            const int per_launch = 2 * nex;
+            const int old = atomicAdd(cnt, 1);
+            const int target = (old / per_launch + 1) * per_launch;
+            uint32_t spins = 0;
+            while (true) {
+              int cur;
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(cur) : "l"(cnt) : "memory");
+              if (cur >= target) break;
+              if (++spins > (1u << 16)) {
+                __nanosleep(128);
+                if (spins > (1u << 16) + (1u << 24)) __trap();
+              }
+            }
+          }
+          __syncwarp();
+          for (int r = 0; r < nex; ++r) {
+            const float2 a0 = __ldcg(ws + ((static_cast<size_t>(mu) * nex + r) * 2 + 0) * BLOCK_M + row_in_tile);
+            const float2 a1 = __ldcg(ws + ((static_cast<size_t>(mu) * nex + r) * 2 + 1) * BLOCK_M + row_in_tile);
+            tsum += a0.x + a1.x;
+            tsq += a0.y + a1.y;
+          }
+        } else {
           float2* mine = ln_slot(static_cast<int>(ln_rank), group) + row_in_tile;
           if (ncl == 1) {
             *mine = make_float2(sum, sq);
@@ -556,12 +588,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             mbar_wait_acquire_cluster(&ln_bar[0], static_cast<uint32_t>(par));
           }
-        }
-        float tsum = 0.0f, tsq = 0.0f;
-        for (int r = 0; r < ncl; ++r) {
-          const float2 a0 = ln_slot(r, 0)[row_in_tile], a1 = ln_slot(r, 1)[row_in_tile];
-          tsum += a0.x + a1.x;
-          tsq += a0.y + a1.y;
+          for (int r = 0; r < ncl; ++r) {
+            const float2 a0 = ln_slot(r, 0)[row_in_tile], a1 = ln_slot(r, 1)[row_in_tile];
+            tsum += a0.x + a1.x;
+            tsq += a0.y + a1.y;
+          }
         }
         const float inv_n = 1.0f / static_cast<float>(p.N);
         const float mean = tsum * inv_n;
@@ -852,7 +883,7 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  const int cluster_x = (CTAS == 2) ? 2 : (EPI == 1 ? plan.p.n_tiles : 1);
+  const int cluster_x = (CTAS == 2) ? 2 : ((EPI == 1 && !plan.p.ln_xchg) ? plan.p.n_tiles : 1);
   if (cluster_x > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = cluster_x;
@@ -985,6 +1016,8 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
                   (g.ln_pe == nullptr || (reinterpret_cast<uintptr_t>(g.ln_pe) & 15) == 0), "gemm: LayerNorm parameter alignment");
     p.ln = 1; p.ln_eps = g.ln_eps; p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_pe = g.ln_pe;
     p.ln_pe_rows = g.ln_pe_rows > 0 ? g.ln_pe_rows : 1;
+    p.ln_xchg = (g.ln_ws != nullptr && g.ln_cnt != nullptr && g.Cout > 256) ? 1 : 0;
+    p.ln_ws = g.ln_ws; p.ln_cnt = g.ln_cnt;
     force_bn = 256;   // one full 256-column tile per CTA, 1-CTA form
   }
   {
@@ -1150,7 +1183,7 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
 
   const long long units = static_cast<long long>((p.m_tiles + best_ctas - 1) / best_ctas) * p.n_tiles;
   plan->grid = static_cast<int>(std::min<long long>(units, sms / best_ctas)) * best_ctas;
-  if (ln) plan->grid = std::min(p.m_tiles, sms / p.n_tiles) * p.n_tiles;   // whole clusters of n_tiles CTAs
+  if (ln) plan->grid = std::min(p.m_tiles, sms / p.n_tiles) * p.n_tiles;   // whole clusters / whole row blocks of n_tiles CTAs
   plan->valid = true;
 }
 

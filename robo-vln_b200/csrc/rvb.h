@@ -86,6 +86,11 @@ struct ConvGemm {
   float ln_eps = 0.0f;
   const float* ln_pe = nullptr;  // [ln_pe_rows, Cout] fp32 added after the norm, or null
   int ln_pe_rows = 1;
+  // Cout > 256: how the Cout/256 CTAs of a row block exchange (sum, sumsq).  Null: thread-block cluster + DSMEM.
+  // Non-null: through global memory, no cluster launch -- ln_ws holds m_tiles*n_tiles*256 float2, ln_cnt
+  // m_tiles*4 ints that are zero before the first launch (monotonic counters: never reset).
+  void* ln_ws = nullptr;
+  int* ln_cnt = nullptr;
   // GroupNorm folded into the store, for feature maps small enough that every 128-row M tile holds WHOLE
   // samples (gn_hw = H*W of the output in {16, 64}) and every N tile whole groups:
   //   out = relu?( GN_groups(acc) * gn_gamma + gn_beta + res )     (res: plain h16 residual, optional)
@@ -142,6 +147,9 @@ struct GemmTcParams {
   const float* ln_beta;
   const float* ln_pe;
   int ln_pe_rows;
+  int ln_xchg;       // 1: statistics exchanged through global memory (ln_ws / ln_cnt), independent CTAs
+  void* ln_ws;
+  int* ln_cnt;
   int nstages;       // pipeline stages in use (fewer when the residual slices take their place)
   int dbg;           // timing experiments only (ROBOVLN_EPI_DEBUG bit mask; results are wrong when set)
 };
