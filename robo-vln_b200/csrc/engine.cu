@@ -701,11 +701,17 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
       RVB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
       static const char* penv = std::getenv("ROBOVLN_PRIORITIES");
       const bool prio = !(penv != nullptr && std::strcmp(penv, "0") == 0);
-      const int p_depth = prio ? prio_hi : prio_lo;
-      const int p_bert = prio ? std::min(prio_lo, prio_hi + 1) : prio_lo;
+      // ROBOVLN_PRIO_ORDER = three digits (depth, BERT, RGB), 0 = highest ... (experiments); the RGB digit applies
+      // to the graph-capture stream, i.e. to the RGB kernel nodes of the replayed graphs
+      static const char* oenv = std::getenv("ROBOVLN_PRIO_ORDER");
+      int od = 0, ob = 1, orr = 9;
+      if (oenv != nullptr && std::strlen(oenv) == 3) { od = oenv[0] - '0'; ob = oenv[1] - '0'; orr = oenv[2] - '0'; }
+      auto lvl = [&](int o) { return prio ? std::min(prio_lo, prio_hi + o) : prio_lo; };
+      const int p_depth = lvl(od);
+      const int p_bert = lvl(ob);
       RVB_CUDA(cudaStreamCreateWithPriority(&side_[0], cudaStreamNonBlocking, p_depth));
       RVB_CUDA(cudaStreamCreateWithPriority(&side_[1], cudaStreamNonBlocking, p_bert));
-      RVB_CUDA(cudaStreamCreateWithFlags(&capture_, cudaStreamNonBlocking));
+      RVB_CUDA(cudaStreamCreateWithPriority(&capture_, cudaStreamNonBlocking, lvl(orr)));
       RVB_CUDA(cudaStreamCreateWithFlags(&upload_, cudaStreamNonBlocking));
       RVB_CUDA(cudaStreamCreateWithPriority(&aux_, cudaStreamNonBlocking, p_depth));
       RVB_CUDA(cudaEventCreateWithFlags(&ev_aux_[0], cudaEventDisableTiming));
