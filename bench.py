@@ -249,6 +249,30 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = global_rows / (ms_e2e / args.steps * 1e-3)
+    # same call with the RGB frames as uint8 (observation ingest): a quarter of the RGB bytes
+    e2e_u8 = None
+    try:
+        u8_sets = [hs["rgb"].to(torch.uint8).pin_memory() for hs in host_sets]
+        for i in range(3):
+            hs = host_sets[i % n_sets]
+            host_out = policy.act_host(u8_sets[i % n_sets], hs["depth"], hs["instruction"], hs["masks"], hs["hidden_hi"], hs["hidden_lo"], out=host_out)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            hs = host_sets[i % n_sets]
+            host_out = policy.act_host(u8_sets[i % n_sets], hs["depth"], hs["instruction"], hs["masks"], hs["hidden_hi"], hs["hidden_lo"], out=host_out)
+            _ = float(host_out["logits"][0, 0])
+        e1.record()
+        barrier()
+        ms_u8 = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_u8], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_u8 = float(t.item())
+        e2e_u8 = {"value": global_rows / (ms_u8 / args.steps * 1e-3), "unit": "obs/s", "ms_per_step": ms_u8 / args.steps,
+                  "h2d_bytes_per_step": B * (256 * 256 * 3 + 256 * 256 * 4 + L * 4 + 2 * 4) + 2 * (2 * N * 512 * 4)}
+    except Exception as exc:
+        e2e_u8 = {"error": str(exc)[:200]}
     h2d = B * (256 * 256 * 3 * 4 + 256 * 256 * 4 + L * 4 + 2 * 4) + 2 * (2 * N * 512 * 4)
     d2h = B * (4 + 2 + 1) * 4 + 2 * (2 * N * 512 * 4)
 
@@ -325,7 +349,7 @@ def run_b200(args):
                 "outputs_finite": finite, "trajectory_shaped": traj,
             },
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                      "ms_per_step": ms_e2e / args.steps},
+                                      "ms_per_step": ms_e2e / args.steps, "uint8_rgb_frames": e2e_u8},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -104,6 +104,12 @@ int hcm_forward_policy_host(hcm_engine* e, const float* rgb, const float* depth,
                             float* logits, float* actions, float* stop_logit, float* hc_hi_out,
                             float* hc_lo_out, void* stream);
 
+/* Element type behind the `rgb` pointer of every entry point: 0 = float32 in 0..255 (default; what the reference's
+ * batch_obs produces, robo_vln_baselines/common/utils.py:59-118), 1 = uint8 [B,H,W,3] exactly as the RGB sensor
+ * delivers it (habitat_extensions/config/robo_vln_task.yaml:10-13).  Results are identical; the uint8 form moves a
+ * quarter of the bytes (observation ingest). */
+int hcm_set_rgb_format(hcm_engine* e, int fmt);
+
 /* Number of kernels the last forward call launched (for bench.py's gpu_launches). */
 int64_t hcm_last_launch_count(hcm_engine* e);
 

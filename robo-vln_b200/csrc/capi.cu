@@ -128,6 +128,13 @@ int hcm_forward_policy_host(hcm_engine* e, const float* rgb, const float* depth,
   });
 }
 
+int hcm_set_rgb_format(hcm_engine* e, int fmt) {
+  return guarded([&] {
+    RVB_CHECK(fmt == 0 || fmt == 1, "hcm_set_rgb_format: 0 = float32 (0..255), 1 = uint8");
+    e->eng.rgb_fmt_ = fmt;
+  });
+}
+
 int64_t hcm_last_launch_count(hcm_engine* e) { return e->eng.launches_; }
 
 int hcm_profile_policy(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) rgb_pad_convert_kernel(const float* __res
 // Packed variant for the two-filter-rows-per-K-block stem: row-pair interleaved [NB, (H+6)/2, Wp, 2, 4]
 // (for every pixel column: row 2t then row 2t+1, 4 channels each with channel 3 zero).  One thread per
 // (row pair, pixel): 24 B read, 16 B written.
-__global__ void __launch_bounds__(256) rgb_pad_convert4_kernel(const float* __restrict__ rgb, h16* __restrict__ out,
+template <typename T>   // float (0..255, the reference's batch_obs output) or uint8_t (the sensor's own format)
+__global__ void __launch_bounds__(256) rgb_pad_convert4_kernel(const T* __restrict__ rgb, h16* __restrict__ out,
                                                                int NB, int H, int W, int Hh, int Wp) {
   RVB_PDL_PROLOGUE();
   const long long total = static_cast<long long>(NB) * Hh * Wp;
@@ -114,9 +115,9 @@ __global__ void __launch_bounds__(256) rgb_pad_convert4_kernel(const float* __re
     for (int r2 = 0; r2 < 2; ++r2) {
       const int y = tp * 2 + r2 - 3;
       if (x >= 0 && x < W && y >= 0 && y < H) {
-        const float* src = rgb + ((static_cast<long long>(img) * H + y) * W + x) * 3;
-        q[2 * r2] = pack_h2(__ldg(src) / 255.0f, __ldg(src + 1) / 255.0f);   // true division, as the reference
-        q[2 * r2 + 1] = pack_h2(__ldg(src + 2) / 255.0f, 0.0f);
+        const T* src = rgb + ((static_cast<long long>(img) * H + y) * W + x) * 3;
+        q[2 * r2] = pack_h2(static_cast<float>(__ldg(src)) / 255.0f, static_cast<float>(__ldg(src + 1)) / 255.0f);   // true division, as the reference
+        q[2 * r2 + 1] = pack_h2(static_cast<float>(__ldg(src + 2)) / 255.0f, 0.0f);
       }
     }
     *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(q[0], q[1], q[2], q[3]);
@@ -809,7 +810,14 @@ void rgb_pad_convert(const float* rgb, h16* out, int NB, int H, int W, int Wp, c
 void rgb_pad_convert4(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s) {
   RVB_CHECK(Wp >= W + 6 && H % 2 == 0, "rgb_pad_convert4: padded width too small / odd height");
   const long long total = static_cast<long long>(NB) * ((H + 6) / 2) * Wp;
-  launch_k(rgb_pad_convert4_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, rgb, out, NB, H, W, (H + 6) / 2, Wp);
+  launch_k(rgb_pad_convert4_kernel<float>, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, rgb, out, NB, H, W, (H + 6) / 2, Wp);
+  RVB_CUDA(cudaGetLastError());
+}
+
+void rgb_pad_convert4_u8(const uint8_t* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s) {
+  RVB_CHECK(Wp >= W + 6 && H % 2 == 0, "rgb_pad_convert4_u8: padded width too small / odd height");
+  const long long total = static_cast<long long>(NB) * ((H + 6) / 2) * Wp;
+  launch_k(rgb_pad_convert4_kernel<uint8_t>, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, s, rgb, out, NB, H, W, (H + 6) / 2, Wp);
   RVB_CUDA(cudaGetLastError());
 }
 

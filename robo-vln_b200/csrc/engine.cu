@@ -205,7 +205,8 @@ void Engine::plan_rgb_trunk(const std::string& ns, Stage& st) {
     if (!dry_) {
       const size_t in_off = static_cast<size_t>(sb) * NBs * H * W * 3;
       st.push_back([this, padded, NBs, H, W, Wp, in_off](cudaStream_t s) {
-        rgb_pad_convert4(args_.rgb + in_off, padded, NBs, H, W, Wp, s);
+        if (rgb_fmt_ == 1) rgb_pad_convert4_u8(reinterpret_cast<const uint8_t*>(args_.rgb) + in_off, padded, NBs, H, W, Wp, s);
+        else rgb_pad_convert4(args_.rgb + in_off, padded, NBs, H, W, Wp, s);
         return 1;
       });
       ConvGemm g;
@@ -875,11 +876,13 @@ void Engine::tl_flush(cudaStream_t s) {
 void Engine::drop_graphs() {
   for (auto& g : graphs_) cudaGraphExecDestroy(g.exec);
   graphs_.clear();
-  if (host_graphs_.g1 != nullptr) cudaGraphExecDestroy(host_graphs_.g1);
-  if (host_graphs_.g1b != nullptr) cudaGraphExecDestroy(host_graphs_.g1b);
-  if (host_graphs_.g2a != nullptr) cudaGraphExecDestroy(host_graphs_.g2a);
-  if (host_graphs_.g2b != nullptr) cudaGraphExecDestroy(host_graphs_.g2b);
-  host_graphs_ = HostGraphs();
+  for (HostGraphs& hg : host_graphs_) {
+    if (hg.g1 != nullptr) cudaGraphExecDestroy(hg.g1);
+    if (hg.g1b != nullptr) cudaGraphExecDestroy(hg.g1b);
+    if (hg.g2a != nullptr) cudaGraphExecDestroy(hg.g2a);
+    if (hg.g2b != nullptr) cudaGraphExecDestroy(hg.g2b);
+    hg = HostGraphs();
+  }
   eager_runs_ = 0;
 }
 
@@ -916,7 +919,8 @@ void Engine::forward_policy_graphed(cudaStream_t s) {
     return;
   }
   const void* key[8] = {user.rgb, user.depth, user.instr_f32, user.instr_i64, user.masks,
-                        reinterpret_cast<const void*>(static_cast<uintptr_t>(user.mask_stride)), user.hc_hi_in, user.hc_lo_in};
+                        reinterpret_cast<const void*>(static_cast<uintptr_t>(user.mask_stride) | (static_cast<uintptr_t>(rgb_fmt_) << 16)),
+                        user.hc_hi_in, user.hc_lo_in};
   GraphEntry* hit = nullptr;
   for (auto& g : graphs_)
     if (std::memcmp(g.key, key, sizeof(key)) == 0) hit = &g;
@@ -1002,7 +1006,7 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
                                  float* stop, float* hc_hi_out, float* hc_lo_out, cudaStream_t s) {
   RVB_CHECK(planned_, "engine not planned");
   const int B = shp_.B, N = shp_.N;
-  const size_t rgb_b = static_cast<size_t>(B) * shp_.rgb_h * shp_.rgb_w * 3 * 4;
+  const size_t rgb_b = static_cast<size_t>(B) * shp_.rgb_h * shp_.rgb_w * 3 * (rgb_fmt_ == 1 ? 1 : 4);
   const size_t dep_b = static_cast<size_t>(B) * shp_.depth_h * shp_.depth_w * 4;
   const size_t ins_b = static_cast<size_t>(shp_.instr_rows) * shp_.L * 4;
   const size_t hc_b = 2ull * N * 512 * 4;
@@ -1044,6 +1048,7 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
     // Four graphs over the fixed staging buffers: G1b = BERT, G1 = depth trunk, G2a = RGB trunk (each with
     // its single-encoder consumers), G2b = hi tail -> lo tail.  Every encoder graph starts as soon as ITS
     // input has landed, on its own stream, underneath the uploads that follow.
+    HostGraphs& host_graphs_ = this->host_graphs_[rgb_fmt_ == 1 ? 1 : 0];
     if (!host_graphs_.valid) {
       auto capture = [&](cudaGraphExec_t* exec, const std::function<void(cudaStream_t)>& body) {
         cudaGraph_t graph = nullptr;

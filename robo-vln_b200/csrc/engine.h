@@ -85,6 +85,9 @@ class Engine {
   int run(const Stage& st, cudaStream_t s);
   bool get_buffer(const std::string& name, void** ptr, int* dtype, std::vector<int64_t>* shape) const;
 
+  // 0: RGB frames are float32 in 0..255 (the reference's batch_obs output); 1: uint8 (the sensor's own format --
+  // a quarter of the upload bytes).  Applies to the `rgb` pointer of every entry point.
+  int rgb_fmt_ = 0;
   RunArgs args_;
   // forward_policy only: the hi head also writes argmax -> sub-goal ids and lo's sub-task embedding
   int64_t* policy_sg_ = nullptr;
@@ -150,7 +153,7 @@ class Engine {
     cudaGraphExec_t g1 = nullptr, g1b = nullptr, g2a = nullptr, g2b = nullptr;
     int64_t launches = 0;
     bool valid = false;
-  } host_graphs_;
+  } host_graphs_[2];   // per RGB input format
   int enc_mask_ = 7;             // run_encoders: 1 = RGB, 2 = depth, 4 = BERT branches (graph capture of subsets)
   uint64_t graph_tick_ = 0;
   int eager_runs_ = 0;           // eager forward_policy calls since the last plan (kernels' one-time setup)

@@ -179,7 +179,8 @@ bool use_simt_gemm();
 // elementwise.cu
 void rgb_stem_im2col(const float* rgb, h16* out, int NB, int H, int W, int Kpitch, cudaStream_t s);
 void rgb_pad_convert(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s);
-void rgb_pad_convert4(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s);   // row-pair interleaved (packed stem)
+void rgb_pad_convert4(const float* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s);
+void rgb_pad_convert4_u8(const uint8_t* rgb, h16* out, int NB, int H, int W, int Wp, cudaStream_t s);   // row-pair interleaved (packed stem)
 void maxpool3x3s2(const h16* in, h16* out, int NB, int H, int W, int C, cudaStream_t s);
 void depth_stem_conv(const float* depth, const float* w, h16* out, int NB, int H, int W, cudaStream_t s);
 void gn_stats(const h16* x, float* stats, int NB, int HW, int C, int G, cudaStream_t s);

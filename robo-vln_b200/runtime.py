@@ -41,6 +41,7 @@ class HcmRuntime:
         self.lo = None
         self._tensors: Dict[str, torch.Tensor] = {}   # keeps prepared weights alive
         self._dirty = True
+        self._rgb_fmt = 0             # engine-side RGB element type: 0 float32, 1 uint8 (hcm_set_rgb_format)
         self._shares = False
         self._shape_key = None
         self._workspace: Optional[torch.Tensor] = None
@@ -168,6 +169,21 @@ class HcmRuntime:
             t = t.float()
         return t.contiguous()
 
+    def _prep_rgb(self, t: torch.Tensor) -> torch.Tensor:
+        """RGB frames: float32 in 0..255 (the reference's batch_obs output) or uint8 exactly as the sensor delivers
+        them -- the engine reads either (hcm_set_rgb_format); other dtypes are converted to float32."""
+        if t.dtype == torch.uint8:
+            if t.device != self.device:
+                t = t.to(self.device, non_blocking=True)
+            t = t.contiguous()
+        else:
+            t = self._prep_obs(t)
+        fmt = 1 if t.dtype == torch.uint8 else 0
+        if fmt != self._rgb_fmt:
+            check(self.lib.hcm_set_rgb_format(self.handle, fmt), "hcm_set_rgb_format")
+            self._rgb_fmt = fmt
+        return t
+
     @staticmethod
     def _sig(rgb: torch.Tensor, depth: torch.Tensor):
         return (rgb.data_ptr(), rgb._version, tuple(rgb.shape), depth.data_ptr(), depth._version, tuple(depth.shape))
@@ -177,7 +193,7 @@ class HcmRuntime:
 
     # ---- forward ---------------------------------------------------------------------------
     def forward_hi(self, rgb, depth, instruction, masks, hidden):
-        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        rgb, depth = self._prep_rgb(rgb), self._prep_obs(depth)
         B = rgb.shape[0]
         N = hidden.shape[1]
         instr = instruction
@@ -202,7 +218,7 @@ class HcmRuntime:
         return logits, hc_out
 
     def forward_lo(self, rgb, depth, masks, hidden, sub_goal):
-        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        rgb, depth = self._prep_rgb(rgb), self._prep_obs(depth)
         B = rgb.shape[0]
         N = hidden.shape[1]
         masks = masks.to(self.device, torch.float32)
@@ -230,7 +246,7 @@ class HcmRuntime:
 
     def forward_policy(self, rgb, depth, instruction, masks, hidden_hi, hidden_lo):
         """hi -> argmax -> lo in one engine call (rollout step, hierarchical_trainer.py:1095-1101)."""
-        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        rgb, depth = self._prep_rgb(rgb), self._prep_obs(depth)
         B, N = rgb.shape[0], hidden_hi.shape[1]
         instr = instruction.to(self.device)
         i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
@@ -256,7 +272,7 @@ class HcmRuntime:
     def encode(self, rgb, depth, instruction=None, n_envs: int = 1, use_lo_weights: bool = False):
         """Frozen encoders only (training path): returns fp32 feature tensors
         {"rgb_feat" [B,16,2048], "rgb_gmean" [B,2048], "depth_feat" [B,16,128], "bert" [1|B,L,768]}."""
-        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        rgb, depth = self._prep_rgb(rgb), self._prep_obs(depth)
         B = rgb.shape[0]
         self.sync_weights()          # may invalidate the current plan (new weights / newly attached half)
         with_bert = instruction is not None
@@ -296,7 +312,7 @@ class HcmRuntime:
         launches): list of {"name", "ms", "flops"}."""
         import json
 
-        rgb, depth = self._prep_obs(rgb), self._prep_obs(depth)
+        rgb, depth = self._prep_rgb(rgb), self._prep_obs(depth)
         B, N = rgb.shape[0], hidden_hi.shape[1]
         instr = instruction.to(self.device)
         i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
@@ -323,9 +339,15 @@ class HcmRuntime:
         """Host-buffer entry: all arguments are CPU float32 tensors (pinned for speed); H2D copies,
         the forward and the D2H copies of the results are inside this call."""
         B, N = rgb.shape[0], hidden_hi.shape[1]
-        for t in (rgb, depth, instruction, masks, hidden_hi, hidden_lo):
+        for t in (depth, instruction, masks, hidden_hi, hidden_lo):
             if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("forward_policy_host expects contiguous float32 CPU tensors")
+        if rgb.device.type != "cpu" or rgb.dtype not in (torch.float32, torch.uint8) or not rgb.is_contiguous():
+            raise ValueError("forward_policy_host expects a contiguous float32 or uint8 CPU tensor for rgb")
+        fmt = 1 if rgb.dtype == torch.uint8 else 0
+        if fmt != self._rgb_fmt:
+            check(self.lib.hcm_set_rgb_format(self.handle, fmt), "hcm_set_rgb_format")
+            self._rgb_fmt = fmt
         if masks.dim() != 2 or masks.shape[1] != 2:
             raise ValueError("masks must be [B,2]")
         self.ensure_plan(B, N, instruction.shape[1], instruction.shape[0], rgb.shape[1:3], depth.shape[1:3])

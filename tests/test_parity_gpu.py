@@ -167,6 +167,40 @@ def test_cross_modal_stage_against_oracle(B, L, shared, models):
     _out(out, ref, "cross_modal pooled", tol=1e-2)
 
 
+def test_uint8_rgb_ingest_matches_float(models):
+    """RGB frames handed over as uint8 (the sensor's format) give bit-identical results to
+    the float32 0..255 tensors the reference's batch_obs builds, on the device entry and on the host entry (eager
+    first call and graph replays)."""
+    import robovln_b200 as R
+    from oracle import weights as W
+
+    hi, lo, _, _ = models
+    pol = R.HcmPolicy(hi, lo)
+    dev = "cuda"
+    inp = W.make_inputs(B=4, L=12, N=4, rgb_hw=256, seed=31, mask_zero_rows=(2,))
+    rgb_u8 = inp["rgb"].to(torch.uint8)
+    assert torch.equal(rgb_u8.float(), inp["rgb"])
+    other = {k: inp[k].to(dev) for k in ("depth", "instruction", "hidden_hi", "hidden_lo", "masks")}
+
+    def run(rgb):
+        out = pol.act({"rgb": rgb, "depth": other["depth"], "instruction": other["instruction"]}, other["hidden_hi"],
+                      other["hidden_lo"], other["masks"])
+        torch.cuda.synchronize()
+        return [o.clone() for o in out]
+
+    ref = run(inp["rgb"].to(dev))
+    for _ in range(3):
+        for x, y in zip(run(rgb_u8.to(dev)), ref):
+            assert torch.equal(x, y)
+    for x, y in zip(run(inp["rgb"].to(dev)), ref):          # and back
+        assert torch.equal(x, y)
+    host = {k: inp[k].pin_memory() for k in ("depth", "instruction", "masks", "hidden_hi", "hidden_lo")}
+    for rgb in (inp["rgb"].pin_memory(), rgb_u8.pin_memory(), rgb_u8.pin_memory(), inp["rgb"].pin_memory(), rgb_u8.pin_memory()):
+        o = pol.act_host(rgb, host["depth"], host["instruction"], host["masks"], host["hidden_hi"], host["hidden_lo"])
+        assert torch.equal(o["logits"], ref[0].cpu()) and torch.equal(o["actions"], ref[1].cpu())
+        assert torch.equal(o["hidden_lo"], ref[4].cpu())
+
+
 def test_graph_replay_matches_eager(models):
     """HcmPolicy.act / act_host replay a captured CUDA graph from the second call with the same input
     pointers on; replays must reproduce the eager (first) call bit for bit, follow NEW input values
