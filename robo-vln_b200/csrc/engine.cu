@@ -454,7 +454,8 @@ void Engine::plan_bert(Stage& st) {
 //   bert: [R*L,768] h16; kvin: [2*B*16,256] h16 (rgb rows then depth rows);
 //   pooled -> out[b*out_pitch + mod*256 + d]
 // ---------------------------------------------------------------------------------------
-void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch) {
+void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch,
+                              Stage* st_vis_rgb, Stage* st_vis_depth) {
   const int B = shp_.B, L = shp_.L;
   const int R = (shp_.instr_rows == 1) ? 1 : B;
   const int64_t MQ = static_cast<int64_t>(R) * L, MV = 2ll * B * 16, MX = 2ll * B * L;
@@ -487,19 +488,31 @@ void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16*
     });
   }
   add_gemm(stq, linear(Q0, MQ, 256, 256, Wb(p + ".fc_q.w", {256, 256}), 256, Wf(p + ".fc_q.b", {256}), ACT_NONE, qq, 256, 0));
-  // key/value side
-  if (use_ln_fused()) {
-    add_gemm(st, with_ln(linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
-                                vis, 256, 0), ln0w, ln0b, 1e-5f));
+  // key/value side.  With per-modality stages given (the policy step), each modality's vis_fc (+LayerNorm) and
+  // fc_k|fc_v run on the stream of the encoder that produced its kv input, before the join.
+  if (use_ln_fused() && st_vis_rgb != nullptr && st_vis_depth != nullptr) {
+    const int64_t MH = MV / 2;
+    Stage* sts[2] = {st_vis_rgb, st_vis_depth};
+    for (int mod = 0; mod < 2; ++mod) {
+      add_gemm(*sts[mod], with_ln(linear(kvin + mod * MH * 256, MH, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256,
+                                         Wf(p + ".vis_fc.b", {256}), ACT_RELU, vis + mod * MH * 256, 256, 0), ln0w, ln0b, 1e-5f));
+      add_gemm(*sts[mod], linear(vis + mod * MH * 256, MH, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}),
+                                 ACT_NONE, kv + mod * MH * 512, 512, 0));
+    }
   } else {
-    add_gemm(st, linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
-                        f32a, 256, 1));
-    st.push_back([f32a, MV, ln0w, ln0b, vis](cudaStream_t s) {
-      layernorm_rows(f32a, static_cast<int>(MV), 256, ln0w, ln0b, 1e-5f, nullptr, 1, vis, s);
-      return 1;
-    });
+    if (use_ln_fused()) {
+      add_gemm(st, with_ln(linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
+                                  vis, 256, 0), ln0w, ln0b, 1e-5f));
+    } else {
+      add_gemm(st, linear(kvin, MV, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256, Wf(p + ".vis_fc.b", {256}), ACT_RELU,
+                          f32a, 256, 1));
+      st.push_back([f32a, MV, ln0w, ln0b, vis](cudaStream_t s) {
+        layernorm_rows(f32a, static_cast<int>(MV), 256, ln0w, ln0b, 1e-5f, nullptr, 1, vis, s);
+        return 1;
+      });
+    }
+    add_gemm(st, linear(vis, MV, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}), ACT_NONE, kv, 512, 0));
   }
-  add_gemm(st, linear(vis, MV, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}), ACT_NONE, kv, 512, 0));
   const int q_shared = (R == 1) ? 1 : 0;
   st.push_back([qq, kv, ctx, B, L, q_shared](cudaStream_t s) { vla_cross_attention(qq, kv, ctx, B, L, 2, q_shared, s); return 1; });
   if (use_ln_fused()) {
@@ -566,7 +579,7 @@ void Engine::plan_hi_tail(Stage& pre, Stage& st) {
     add_gemm(st_depth_post_hi_, linear(tokens_d_, B, 3072, 3072, Wb("hi.depth_linear.w", {128, 3072}), 128,
                                        Wf("hi.depth_linear.b", {128}), ACT_RELU, concat_hi_ + 256, 896, 0));
   }
-  plan_cross_modal(st_bert_post_, st, bert_out_, kvin_, concat_hi_ + 384, 896);
+  plan_cross_modal(st_bert_post_, st, bert_out_, kvin_, concat_hi_ + 384, 896, &st_rgb_post_hi_, &st_depth_post_hi_);
   if (dry_) return;
   add_gemm(st, linear(concat_hi_, B, 896, 896, Wb("hi.lstm.wih", {2048, 896}), 2048, Wf("hi.lstm.b", {2048}), ACT_NONE,
                       gx_hi_, 2048, 1));

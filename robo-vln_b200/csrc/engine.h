@@ -117,7 +117,8 @@ class Engine {
                        h16* out_last);
   void plan_depth_trunk(const std::string& ns, Stage& st);
   void plan_bert(Stage& st);
-  void plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch);
+  void plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch,
+                        Stage* st_vis_rgb = nullptr, Stage* st_vis_depth = nullptr);
   void plan_hi_tail(Stage& pre, Stage& st);
   void plan_lo_tail(Stage& st);
 
