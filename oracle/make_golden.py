@@ -36,7 +36,18 @@ CASES = {
     # the reference's native 224x224 RGB (adaptive pool 7x7 -> 4x4 with overlapping windows),
     # single step with mask = 1 so the incoming hidden state is carried
     "step_rgb224_keep_hidden": dict(B=1, L=8, N=1, rgb_hw=224, seed=3, mask_zero_rows=()),
+    # BASELINE.json configs[1] at FULL size: 64 observations, 64 distinct 80-token instructions, as one 64-step
+    # trajectory (the only shape the unmodified reference runs) with an episode reset at step 37.  The large
+    # intermediates are stored as per-row statistics (mean, mean |x|) to keep the fixture small.
+    "cfg2_b64_l80": dict(B=64, L=80, N=1, rgb_hw=256, seed=4, mask_zero_rows=(0, 37)),
 }
+REDUCED = {"cfg2_b64_l80"}        # cases whose big intermediates are stored as statistics
+
+
+def row_stats(x: np.ndarray) -> np.ndarray:
+    """[B, ...] -> [B, 2]: mean and mean absolute value of every row (sample)."""
+    f = x.reshape(x.shape[0], -1).astype(np.float64)
+    return np.stack([f.mean(axis=1), np.abs(f).mean(axis=1)], axis=1).astype(np.float32)
 
 
 def run_case(hi, lo, kw):
@@ -91,8 +102,15 @@ def main():
     lo.load_state_dict(W.make_state_dict("lo", 0), strict=True)
     print("loaded synthetic weights (strict):", missing)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    only = set(sys.argv[1:])
     for name, kw in CASES.items():
+        if only and name not in only:
+            continue
         res = run_case(hi, lo, kw)
+        if name in REDUCED:
+            big = ("hi.depth_embedding", "hi.rgb_embedding", "hi.bert", "hi.ins_rgb_att_tokens", "hi.ins_depth_att_tokens",
+                   "lo.depth_embedding", "lo.rgb_embedding")
+            res = {(k + ".stats" if k in big else k): (row_stats(v) if k in big else v) for k, v in res.items()}
         path = os.path.join(ROOT, "tests", "golden", name + ".npz")
         np.savez_compressed(path, **res)
         print(name, {k: (v.shape, float(np.abs(v).max())) for k, v in res.items()})

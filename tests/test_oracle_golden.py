@@ -9,7 +9,7 @@ import torch
 
 from oracle import hcm_oracle as O
 from oracle import weights as W
-from oracle.make_golden import CASES
+from oracle.make_golden import CASES, REDUCED, row_stats
 
 TOL = 2e-4
 
@@ -38,21 +38,29 @@ def test_oracle_matches_reference_golden(case, sds, golden_dir):
         act, stop, hid_lo, il = O.lo_forward(lo_sd, inp["rgb"], inp["depth"], inp["hidden_lo"],
                                              inp["masks"], inp["sub_goal"], return_intermediates=True)
     B = inp["rgb"].shape[0]
-    _close(it["depth_embedding"].view(B, 192, 4, 4), gold["hi.depth_embedding"], "hi.depth_embedding")
-    _close(it["rgb_embedding"].view(B, 2112, 4, 4), gold["hi.rgb_embedding"], "hi.rgb_embedding")
-    _close(it["bert"], gold["hi.bert"], "hi.bert")
+    if case in REDUCED:      # full-size case: the big intermediates are stored as per-row (mean, mean |x|)
+        st = lambda t: row_stats(t.detach().numpy())                                              # noqa: E731
+        _close(st(it["depth_embedding"]), gold["hi.depth_embedding.stats"], "hi.depth_embedding.stats")
+        _close(st(it["rgb_embedding"]), gold["hi.rgb_embedding.stats"], "hi.rgb_embedding.stats")
+        _close(st(it["bert"]), gold["hi.bert.stats"], "hi.bert.stats")
+        _close(st(il["depth_embedding"]), gold["lo.depth_embedding.stats"], "lo.depth_embedding.stats")
+        _close(st(il["rgb_embedding"]), gold["lo.rgb_embedding.stats"], "lo.rgb_embedding.stats")
+    else:
+        _close(it["depth_embedding"].view(B, 192, 4, 4), gold["hi.depth_embedding"], "hi.depth_embedding")
+        _close(it["rgb_embedding"].view(B, 2112, 4, 4), gold["hi.rgb_embedding"], "hi.rgb_embedding")
+        _close(it["bert"], gold["hi.bert"], "hi.bert")
+        _close(it["ins_rgb_att"], gold["hi.ins_rgb_att_tokens"].mean(axis=1), "ins_rgb_att")
+        _close(it["ins_depth_att"], gold["hi.ins_depth_att_tokens"].mean(axis=1), "ins_depth_att")
+        _close(il["depth_embedding"], gold["lo.depth_embedding"], "lo.depth_embedding")
+        _close(il["rgb_embedding"], gold["lo.rgb_embedding"], "lo.rgb_embedding")
     _close(it["rnn_in"], gold["hi.rnn_in"], "hi.rnn_in")
     _close(it["rnn_out"], gold["hi.rnn_out"], "hi.rnn_out")
-    _close(it["ins_rgb_att"], gold["hi.ins_rgb_att_tokens"].mean(axis=1), "ins_rgb_att")
-    _close(it["ins_depth_att"], gold["hi.ins_depth_att_tokens"].mean(axis=1), "ins_depth_att")
     _close(logits, gold["hi.logits"], "hi.logits")
-    _close(hid, gold["hi.hidden"], "hi.hidden")
-    _close(il["depth_embedding"], gold["lo.depth_embedding"], "lo.depth_embedding")
-    _close(il["rgb_embedding"], gold["lo.rgb_embedding"], "lo.rgb_embedding")
+    _close(hid, gold["hi.hidden"], "hi.hidden", tol=TOL if case not in REDUCED else 2e-3)   # |c| reaches 23 after 64 steps
     _close(il["rnn_in"], gold["lo.rnn_in"], "lo.rnn_in")
     _close(act, gold["lo.actions"], "lo.actions")
     _close(stop, gold["lo.stop"], "lo.stop")
-    _close(hid_lo, gold["lo.hidden"], "lo.hidden")
+    _close(hid_lo, gold["lo.hidden"], "lo.hidden", tol=TOL if case not in REDUCED else 2e-3)
 
 
 def test_golden_features_are_nontrivial(golden_dir):
