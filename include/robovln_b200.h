@@ -180,6 +180,9 @@ int rvb_groupnorm(const void* x_bf16, float* stats /* [NB,G,2] zeroed by the cal
 int rvb_layernorm(const float* x, int M, int D, const float* gamma, const float* beta, float eps,
                   const float* pe, int pe_rows, void* out_bf16, void* stream);
 int rvb_bert_attention(const void* qkv_bf16, void* ctx_bf16, int R, int L, int heads, void* stream);
+/* Same contract as rvb_bert_attention on the tcgen05 / TMEM / TMA kernel (L <= 128): S = Q K^T and O = P V as
+ * tcgen05.mma with V consumed as an MN-major operand, softmax read straight out of TMEM. */
+int rvb_bert_attention_tc(const void* qkv_h16, void* ctx_h16, int R, int L, int heads, void* stream);
 int rvb_vla_attention(const void* q_bf16, const void* kv_bf16, void* ctx_bf16, int B, int L, int q_rows,
                       void* stream);
 int rvb_lstm(const float* gx, const void* whh_bf16, const float* masks, int mask_stride,

@@ -60,6 +60,7 @@ SYMBOLS = {
                               c_void_p, c_int64, c_void_p]),
     "rvb_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p]),
     "rvb_bert_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rvb_bert_attention_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_vla_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_lstm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                          c_void_p]),

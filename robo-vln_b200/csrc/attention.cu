@@ -264,6 +264,10 @@ __global__ void __launch_bounds__(256) vla_attn_kernel(const h16* __restrict__ q
 
 void bert_self_attention(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s) {
   RVB_CHECK(L >= 1 && L <= 256, "bert attention: 1 <= L <= 256 (INSTRUCTION_ENCODER.max_length is 200)");
+  if (L <= 128 && heads * HD * 3 % 8 == 0 && use_tc_attention()) {   // tcgen05 / TMEM kernel (attention_tc.cu)
+    bert_self_attention_tc(qkv, ctx, R, L, heads, s);
+    return;
+  }
   const int lkt = (L + 15) / 16;
   if (lkt <= 2) launch_bert_attn<2>(qkv, ctx, R, L, heads, s);
   else if (lkt <= 5) launch_bert_attn<5>(qkv, ctx, R, L, heads, s);

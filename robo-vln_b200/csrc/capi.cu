@@ -331,6 +331,10 @@ int rvb_bert_attention(const void* qkv_bf16, void* ctx_bf16, int R, int L, int h
   return guarded([&] { bert_self_attention(B16(qkv_bf16), B16(ctx_bf16), R, L, heads, S(stream)); });
 }
 
+int rvb_bert_attention_tc(const void* qkv_h16, void* ctx_h16, int R, int L, int heads, void* stream) {
+  return guarded([&] { bert_self_attention_tc(B16(qkv_h16), B16(ctx_h16), R, L, heads, S(stream)); });
+}
+
 int rvb_vla_attention(const void* q_bf16, const void* kv_bf16, void* ctx_bf16, int B, int L, int q_rows, void* stream) {
   return guarded([&] { vla_cross_attention(B16(q_bf16), B16(kv_bf16), B16(ctx_bf16), B, L, 1, q_rows == L ? 1 : 0, S(stream)); });
 }

@@ -932,6 +932,15 @@ bool use_direct_epilogue() {
 
 thread_local int g_pdl_override = -1;
 
+void tma_encode_2d_h16(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_cols,
+                       uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {pitch_bytes};
+  const uint32_t box[2] = {box_cols, box_rows};
+  const uint32_t ones[2] = {1, 1};
+  encode_map(map, kH16Type, base, 2, dims, strides, box, ones);
+}
+
 bool use_pdl() {
   if (g_pdl_override >= 0) return g_pdl_override == 1;
   static int v = -1;

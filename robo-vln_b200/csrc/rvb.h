@@ -212,6 +212,12 @@ void heads_fused(const float* y, int M, int K, const float* wA, const float* bA,
 void argmax_rows(const float* x, int M, int n, int64_t* out, cudaStream_t s);
 void sinusoid_table(float* pe, int L, int D, cudaStream_t s);
 
+// gemm_tc.cu: 2-D tensor map over a row-major 16-bit matrix [rows, cols] (pitch in bytes), 128B swizzle
+void tma_encode_2d_h16(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_cols,
+                       uint32_t box_rows);
+// attention_tc.cu -- tcgen05 / TMEM / TMA self-attention for L <= 128 (ROBOVLN_ATTN=tc selects it in the engine)
+bool use_tc_attention();
+void bert_self_attention_tc(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s);
 // attention.cu
 void bert_self_attention(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s);
 void vla_cross_attention(const h16* q, const h16* kv, h16* ctx, int B, int L, int n_mod, int q_shared,

@@ -71,14 +71,20 @@ def test_layernorm(D, M, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("L,R", [(20, 3), (80, 4), (12, 2), (128, 2), (200, 1), (1, 2)])
-def test_bert_attention(L, R, dtype):
+@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
+@pytest.mark.parametrize("L,R", [(20, 3), (80, 4), (12, 2), (128, 2), (200, 1), (1, 2), (80, 64)])
+def test_bert_attention(L, R, impl, dtype):
+    """Both self-attention kernels: warp-level mma.sync (the engine's default) and the tcgen05 / TMEM / TMA kernel
+    (L <= 128; V as an MN-major operand) against torch."""
     from tests.gpu_util import H16, OUT_TOL, P, check, lib, stream
 
+    if impl == "tcgen05" and L > 128:
+        pytest.skip("the tcgen05 kernel holds one <= 128-key tile")
     heads = 12
     qkv = _mk((R * L, 3 * heads * 64), 1.0, 9, dtype)
     ctx = torch.empty((R * L, heads * 64), dtype=H16[dtype], device="cuda")
-    check(lib(dtype).rvb_bert_attention(P(qkv), P(ctx), R, L, heads, stream()), "rvb_bert_attention", dtype)
+    fn = lib(dtype).rvb_bert_attention if impl == "mma_sync" else lib(dtype).rvb_bert_attention_tc
+    check(fn(P(qkv), P(ctx), R, L, heads, stream()), "rvb_bert_attention[%s]" % impl, dtype)
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(R, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
     s = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
