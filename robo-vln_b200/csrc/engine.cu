@@ -1100,7 +1100,7 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
       host_graphs_.launches = n + static_cast<int64_t>(st_pre_.size());
       host_graphs_.valid = true;
     }
-    // uploads in the order the encoders can start: instruction (tiny) -> BERT, depth -> depth trunk, RGB -> RGB trunk
+    // uploads: instruction (tiny) -> BERT graph, then the frames; every encoder graph starts when ITS input has landed
     RVB_CUDA(cudaMemcpyAsync(stage_instr_, instr, ins_b, cudaMemcpyHostToDevice, s));
     RVB_CUDA(cudaMemcpyAsync(stage_masks_, masks, static_cast<size_t>(B) * 2 * 4, cudaMemcpyHostToDevice, s));
     RVB_CUDA(cudaMemcpyAsync(stage_hc_hi_, hc_hi_in, hc_b, cudaMemcpyHostToDevice, s));
@@ -1110,13 +1110,27 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
     RVB_CUDA(cudaGraphLaunch(host_graphs_.g1b, upload_));
     RVB_CUDA(cudaEventRecord(ev_upload_, upload_));
     run(st_pre_, s);
-    RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, s));
-    RVB_CUDA(cudaEventRecord(ev_aux_[0], s));
-    RVB_CUDA(cudaStreamWaitEvent(aux_, ev_aux_[0], 0));
-    RVB_CUDA(cudaGraphLaunch(host_graphs_.g1, aux_));
-    RVB_CUDA(cudaEventRecord(ev_aux_[1], aux_));
-    RVB_CUDA(cudaMemcpyAsync(stage_rgb_, rgb, rgb_b, cudaMemcpyHostToDevice, s));
-    RVB_CUDA(cudaGraphLaunch(host_graphs_.g2a, s));
+    static const char* uenv = std::getenv("ROBOVLN_UPLOAD_ORDER");
+    const bool rgb_first = (uenv != nullptr) ? std::strcmp(uenv, "rgb") == 0 : true;
+    if (rgb_first) {
+      // RGB frames first (default; measured 4.31 -> 4.24 ms with float32 frames, 4.13 -> 4.07 with uint8): the RGB
+      // trunk is the longest chain and the one that fills the GPU; the depth upload follows on the depth stream
+      RVB_CUDA(cudaMemcpyAsync(stage_rgb_, rgb, rgb_b, cudaMemcpyHostToDevice, s));
+      RVB_CUDA(cudaEventRecord(ev_aux_[0], s));
+      RVB_CUDA(cudaGraphLaunch(host_graphs_.g2a, s));
+      RVB_CUDA(cudaStreamWaitEvent(aux_, ev_aux_[0], 0));
+      RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, aux_));
+      RVB_CUDA(cudaGraphLaunch(host_graphs_.g1, aux_));
+      RVB_CUDA(cudaEventRecord(ev_aux_[1], aux_));
+    } else {
+      RVB_CUDA(cudaMemcpyAsync(stage_depth_, depth, dep_b, cudaMemcpyHostToDevice, s));
+      RVB_CUDA(cudaEventRecord(ev_aux_[0], s));
+      RVB_CUDA(cudaStreamWaitEvent(aux_, ev_aux_[0], 0));
+      RVB_CUDA(cudaGraphLaunch(host_graphs_.g1, aux_));
+      RVB_CUDA(cudaEventRecord(ev_aux_[1], aux_));
+      RVB_CUDA(cudaMemcpyAsync(stage_rgb_, rgb, rgb_b, cudaMemcpyHostToDevice, s));
+      RVB_CUDA(cudaGraphLaunch(host_graphs_.g2a, s));
+    }
     RVB_CUDA(cudaStreamWaitEvent(s, ev_upload_, 0));
     RVB_CUDA(cudaStreamWaitEvent(s, ev_aux_[1], 0));
     RVB_CUDA(cudaGraphLaunch(host_graphs_.g2b, s));
