@@ -163,44 +163,51 @@ __global__ void maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict_
 // [NB,Ho,Wo,32]  (resnet_policy.py:184-186, resnet.py:185-196).  fp32 math on CUDA cores:
 // 12.8 MFLOP per image.
 // ---------------------------------------------------------------------------------------
+constexpr int DS_ROWS = 8;   // output rows per CTA: the 49 x 32 weights and the overlapping input rows are staged once per 8 rows
 __global__ void __launch_bounds__(256) depth_stem_kernel(const float* __restrict__ depth, const float* __restrict__ w,
                                                          h16* __restrict__ out, int H, int W, int Hp, int Wp, int Ho,
                                                          int Wo) {
   RVB_PDL_PROLOGUE();
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* ws = reinterpret_cast<float*>(sm_raw);  // [49][32]
-  float* rows = ws + 49 * 32;                    // [7][Wp + 6]
+  float* rows = ws + 49 * 32;                    // [2*DS_ROWS + 5][Wp + 6] pooled input rows (zero padded)
   const int img = blockIdx.y;
-  const int ho = blockIdx.x;
+  const int ho0 = blockIdx.x * DS_ROWS;
   const int RW = Wp + 6;
+  constexpr int NR = 2 * DS_ROWS + 5;
   for (int i = threadIdx.x; i < 49 * 32; i += blockDim.x) {
     const int k = i / 32, ch = i % 32;
     ws[i] = w[ch * 49 + k];
   }
   const float* base = depth + static_cast<long long>(img) * H * W;
-  for (int i = threadIdx.x; i < 7 * RW; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NR * RW; i += blockDim.x) {
     const int r = i / RW;
     const int x = i - r * RW - 3;
-    const int hp = 2 * ho + r - 3;
+    const int hp = 2 * ho0 + r - 3;
     float v = 0.0f;
     if (hp >= 0 && hp < Hp && x >= 0 && x < Wp) {
-      const float* q = base + static_cast<long long>(2 * hp) * W + 2 * x;
-      v = 0.25f * (q[0] + q[1] + q[W] + q[W + 1]);
+      const float2 a = *reinterpret_cast<const float2*>(base + static_cast<long long>(2 * hp) * W + 2 * x);
+      const float2 b = *reinterpret_cast<const float2*>(base + static_cast<long long>(2 * hp + 1) * W + 2 * x);
+      v = 0.25f * (a.x + a.y + b.x + b.y);
     }
     rows[i] = v;
   }
   __syncthreads();
-  // thread = (channel, group of 4 consecutive output columns): per filter row the 13 inputs the four
+  // thread = (channel, group of 4 consecutive output columns) x output row: per filter row the 13 inputs the four
   // sliding windows share are read once and each weight feeds 4 FMAs (0.7 shared loads per FMA instead of 2)
   const int ch = threadIdx.x & 31;
-  for (int wg = threadIdx.x >> 5; wg * 4 < Wo; wg += blockDim.x >> 5) {
-    const int wo0 = wg * 4;
+  const int wgroups = (Wo + 3) / 4;
+  for (int item = threadIdx.x >> 5; item < DS_ROWS * wgroups; item += blockDim.x >> 5) {
+    const int ro = item / wgroups, wo0 = (item - ro * wgroups) * 4;
+    const int ho = ho0 + ro;
+    if (ho >= Ho) continue;
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int r = 0; r < 7; ++r) {
+      const float* rr = rows + (2 * ro + r) * RW + 2 * wo0;
       float x[13];
 #pragma unroll
-      for (int i = 0; i < 13; ++i) x[i] = (2 * wo0 + i < RW) ? rows[r * RW + 2 * wo0 + i] : 0.0f;
+      for (int i = 0; i < 13; ++i) x[i] = (2 * wo0 + i < RW) ? rr[i] : 0.0f;
 #pragma unroll
       for (int s = 0; s < 7; ++s) {
         const float wv = ws[(r * 7 + s) * 32 + ch];
@@ -832,8 +839,9 @@ void maxpool3x3s2(const h16* in, h16* out, int NB, int H, int W, int C, cudaStre
 void depth_stem_conv(const float* depth, const float* w, h16* out, int NB, int H, int W, cudaStream_t s) {
   const int Hp = H / 2, Wp = W / 2;
   const int Ho = (Hp + 6 - 7) / 2 + 1, Wo = (Wp + 6 - 7) / 2 + 1;
-  const size_t smem = (49 * 32 + 7 * (Wp + 6)) * sizeof(float);
-  dim3 grid(Ho, NB);
+  RVB_CHECK(W % 2 == 0, "depth stem: even width");
+  const size_t smem = (49 * 32 + (2 * DS_ROWS + 5) * (Wp + 6)) * sizeof(float);
+  dim3 grid((Ho + DS_ROWS - 1) / DS_ROWS, NB);
   launch_k(depth_stem_kernel, dim3(grid), dim3(256), smem, s, depth, w, out, H, W, Hp, Wp, Ho, Wo);
   RVB_CUDA(cudaGetLastError());
 }

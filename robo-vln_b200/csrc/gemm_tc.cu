@@ -26,6 +26,12 @@
 //   warps 2..9 = epilogue in two groups of four (one warp per TMEM lane quadrant); the groups
 //   take alternate 128-byte column chunks: tcgen05.ld -> bias / residual / ReLU|GELU ->
 //   128B-swizzled smem staging -> TMA store (coalesced, clipped at the tensor edges).
+// * Epilogue variants (third template parameter): 0 = bias / residual / activation; 1 = LayerNorm folded into the
+//   store (two passes over the TMEM accumulator with tcgen05.ld / tcgen05.st, row statistics exchanged between the
+//   N/256 CTAs of a row block over DSMEM or global memory); 2 = GroupNorm folded into the store for feature maps of
+//   <= 64 pixels (whole samples per tile: segmented warp-shuffle statistics) -- the depth trunk's layers 3-4.
+// * The RGB stem runs here too: a row-pair-interleaved padded image and an overlapping-window tensor map put two
+//   filter rows in every 64-wide K block ("window == 2").
 #include "common.cuh"
 #include "rvb.h"
 
