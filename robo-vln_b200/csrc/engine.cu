@@ -889,6 +889,7 @@ void Engine::tl_flush(cudaStream_t s) {
 void Engine::drop_graphs() {
   for (auto& g : graphs_) cudaGraphExecDestroy(g.exec);
   graphs_.clear();
+  graph_miss_streak_ = 0;
   for (HostGraphs& hg : host_graphs_) {
     if (hg.g1 != nullptr) cudaGraphExecDestroy(hg.g1);
     if (hg.g1b != nullptr) cudaGraphExecDestroy(hg.g1b);
@@ -937,7 +938,18 @@ void Engine::forward_policy_graphed(cudaStream_t s) {
   GraphEntry* hit = nullptr;
   for (auto& g : graphs_)
     if (std::memcmp(g.key, key, sizeof(key)) == 0) hit = &g;
+  if (hit == nullptr && graph_miss_streak_ >= 4) {
+    // callers that hand over fresh buffers on every call would pay a capture + instantiation per step: after four
+    // misses in a row run eagerly (every 64th call tries the cache again)
+    if ((++graph_miss_streak_ & 63) != 0) {
+      forward_policy(s);
+      copy_out();
+      args_ = user;
+      return;
+    }
+  }
   if (hit == nullptr) {
+    ++graph_miss_streak_;
     if (graphs_.size() >= 8) {   // evict the least recently used
       size_t lru = 0;
       for (size_t i = 1; i < graphs_.size(); ++i)
@@ -968,6 +980,7 @@ void Engine::forward_policy_graphed(cudaStream_t s) {
     graphs_.push_back(e);
     hit = &graphs_.back();
   }
+  else graph_miss_streak_ = 0;
   hit->last_use = ++graph_tick_;
   RVB_CUDA(cudaGraphLaunch(hit->exec, s));
   launches_ = hit->launches;
