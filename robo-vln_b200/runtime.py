@@ -385,6 +385,22 @@ class HcmRuntime:
         self._keep = (b16, r16, d16)
         return out
 
+    def encode_bert(self, instruction: torch.Tensor, B: int, n_envs: int = 1) -> torch.Tensor:
+        """BERT only (pre-computed visual features path): instruction [1|B, L] -> fp32 [1|B, L, 768]."""
+        instr = instruction.to(self.device)
+        if instr.dim() != 2 or instr.shape[0] not in (1, B):
+            raise ValueError("instruction must be [1 or B, L]")
+        self.sync_weights()
+        hw = (self._shape_key[4], self._shape_key[5]) if self._shape_key else ((256, 256), (256, 256))
+        N = n_envs if B % max(n_envs, 1) == 0 else 1
+        self.ensure_plan(B, N, instr.shape[1], instr.shape[0], hw[0], hw[1])
+        i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
+        i_i64 = instr.contiguous() if instr.dtype == torch.int64 else None
+        with torch.cuda.device(self.device):
+            check(self.lib.hcm_run_bert(self.handle, _ptr(i_f32), _ptr(i_i64), self._stream()), "hcm_run_bert")
+        self._keep = (i_f32, i_i64)
+        return self.get_buffer("bert").float()
+
     def get_buffer(self, name: str) -> torch.Tensor:
         """Copy of an internal stage buffer (parity tests)."""
         ptr = ctypes.c_void_p()

@@ -62,10 +62,32 @@ class Seq2Seq_HighLevel_CMA(HcmModuleBase):
         -> (logits [B,4], rnn_hidden_states [2,N,512])"""
         observations, rnn_hidden_states, prev_actions, masks = batch
         del batch
-        if "rgb_features" in observations or "depth_features" in observations:
-            raise NotImplementedError("pre-computed rgb_features/depth_features are not supported yet")
         instruction = observations["instruction"]
         rt = self.runtime()
+        if "rgb_features" in observations or "depth_features" in observations:
+            # pre-computed trunk outputs (resnet_encoders.py:83-84,207-208): rgb_features [B,2048,4,4] (after the
+            # adaptive pool), depth_features [B,128,4,4].  BERT (and a trunk whose features are not given) still
+            # run on the engine; the tail runs as torch ops on the GPU (autograd-capable, like the training path).
+            from . import torch_tail
+
+            dev = rt.device
+            have_r, have_d = "rgb_features" in observations, "depth_features" in observations
+            n_envs = rnn_hidden_states.shape[1]
+            if have_r and have_d:
+                B = observations["rgb_features"].shape[0]
+                feats = {"bert": rt.encode_bert(instruction, B, n_envs)}
+            else:
+                feats = rt.encode(observations["rgb"], observations["depth"], instruction, n_envs=n_envs)
+            if have_r:
+                feats["rgb_feat"] = observations["rgb_features"].to(dev, torch.float32).flatten(2).permute(0, 2, 1)
+            if have_d:
+                feats["depth_feat"] = observations["depth_features"].to(dev, torch.float32).flatten(2).permute(0, 2, 1)
+            with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+                logits, hidden = torch_tail.hi_tail(self, feats["rgb_feat"], feats["depth_feat"], feats["bert"],
+                                                    rnn_hidden_states.to(dev, torch.float32), masks.to(dev, torch.float32),
+                                                    self.dropout_p)
+            del observations["instruction"]
+            return logits, hidden
         if self.training and torch.is_grad_enabled():
             # training step (hierarchical_trainer.py:506-513): frozen encoders on the engine, the
             # trainable tail under autograd (torch_tail.py).  BatchNorm stays in eval mode -- the

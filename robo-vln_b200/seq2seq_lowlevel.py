@@ -31,9 +31,25 @@ class Seq2Seq_LowLevel(HcmModuleBase):
         -> (actions [B,2], stop_logit [B,1], rnn_hidden_states [2,N,512])"""
         observations, rnn_hidden_states, prev_actions, masks, discrete_actions = batch
         del batch
-        if "rgb_features" in observations or "depth_features" in observations:
-            raise NotImplementedError("pre-computed rgb_features/depth_features are not supported yet")
         rt = self.runtime()
+        if "rgb_features" in observations or "depth_features" in observations:
+            # pre-computed trunk outputs (resnet_encoders.py:83-84,207-208): rgb_features [B,2048(,1,1)] (global
+            # average pool), depth_features [B,128,4,4]; the tail runs as torch ops on the GPU
+            from . import torch_tail
+
+            dev = rt.device
+            have_r, have_d = "rgb_features" in observations, "depth_features" in observations
+            feats = {}
+            if not (have_r and have_d):
+                feats = rt.encode(observations["rgb"], observations["depth"], None, n_envs=rnn_hidden_states.shape[1],
+                                  use_lo_weights=True)
+            if have_r:
+                feats["rgb_gmean"] = observations["rgb_features"].to(dev, torch.float32).flatten(1)
+            if have_d:
+                feats["depth_feat"] = observations["depth_features"].to(dev, torch.float32).flatten(2).permute(0, 2, 1)
+            with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+                return torch_tail.lo_tail(self, feats["rgb_gmean"], feats["depth_feat"], rnn_hidden_states.to(dev, torch.float32),
+                                          masks.to(dev, torch.float32), discrete_actions.to(dev))
         if self.training and torch.is_grad_enabled():
             # training step (hierarchical_trainer.py:539-555): see Seq2Seq_HighLevel_CMA.forward
             from . import torch_tail

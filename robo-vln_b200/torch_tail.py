@@ -73,7 +73,7 @@ def lstm_state_encoder(rnn, x: torch.Tensor, hidden: torch.Tensor, masks: torch.
     m = masks.view(T, N)
     starts = [0] + ([t + 1 for t, v in enumerate((m[1:] == 0.0).any(dim=1).tolist()) if v] if T > 1 else [])
     xs = x.view(T, N, -1)
-    weights = [rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0]
+    weights = [rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0]   # cuDNN re-packs them per call (warning is benign)
     h, c = hidden[0:1], hidden[1:2]
     outs = []
     for i, t0 in enumerate(starts):

@@ -236,6 +236,39 @@ def test_uint8_rgb_ingest_matches_float(models):
         assert torch.equal(o["hidden_lo"], ref[4].cpu())
 
 
+def test_precomputed_visual_features(models):
+    """observations["rgb_features"] / ["depth_features"] (resnet_encoders.py:83-84,207-208) bypass the trunks: features
+    taken from the oracle's trunks must give the oracle's outputs (BERT still runs on the engine)."""
+    from oracle import hcm_oracle as O
+    from oracle import weights as W
+
+    hi, lo, sd_hi, sd_lo = models
+    inp = W.make_inputs(B=3, L=14, N=1, rgb_hw=256, seed=41, mask_zero_rows=(0,))
+    dev = "cuda"
+    with torch.no_grad():
+        r_logits, r_hid, it = O.hi_forward(sd_hi, inp["rgb"], inp["depth"], inp["instruction"], inp["hidden_hi"], inp["masks"],
+                                           return_intermediates=True)
+        r_act, r_stop, r_hl = O.lo_forward(sd_lo, inp["rgb"], inp["depth"], inp["hidden_lo"], inp["masks"], inp["sub_goal"])
+        rgb_f = it["rgb_embedding"].view(3, 2112, 4, 4)[:, :2048].contiguous()
+        dep_f = it["depth_embedding"].view(3, 192, 4, 4)[:, :128].contiguous()
+        rgb_g = O.rgb_trunk(sd_lo, "rgb_encoder.", inp["rgb"]).mean(dim=(2, 3), keepdim=True)
+        obs = {"rgb_features": rgb_f.to(dev), "depth_features": dep_f.to(dev), "instruction": inp["instruction"].to(dev)}
+        logits, hid = hi((obs, inp["hidden_hi"].to(dev), None, inp["masks"].to(dev)))
+        assert "instruction" not in obs
+        _out(logits, r_logits, "logits (precomputed features)")
+        _out(hid, r_hid, "hidden (precomputed features)")
+        # one of the two given: the other trunk runs on the engine
+        obs = {"rgb": inp["rgb"].to(dev), "depth": inp["depth"].to(dev), "depth_features": dep_f.to(dev),
+               "instruction": inp["instruction"].to(dev)}
+        logits2, _ = hi((obs, inp["hidden_hi"].to(dev), None, inp["masks"].to(dev)))
+        _out(logits2, r_logits, "logits (depth features only)")
+        obs = {"rgb_features": rgb_g.to(dev), "depth_features": dep_f.to(dev)}
+        act, stop, hl = lo((obs, inp["hidden_lo"].to(dev), None, inp["masks"].to(dev), inp["sub_goal"].to(dev)))
+        _out(act, r_act, "actions (precomputed features)")
+        _out(stop, r_stop, "stop (precomputed features)")
+        _out(hl, r_hl, "hidden_lo (precomputed features)")
+
+
 def test_graph_replay_matches_eager(models):
     """HcmPolicy.act / act_host replay a captured CUDA graph from the second call with the same input
     pointers on; replays must reproduce the eager (first) call bit for bit, follow NEW input values
