@@ -88,7 +88,7 @@ int hcm_forward_hi(hcm_engine* e, const float* rgb, const float* depth, const fl
     a.rgb = rgb; a.depth = depth; a.instr_f32 = instr_f32; a.instr_i64 = instr_i64;
     a.masks = masks; a.mask_stride = mask_stride; a.hc_hi_in = hc_in; a.hc_hi_out = hc_out; a.logits = logits;
     e->eng.args_ = a;
-    e->eng.forward_hi(S(stream));
+    e->eng.forward_hi_graphed(S(stream));
   });
 }
 

@@ -900,31 +900,45 @@ void Engine::drop_graphs() {
   eager_runs_ = 0;
 }
 
-void Engine::forward_policy_graphed(cudaStream_t s) {
+void Engine::forward_policy_graphed(cudaStream_t s) { forward_graphed(0, s); }
+void Engine::forward_hi_graphed(cudaStream_t s) { forward_graphed(1, s); }
+
+// kind 0: hi -> argmax -> lo (forward_policy); kind 1: hi only (forward_hi, the module API's first call)
+void Engine::forward_graphed(int kind, cudaStream_t s) {
   static const char* env = std::getenv("ROBOVLN_GRAPH");
   const bool enabled = !(env != nullptr && std::strcmp(env, "0") == 0) && multi_stream_;
+  auto forward_policy = [this, kind](cudaStream_t st) {   // the body that is run eagerly or captured
+    if (kind == 0) this->forward_policy(st);
+    else this->forward_hi(st);
+  };
   if (!enabled) {
     forward_policy(s);
     return;
   }
-  RVB_CHECK(planned_ && have_hi_ && have_lo_ && lo_shares_trunks_, "forward_policy needs a planned hi+lo engine with shared trunks");
+  if (kind == 0)
+    RVB_CHECK(planned_ && have_hi_ && have_lo_ && lo_shares_trunks_, "forward_policy needs a planned hi+lo engine with shared trunks");
+  else
+    RVB_CHECK(planned_ && have_hi_, "forward_hi: engine not planned or hi weights missing");
   const RunArgs user = args_;
   const int B = shp_.B, N = shp_.N;
   // the graph writes engine-owned buffers; the caller's (fresh every call) get small device copies
-  args_.logits = logits_buf_; args_.actions = act_buf_; args_.stop = stop_buf_;
-  args_.hc_hi_out = hc_hi_buf_; args_.hc_lo_out = hc_lo_buf_; args_.sub_goal_out = subgoal_buf_;
+  args_.logits = logits_buf_; args_.hc_hi_out = hc_hi_buf_;
+  if (kind == 0) {
+    args_.actions = act_buf_; args_.stop = stop_buf_; args_.hc_lo_out = hc_lo_buf_; args_.sub_goal_out = subgoal_buf_;
+  }
   auto copy_out = [&]() {
     if (user.logits == logits_buf_) return;   // host entry: results are read from the engine's buffers directly
     const size_t hc_b = 2ull * N * 512 * 4;
     RVB_CUDA(cudaMemcpyAsync(user.logits, logits_buf_, static_cast<size_t>(B) * 16, cudaMemcpyDeviceToDevice, s));
+    RVB_CUDA(cudaMemcpyAsync(user.hc_hi_out, hc_hi_buf_, hc_b, cudaMemcpyDeviceToDevice, s));
+    if (kind != 0) return;
     RVB_CUDA(cudaMemcpyAsync(user.actions, act_buf_, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, s));
     RVB_CUDA(cudaMemcpyAsync(user.stop, stop_buf_, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, s));
-    RVB_CUDA(cudaMemcpyAsync(user.hc_hi_out, hc_hi_buf_, hc_b, cudaMemcpyDeviceToDevice, s));
     RVB_CUDA(cudaMemcpyAsync(user.hc_lo_out, hc_lo_buf_, hc_b, cudaMemcpyDeviceToDevice, s));
     if (user.sub_goal_out != nullptr)
       RVB_CUDA(cudaMemcpyAsync(user.sub_goal_out, subgoal_buf_, static_cast<size_t>(B) * 8, cudaMemcpyDeviceToDevice, s));
   };
-  RVB_CHECK(user.hc_hi_in != hc_hi_buf_ && user.hc_lo_in != hc_lo_buf_, "hidden state in/out must not alias");
+  RVB_CHECK(user.hc_hi_in != hc_hi_buf_ && (kind != 0 || user.hc_lo_in != hc_lo_buf_), "hidden state in/out must not alias");
   if (eager_runs_ < 1) {   // first call after planning runs eagerly: one-time kernel attribute setup is not capturable
     forward_policy(s);
     ++eager_runs_;
@@ -934,7 +948,7 @@ void Engine::forward_policy_graphed(cudaStream_t s) {
   }
   const void* key[8] = {user.rgb, user.depth, user.instr_f32, user.instr_i64, user.masks,
                         reinterpret_cast<const void*>(static_cast<uintptr_t>(user.mask_stride) | (static_cast<uintptr_t>(rgb_fmt_) << 16)),
-                        user.hc_hi_in, user.hc_lo_in};
+                        user.hc_hi_in, kind == 0 ? static_cast<const void*>(user.hc_lo_in) : reinterpret_cast<const void*>(uintptr_t(1))};
   GraphEntry* hit = nullptr;
   for (auto& g : graphs_)
     if (std::memcmp(g.key, key, sizeof(key)) == 0) hit = &g;

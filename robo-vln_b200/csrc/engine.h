@@ -72,6 +72,8 @@ class Engine {
   // forward_policy replayed from a CUDA graph (captured once per distinct set of input pointers; outputs go
   // through engine-owned buffers and are copied to the caller's).  ROBOVLN_GRAPH=0 disables.
   void forward_policy_graphed(cudaStream_t s);
+  void forward_hi_graphed(cudaStream_t s);     // the module API's hi call (hierarchical_trainer.py:1096-1097), same cache
+  void forward_graphed(int kind, cudaStream_t s);
   void forward_policy_host(const float* rgb, const float* depth, const float* instr, const float* masks,
                            const float* hc_hi_in, const float* hc_lo_in, float* logits, float* actions, float* stop,
                            float* hc_hi_out, float* hc_lo_out, cudaStream_t s);
