@@ -723,6 +723,9 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
       auto lvl = [&](int o) { return prio ? std::min(prio_lo, prio_hi + o) : prio_lo; };
       const int p_depth = lvl(od);
       const int p_bert = lvl(ob);
+      // explicit per-launch priorities (captured into the graphs' kernel nodes): ROBOVLN_NODE_PRIO=1
+      static const char* nenv = std::getenv("ROBOVLN_NODE_PRIO");
+      if (nenv != nullptr && std::strcmp(nenv, "1") == 0) { node_prio_[0] = p_depth; node_prio_[1] = p_bert; }
       RVB_CUDA(cudaStreamCreateWithPriority(&side_[0], cudaStreamNonBlocking, p_depth));
       RVB_CUDA(cudaStreamCreateWithPriority(&side_[1], cudaStreamNonBlocking, p_bert));
       RVB_CUDA(cudaStreamCreateWithPriority(&capture_, cudaStreamNonBlocking, lvl(orr)));
@@ -795,8 +798,11 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool 
   }
   while (ir < rgb.size() || id < dep.size() || ib < nb) {
     if (ir < rgb.size()) { launches_ += (*rgb[ir])(s); tl_mark(0, &rgb[ir]->name, s); ++ir; }
+    g_launch_prio = node_prio_[1];
     if (ib < nb) { launches_ += (*bert[ib])(side_[1]); tl_mark(2, &bert[ib]->name, side_[1]); ++ib; }
+    g_launch_prio = node_prio_[0];
     for (int k = 0; k < 3 && id < dep.size(); ++k) { launches_ += (*dep[id])(side_[0]); tl_mark(1, &dep[id]->name, side_[0]); ++id; }
+    g_launch_prio = 0;
   }
   if (!dep.empty()) {
     RVB_CUDA(cudaEventRecord(events_[1], side_[0]));

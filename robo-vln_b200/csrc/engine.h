@@ -159,6 +159,7 @@ class Engine {
   } host_graphs_[2];   // per RGB input format
   int enc_mask_ = 7;             // run_encoders: 1 = RGB, 2 = depth, 4 = BERT branches (graph capture of subsets)
   uint64_t graph_tick_ = 0;
+  int node_prio_[2] = {0, 0};    // per-launch priority attribute for depth / BERT ops (0 = none)
   int graph_miss_streak_ = 0;    // consecutive graph-cache misses (fresh pointers every call -> eager fallback)
   int eager_runs_ = 0;           // eager forward_policy calls since the last plan (kernels' one-time setup)
   void drop_graphs();

@@ -887,8 +887,13 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int na = 0;
+  if (g_launch_prio != 0) {
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = g_launch_prio;
+    ++na;
+  }
   const int cluster_x = (CTAS == 2) ? 2 : ((EPI == 1 && !plan.p.ln_xchg) ? plan.p.n_tiles : 1);
   if (cluster_x > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
@@ -937,6 +942,7 @@ bool use_direct_epilogue() {
 }  // namespace
 
 thread_local int g_pdl_override = -1;
+thread_local int g_launch_prio = 0;
 
 void tma_encode_2d_h16(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_cols,
                        uint32_t box_rows) {

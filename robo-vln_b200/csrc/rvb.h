@@ -38,7 +38,8 @@ struct Error : public std::runtime_error {
 // library calls griddepcontrol.wait before touching data a predecessor may still be writing.
 // ROBOVLN_PDL=0 launches plainly (validation).
 bool use_pdl();
-extern thread_local int g_pdl_override;   // -1: environment default; 0 / 1: forced for the launches that follow
+extern thread_local int g_pdl_override;
+extern thread_local int g_launch_prio;    // 0: none; otherwise cudaLaunchAttributePriority for the launches that follow   // -1: environment default; 0 / 1: forced for the launches that follow
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg;
@@ -46,11 +47,20 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (use_pdl()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_launch_prio != 0) {
+    at[na].id = cudaLaunchAttributePriority;
+    at[na].val.priority = g_launch_prio;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = na;
   RVB_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
 }
 
