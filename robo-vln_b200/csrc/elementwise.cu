@@ -127,8 +127,20 @@ __global__ void __launch_bounds__(256) rgb_pad_convert4_kernel(const T* __restri
 // ---------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 max pooling, NHWC h16
 // ---------------------------------------------------------------------------------------
-__global__ void maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict__ out, int NB, int H, int W, int C,
-                                    int Ho, int Wo) {
+RVB_DEVICE uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+#if RVB_BF16
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+#else
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+#endif
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// One thread per (output pixel, 8-channel vector): the nine 16-byte taps are loaded up front (taps that fall
+// outside the image are redirected to the centre tap, which is always inside, so no -inf and no branches) and
+// reduced with packed 16-bit max.
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict__ out, int NB, int H,
+                                                           int W, int C, int Ho, int Wo) {
   RVB_PDL_PROLOGUE();
   const int cv = C / 8;
   const long long total = static_cast<long long>(NB) * Ho * Wo * cv;
@@ -139,22 +151,26 @@ __global__ void maxpool3x3s2_kernel(const h16* __restrict__ in, h16* __restrict_
     const int wo = static_cast<int>(pix % Wo);
     const int ho = static_cast<int>((pix / Wo) % Ho);
     const int img = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
-    float m[8];
+    const h16* base = in + static_cast<long long>(img) * H * W * C + v * 8;
+    uint4 t[9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
     for (int r = 0; r < 3; ++r) {
-      const int h = 2 * ho + r - 1;
-      if (h < 0 || h >= H) continue;
-      for (int s = 0; s < 3; ++s) {
-        const int w = 2 * wo + s - 1;
-        if (w < 0 || w >= W) continue;
-        float f[8];
-        load8(in + ((static_cast<long long>(img) * H + h) * W + w) * C + v * 8, f);
+      int h = 2 * ho + r - 1;
+      h = (h < 0 || h >= H) ? 2 * ho : h;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      for (int s = 0; s < 3; ++s) {
+        int w = 2 * wo + s - 1;
+        w = (w < 0 || w >= W) ? 2 * wo : w;
+        t[r * 3 + s] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(h) * W + w) * C));
       }
     }
-    store8(out + pix * C + v * 8, m);
+    uint4 m = t[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) {
+      m.x = hmax2_u32(m.x, t[k].x); m.y = hmax2_u32(m.y, t[k].y);
+      m.z = hmax2_u32(m.z, t[k].z); m.w = hmax2_u32(m.w, t[k].w);
+    }
+    *reinterpret_cast<uint4*>(out + pix * C + v * 8) = m;
   }
 }
 
