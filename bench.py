@@ -5,11 +5,14 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
     python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host CPU
 
-One "step" = one policy forward over one batch of synthetic observations: 64 environments per
-GPU (rollout-shaped: N=64, T=1), 256x256 RGB + 256x256 depth + an 80-token instruction per
-environment (64 distinct instructions), through hi AND lo.  With N GPUs every rank runs its own
-64 environments (weak scaling; N=8 is BASELINE.json configs[3], 512 environments) and the only
-collective is the all-gather of the packed [B,7] outputs, inside the timed region.
+One "step" = one policy forward over one batch of synthetic observations (rollout-shaped: N=B, T=1),
+256x256 RGB + 256x256 depth + an 80-token instruction per environment (all instructions distinct),
+through hi AND lo.
+  --gpus 1 : BASELINE.json configs[1], 64 environments on one B200 (the configuration the metric is quoted on);
+             the line also carries `strong_scaling_base`: the 512-environment batch of configs[3] on this ONE GPU.
+  --gpus N : BASELINE.json configs[3], STRONG scaling: a fixed global batch of 512 environments sharded over the
+             ranks (512/N each; 64 per GPU at N=8), one all-gather of the packed [512,7] outputs inside the timed
+             region.  `--scaling weak` keeps 64 environments per rank instead.
 
 Prints ONE JSON line (rank 0).  See the task contract for the keys.
 """
@@ -29,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 GFLOP_PER_OBS = 25.29          # algorithmic, SURVEY.md 8(d) / BASELINE.md section 3 (L=80, trunks shared, BERT per row)
 METRIC = "policy_forward_obs_per_sec"
+STRONG_GLOBAL_BATCH = 512      # BASELINE.json configs[3]
 
 
 def _peaks():
@@ -123,26 +127,161 @@ def cpu_oracle_obs_per_sec(sample_rows: int, L: int, steps: int, warmup: int):
     return sample_rows * steps / total, total / steps * 1e3, cores
 
 
+def batch_plan(args, world: int):
+    """(per-rank batch, global batch, scaling label) for this launch."""
+    if world == 1:
+        return args.batch, args.batch, "strong"
+    if args.scaling == "weak":
+        return args.batch, args.batch * world, "weak"
+    if STRONG_GLOBAL_BATCH % world != 0:
+        raise SystemExit("bench.py: --gpus must divide the %d-environment global batch" % STRONG_GLOBAL_BATCH)
+    return STRONG_GLOBAL_BATCH // world, STRONG_GLOBAL_BATCH, "strong"
+
+
+def make_config(args, world: int):
+    """The `config` object of the JSON line -- identical for both arms (--impl b200 / reference) at a given N."""
+    B, G, scaling = batch_plan(args, world)
+    if world == 1:
+        wl = ("cfg2: HCM policy forward (hi -> argmax -> lo), batch=%d rollout-shaped (N=%d,T=1), 256x256 RGB + 256x256 depth, "
+              "%d distinct %d-token instructions, random-init weights" % (B, B, B, args.seq_len))
+    else:
+        wl = ("cfg4: HCM policy forward (hi -> argmax -> lo), global batch=%d rollout-shaped sharded over %d GPUs (%d/GPU, %s "
+              "scaling), 256x256 RGB + 256x256 depth, distinct %d-token instructions, one all-gather of the [%d,7] outputs, "
+              "random-init weights" % (G, world, B, scaling, args.seq_len, G))
+    return {"workload": wl, "per_gpu_batch": B, "global_batch": G, "seq_len": args.seq_len, "parallelism": "dp%d" % world,
+            "l2": "3 rotating input sets and a per-step working set of ~36 MB per observation vs 126 MB L2"}, scaling
+
+
 def run_reference(args):
+    """Reference arm: the reference's own algorithm (fp32 PyTorch CPU, the oracle port pinned to the unmodified
+    reference's outputs) on the box's host cores, every step one FULL per-GPU batch of the benchmark configuration
+    (64 observations by default; at N>1 rank 0 alone runs a 64-observation sample of the global batch)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     rows = args.cpu_sample_rows
-    v, ms, cores = cpu_oracle_obs_per_sec(rows, args.seq_len, args.steps, max(1, min(args.warmup, 3)))
+    v, ms, cores = cpu_oracle_obs_per_sec(rows, args.seq_len, args.steps, args.warmup)
+    config, scaling = make_config(args, world)
+    B, G, _ = batch_plan(args, world)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "obs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: HCM policy forward (hi+lo), 256x256 RGB-D, L=%d, rollout-shaped" % args.seq_len,
-                   "per_gpu_batch": args.batch, "seq_len": args.seq_len,
-                   "note": "CPU arm: each step is a %d-observation sample of the batch" % rows},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": v, "unit": "obs/s", "cores": cores, "kind": "port",
-                         "sample": "%d observations/step x %d steps, oracle/hcm_oracle.py (fp32 torch CPU restatement "
-                                   "of the reference modules; the Python reference itself cannot travel to the box)" % (rows, args.steps)},
+                         "sample": "%d observations/step (%s) x %d steps (+%d warm-up), hi AND lo each running its own trunks as "
+                                   "the reference executes them; oracle/hcm_oracle.py (fp32 torch CPU restatement pinned to the "
+                                   "unmodified reference's outputs; the Python reference itself cannot travel to the box)"
+                                   % (rows, "the full batch" if rows == G else "a sample of the %d-observation batch" % G,
+                                      args.steps, args.warmup)},
         "e2e": {"value": v, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class PolicyBench:
+    """Synthetic inputs + timed loops for one per-rank batch size."""
+
+    def __init__(self, policy, B, L, dev, rank, world, global_rows, n_sets=3, host=True):
+        import torch
+
+        self.torch = torch
+        self.policy, self.B, self.L, self.dev, self.world, self.global_rows = policy, B, L, dev, world, global_rows
+        self.n_sets = n_sets
+        g = torch.Generator(device="cpu")
+        g.manual_seed(1 + rank)
+        N = B
+
+        def make_host_set():
+            ids = torch.randint(1000, 30522, (B, L), generator=g).float()
+            ids[:, 0] = 101
+            ids[:, -1] = 102
+            masks = torch.ones((B, 2))
+            masks[::7] = 0.0
+            pin = (lambda t: t.pin_memory()) if host else (lambda t: t)
+            rgb8 = torch.randint(0, 256, (B, 256, 256, 3), generator=g, dtype=torch.uint8)
+            return {
+                "rgb_u8": pin(rgb8), "rgb": pin(rgb8.float()),      # the sensor's uint8 frames / batch_obs' float32 copy of them
+                "depth": pin(torch.rand((B, 256, 256, 1), generator=g)),
+                "instruction": pin(ids), "masks": pin(masks),
+                "hidden_hi": pin(torch.randn((2, N, 512), generator=g) * 0.1),
+                "hidden_lo": pin(torch.randn((2, N, 512), generator=g) * 0.1),
+            }
+
+        self.host_sets = [make_host_set() for _ in range(n_sets)]
+        self.dev_sets = [{k: v.to(dev) for k, v in hs.items() if k != "rgb_u8"} for hs in self.host_sets]
+        self.out = None
+
+    def barrier(self):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _max_over_ranks(self, ms):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            t = self.torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_device(self, i):
+        from robovln_b200 import sharding
+
+        d = self.dev_sets[i % self.n_sets]
+        obs = {"rgb": d["rgb"], "depth": d["depth"], "instruction": d["instruction"]}
+        logits, act, stop, hh, hl, sub = self.policy.act(obs, d["hidden_hi"], d["hidden_lo"], d["masks"])
+        packed = sharding.pack_outputs(logits, act, stop)
+        if self.world > 1:
+            packed = sharding.all_gather_outputs(packed, self.global_rows)
+        return packed
+
+    def time_device(self, steps, warmup, sampler=None):
+        """device-resident inputs: ms per step (max over ranks), last output"""
+        torch = self.torch
+        for i in range(warmup):
+            self.step_device(i)
+        self.barrier()
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for i in range(steps):
+            out = self.step_device(i)
+        e1.record()
+        self.barrier()
+        return self._max_over_ranks(e0.elapsed_time(e1)) / steps, out
+
+    def time_host(self, steps, rgb_key):
+        """host (pinned) buffers -> H2D + forward + D2H inside policy.act_host; the step's result is read on the host"""
+        torch = self.torch
+        host_out = self.out
+        for i in range(3):
+            hs = self.host_sets[i % self.n_sets]
+            host_out = self.policy.act_host(hs[rgb_key], hs["depth"], hs["instruction"], hs["masks"], hs["hidden_hi"], hs["hidden_lo"], out=host_out)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            hs = self.host_sets[i % self.n_sets]
+            host_out = self.policy.act_host(hs[rgb_key], hs["depth"], hs["instruction"], hs["masks"], hs["hidden_hi"], hs["hidden_lo"], out=host_out)
+            _ = float(host_out["logits"][0, 0])          # the step's result is read on the host
+        e1.record()
+        self.barrier()
+        self.out = host_out
+        return self._max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def h2d_bytes(self, rgb_bytes_per_px):
+        B, L = self.B, self.L
+        return B * (256 * 256 * 3 * rgb_bytes_per_px + 256 * 256 * 4 + L * 4 + 2 * 4) + 2 * (2 * B * 512 * 4)
+
+    def d2h_bytes(self):
+        return self.B * (4 + 2 + 1) * 4 + 2 * (2 * self.B * 512 * 4)
 
 
 def run_b200(args):
@@ -163,122 +302,36 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     import robovln_b200 as R
-    from robovln_b200 import sharding
 
-    B, L = args.batch, args.seq_len
-    N = B                                   # rollout-shaped: one step of B environments
+    L = args.seq_len
+    B, global_rows, _ = batch_plan(args, world)
+    config, scaling = make_config(args, world)
+    warmup = max(args.warmup, 3)
     policy = R.HcmPolicy().share_frozen_trunks().to(dev).eval()
     rt = policy._runtime()
-
-    g = torch.Generator(device="cpu")
-    g.manual_seed(1 + rank)
-    n_sets = 3                              # rotating input sets: 3 x 67 MB > 126 MB L2
-
-    def make_host_set():
-        ids = torch.randint(1000, 30522, (B, L), generator=g).float()
-        ids[:, 0] = 101
-        ids[:, -1] = 102
-        masks = torch.ones((B, 2))
-        masks[::7] = 0.0
-        return {
-            "rgb": torch.randint(0, 256, (B, 256, 256, 3), generator=g).float().pin_memory(),
-            "depth": torch.rand((B, 256, 256, 1), generator=g).pin_memory(),
-            "instruction": ids.pin_memory(), "masks": masks.pin_memory(),
-            "hidden_hi": (torch.randn((2, N, 512), generator=g) * 0.1).pin_memory(),
-            "hidden_lo": (torch.randn((2, N, 512), generator=g) * 0.1).pin_memory(),
-        }
-
-    host_sets = [make_host_set() for _ in range(n_sets)]
-    dev_sets = [{k: v.to(dev) for k, v in hs.items()} for hs in host_sets]
-    global_rows = B * world
-
-    def step_device(i):
-        d = dev_sets[i % n_sets]
-        obs = {"rgb": d["rgb"], "depth": d["depth"], "instruction": d["instruction"]}
-        logits, act, stop, hh, hl, sub = policy.act(obs, d["hidden_hi"], d["hidden_lo"], d["masks"])
-        packed = sharding.pack_outputs(logits, act, stop)
-        if world > 1:
-            packed = sharding.all_gather_outputs(packed, global_rows)
-        return packed
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    pb = PolicyBench(policy, B, L, dev, rank, world, global_rows)
 
     # ---- device-resident throughput ("value") ---------------------------------------------
-    for i in range(max(args.warmup, 3)):
-        step_device(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        out = step_device(i)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step, out = pb.time_device(args.steps, warmup, sampler)
     launches = rt.launches() * args.steps + (args.steps if world > 1 else 0)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
     value = global_rows / (ms_step * 1e-3)
     finite = bool(torch.isfinite(out).all().item())
 
     # ---- end to end through the host-buffer API (H2D + forward + D2H per step) --------------
-    host_out = None
-    for i in range(3):
-        host_out = policy.act_host(**{k: host_sets[i % n_sets][k] for k in ("rgb", "depth", "instruction", "masks", "hidden_hi", "hidden_lo")}, out=host_out)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        hs = host_sets[i % n_sets]
-        host_out = policy.act_host(hs["rgb"], hs["depth"], hs["instruction"], hs["masks"], hs["hidden_hi"], hs["hidden_lo"], out=host_out)
-        _ = float(host_out["logits"][0, 0])          # the step's result is read on the host
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = global_rows / (ms_e2e / args.steps * 1e-3)
-    # same call with the RGB frames as uint8 (observation ingest): a quarter of the RGB bytes
-    e2e_u8 = None
-    try:
-        u8_sets = [hs["rgb"].to(torch.uint8).pin_memory() for hs in host_sets]
-        for i in range(3):
-            hs = host_sets[i % n_sets]
-            host_out = policy.act_host(u8_sets[i % n_sets], hs["depth"], hs["instruction"], hs["masks"], hs["hidden_hi"], hs["hidden_lo"], out=host_out)
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            hs = host_sets[i % n_sets]
-            host_out = policy.act_host(u8_sets[i % n_sets], hs["depth"], hs["instruction"], hs["masks"], hs["hidden_hi"], hs["hidden_lo"], out=host_out)
-            _ = float(host_out["logits"][0, 0])
-        e1.record()
-        barrier()
-        ms_u8 = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms_u8], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_u8 = float(t.item())
-        e2e_u8 = {"value": global_rows / (ms_u8 / args.steps * 1e-3), "unit": "obs/s", "ms_per_step": ms_u8 / args.steps,
-                  "h2d_bytes_per_step": B * (256 * 256 * 3 + 256 * 256 * 4 + L * 4 + 2 * 4) + 2 * (2 * N * 512 * 4)}
-    except Exception as exc:
-        e2e_u8 = {"error": str(exc)[:200]}
-    h2d = B * (256 * 256 * 3 * 4 + 256 * 256 * 4 + L * 4 + 2 * 4) + 2 * (2 * N * 512 * 4)
-    d2h = B * (4 + 2 + 1) * 4 + 2 * (2 * N * 512 * 4)
+    # headline: the RGB frames as the simulator's sensor delivers them (uint8); secondary: the
+    # float32 0..255 copies the reference's batch_obs makes of them (4x the RGB bytes)
+    ms_u8 = pb.time_host(args.steps, "rgb_u8")
+    ms_f32 = pb.time_host(args.steps, "rgb")
+    e2e = {"value": global_rows / (ms_u8 * 1e-3), "unit": "obs/s", "h2d_bytes_per_step": pb.h2d_bytes(1),
+           "d2h_bytes_per_step": pb.d2h_bytes(), "ms_per_step": ms_u8, "rgb_frames": "uint8 [B,256,256,3] (sensor format)",
+           "float32_rgb_frames": {"value": global_rows / (ms_f32 * 1e-3), "unit": "obs/s", "ms_per_step": ms_f32,
+                                  "h2d_bytes_per_step": pb.h2d_bytes(4)}}
 
     # ---- per-launch profile of one step -> roofline of the dominant kernel ------------------
     peaks = _peaks()
-    d = dev_sets[0]
+    d = pb.dev_sets[0]
     rt.profile_policy(d["rgb"], d["depth"], d["instruction"], d["masks"], d["hidden_hi"], d["hidden_lo"])      # warm
     ops = rt.profile_policy(d["rgb"], d["depth"], d["instruction"], d["masks"], d["hidden_hi"], d["hidden_lo"])
     gemm_ms = sum(o["ms"] for o in ops if o["flops"] > 0)
@@ -287,18 +340,22 @@ def run_b200(args):
     all_ms = sum(o["ms"] for o in ops)
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tp):          # dram__bytes_read.sum + dram__bytes_write.sum per gemm_tc launch, from the committed ncu pass
-        try:
-            traffic = float(json.load(open(tp))["dram_bytes_per_launch"])
-        except Exception:
-            traffic = None
+    traffic_src = None
+    for tp in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tp):          # dram__bytes_read.sum + dram__bytes_write.sum per tensor-core launch, from the committed ncu pass
+            try:
+                traffic = float(json.load(open(tp))["dram_bytes_per_launch"])
+                traffic_src = os.path.basename(tp)
+                break
+            except Exception:
+                traffic = None
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM), %d launches/step" % n_gemm,
+        "bound": "tensor", "kernel": "tcgen05 kernels (gemm_tc_kernel implicit GEMM + fused cross-modal block), %d launches/step" % n_gemm,
         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
         "peak_source": "%s, sustained bf16 (kernel timed inside the step)" % peaks["source"], "traffic": traffic,
-        "traffic_note": "average DRAM bytes per gemm_tc launch (ncu, profiles/r01_gemm_traffic.json); 'achieved' is FLOP/s "
-                        "(tensor-bound kernel), average FLOPs per launch = flops_per_step / launches",
+        "traffic_note": "average DRAM bytes per tensor-core launch (ncu, profiles/%s); 'achieved' is FLOP/s "
+                        "(tensor-bound kernel), average FLOPs per launch = flops_per_step / launches" % traffic_src,
         "flops_per_step": gemm_fl, "ms_per_step_in_kernel": gemm_ms, "kernel_share_of_step": gemm_ms / all_ms if all_ms else None,
         "step_frac_of_tensor_peak": value / world * GFLOP_PER_OBS * 1e9 / (peaks["bf16_tflops"] * 1e12),
         "single_stream_step_ms": all_ms,
@@ -307,16 +364,17 @@ def run_b200(args):
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
         json.dump({"ops": ops, "roofline": roofline, "ms_per_step": ms_step}, open(args.profile_out, "w"), indent=1)
 
-    # ---- secondary shape: one 64-step trajectory, N=1, one shared instruction ----------
+    # ---- secondary shape: one B-step trajectory, N=1, one shared instruction ----------
     traj = None
     if rank == 0 and world == 1:
         try:
-            d0 = dev_sets[0]
+            d0 = pb.dev_sets[0]
             tobs = {"rgb": d0["rgb"], "depth": d0["depth"], "instruction": d0["instruction"][:1].contiguous()}
             th = torch.zeros((2, 1, 512), device=dev)
             for _ in range(3):
                 policy.act(dict(tobs), th, th.clone(), d0["masks"])
             torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(10):
                 policy.act(dict(tobs), th, th.clone(), d0["masks"])
@@ -328,29 +386,37 @@ def run_b200(args):
         except Exception as exc:      # never lose the contract line over the secondary number
             traj = {"error": str(exc)[:200]}
 
+    # ---- strong-scaling base: the 512-environment batch of configs[3] on this ONE GPU ------------------------
+    strong_base = None
+    if world == 1 and not args.skip_strong_base:
+        try:
+            del pb
+            torch.cuda.empty_cache()
+            pbs = PolicyBench(policy, STRONG_GLOBAL_BATCH, L, dev, rank, 1, STRONG_GLOBAL_BATCH, n_sets=2, host=False)
+            sms, sout = pbs.time_device(max(3, args.steps // 4), 3)
+            strong_base = {"global_batch": STRONG_GLOBAL_BATCH, "n_gpus": 1, "ms_per_step": sms, "value": STRONG_GLOBAL_BATCH / (sms * 1e-3),
+                           "unit": "obs/s", "outputs_finite": bool(torch.isfinite(sout).all().item()),
+                           "note": "strong-scaling speed-up at N GPUs = value(N) / this value (same 512-environment global batch)"}
+            del pbs
+        except Exception as exc:
+            strong_base = {"error": str(exc)[:200]}
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         v, ms, cores = cpu_oracle_obs_per_sec(args.cpu_sample_rows, L, 3, 1)
         cpu = {"value": v, "unit": "obs/s", "cores": cores, "kind": "port",
-               "sample": "%d observations/step x 3 steps (+1 warm-up) of the same shapes through oracle/hcm_oracle.py "
-                         "(fp32 torch CPU restatement pinned to the reference's outputs)" % args.cpu_sample_rows}
+               "sample": "%d observations/step (%s) x 3 steps (+1 warm-up) of the same shapes through oracle/hcm_oracle.py "
+                         "(fp32 torch CPU restatement pinned to the reference's outputs)"
+                         % (args.cpu_sample_rows, "the full batch" if args.cpu_sample_rows == B else "a sample of the batch")}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "obs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": rt.dtype_name, "data": "synthetic",
-            "config": {
-                "workload": "cfg2: HCM policy forward (hi -> argmax -> lo), batch=64/GPU rollout-shaped (N=64,T=1), "
-                            "256x256 RGB + 256x256 depth, 64 distinct 80-token instructions, random-init weights",
-                "per_gpu_batch": B, "global_batch": global_rows, "seq_len": L, "parallelism": "dp%d" % world,
-                "l2": "3 rotating input sets (201 MB) and a >2 GB per-step working set vs 126 MB L2",
-                "outputs_finite": finite, "trajectory_shaped": traj,
-            },
-            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "obs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                      "ms_per_step": ms_e2e / args.steps, "uint8_rgb_frames": e2e_u8},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": rt.dtype_name, "data": "synthetic", "config": config,
+            "outputs_finite": finite, "trajectory_shaped": traj, "strong_scaling_base": strong_base,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -463,8 +529,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="environments per GPU")
     ap.add_argument("--seq-len", type=int, default=80)
-    ap.add_argument("--cpu-sample-rows", type=int, default=4)
+    ap.add_argument("--cpu-sample-rows", type=int, default=64, help="observations per CPU step (64 = the full per-GPU batch)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-strong-base", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N>1: strong = fixed 512-environment global batch (configs[3]); weak = 64 environments per rank")
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--workload", default="policy", choices=["policy", "cross_modal", "train"],
                     help="policy = BASELINE.json metric (default, the contract line); cross_modal = configs[2]; train = configs[4]")

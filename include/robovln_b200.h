@@ -185,11 +185,38 @@ int rvb_bert_attention(const void* qkv_bf16, void* ctx_bf16, int R, int L, int h
 int rvb_bert_attention_tc(const void* qkv_h16, void* ctx_h16, int R, int L, int heads, void* stream);
 int rvb_vla_attention(const void* q_bf16, const void* kv_bf16, void* ctx_bf16, int B, int L, int q_rows,
                       void* stream);
+/* Fused cross-modal block (csrc/vla_block.cu; transformer.py:262-281, :209-221, :81-126, :38-43): attention over the 16
+ * visual cells + fc_o + LayerNorm + position-wise FFN + LayerNorm + token mean in one tcgen05 kernel, L <= 128.
+ *   q0  [R*L, 256]      LN0(relu(ins_fc(bert))) + PE, R = 1 (q_shared) or B
+ *   kvx [2*B*16, 1288]  per visual cell (rgb rows, then depth rows): K'(4 heads x 256) | c(4 + 4 pad) | V(256), where
+ *                       K'_h = Wq_h^T k_h and c_h = bq_h . k_h fold fc_q into the key side
+ *   out [B, out_pitch]  pooled tokens, modality m at column m*256;  y_tokens (optional) [2, B, L, 256] */
+int rvb_vla_block(const void* q0_h16, const void* kvx_h16, const void* wo_h16, const void* w1_h16, const void* w2_h16,
+                  const float* bo, const float* b1, const float* b2, const float* ln1g, const float* ln1b,
+                  const float* ln2g, const float* ln2b, float eps, int B, int L, int q_shared, void* out_h16,
+                  int64_t out_pitch, void* y_tokens_h16, void* stream);
 int rvb_lstm(const float* gx, const void* whh_bf16, const float* masks, int mask_stride,
              const float* hc_in, float* hc_out, float* h_scratch, float* y, int T, int N, void* stream);
 int rvb_maxpool3x3s2(const void* in_bf16, void* out_bf16, int NB, int H, int W, int C, void* stream);
 int rvb_rgb_stem_im2col(const float* rgb, void* out_bf16, int NB, int H, int W, int Kpitch, void* stream);
 int rvb_depth_stem(const float* depth, const float* w, void* out_bf16, int NB, int H, int W, void* stream);
+
+/* ---- host-side plumbing kernels (csrc/prep.cu) --------------------------------------------
+ * rvb_pack_weight: fp32 parameter [O, I, KH, KW] (nn.Conv2d / nn.Linear layout, the reference's state_dict) ->
+ *   16-bit [O, KH*KW*I] with k = (r*KW + s)*I + c, rows `out_pitch` elements apart (0 = dense); with bn_* given,
+ *   eval-mode BatchNorm (torchvision ResNet-50 behind resnet_encoders.py:151) is folded in: weights scaled by
+ *   gamma / sqrt(var + eps), bias_out[o] = beta - mean * scale.
+ * rvb_compare_many: mismatch_dev[0] = 1 iff any of the n buffer pairs (device arrays of device pointers, sizes in
+ *   32-bit words) differ -- the bit-identity check that makes running hi's and lo's frozen trunks once legal.
+ * rvb_checksum: out2_dev[0..1] = 128-bit order-independent content checksum of a device buffer (used to decide
+ *   whether lo may reuse the trunk features hi computed: hierarchical_trainer.py:1096-1100 hands both models
+ *   the same observation batch). */
+int rvb_pack_weight(const float* w_f32, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                    const float* bn_var, float eps, void* out_h16, float* bias_out, int O, int I, int KH, int KW,
+                    int64_t out_pitch, void* stream);
+int rvb_compare_many(const void* const* a_dev, const void* const* b_dev, const int64_t* words_dev, int n,
+                     int* mismatch_dev, void* stream);
+int rvb_checksum(const void* dev_ptr, size_t bytes, uint64_t* out2_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,11 +62,16 @@ SYMBOLS = {
     "rvb_bert_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_bert_attention_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_vla_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rvb_vla_block": (c_int, [c_void_p] * 12 + [c_float, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "rvb_lstm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                          c_void_p]),
     "rvb_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rvb_rgb_stem_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rvb_depth_stem": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "rvb_pack_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int,
+                                c_int, c_int, c_int64, c_void_p]),
+    "rvb_compare_many": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "rvb_checksum": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
 }
 
 _libs = {}

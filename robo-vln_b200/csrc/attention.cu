@@ -174,10 +174,9 @@ template <int LKT>
 void launch_bert_attn(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s) {
   constexpr int LP = LKT * 16;
   const size_t smem = static_cast<size_t>(3) * LP * PITCH * sizeof(h16);
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
+  static PerDeviceOnce attr_once;
+  if (smem > 48 * 1024 && attr_once.first()) {
     RVB_CUDA(cudaFuncSetAttribute(bert_attn_kernel<LKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = true;
   }
   const int qtiles = (L + 15) / 16;
   const int nwarps = qtiles < 8 ? qtiles : 8;

@@ -194,10 +194,9 @@ void bert_self_attention_tc(const h16* qkv, h16* ctx, int R, int L, int heads, c
   CUtensorMap tmQ, tmKV;
   tma_encode_2d_h16(&tmQ, qkv, cols, rows, cols * 2, AT_HD, 128);
   tma_encode_2d_h16(&tmKV, qkv, cols, rows, cols * 2, AT_HD, static_cast<uint32_t>(LP));
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     RVB_CUDA(cudaFuncSetAttribute(bert_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr = true;
   }
   launch_k(bert_attn_tc_kernel, dim3(heads, R), dim3(AT_THREADS), AT_SMEM, s, tmQ, tmKV, ctx, L, LP, heads);
   RVB_CUDA(cudaGetLastError());

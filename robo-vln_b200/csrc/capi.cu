@@ -77,6 +77,9 @@ int hcm_plan(hcm_engine* e, const hcm_shape* shape, void* workspace, size_t work
     // deterministic contents for padding columns that no kernel writes
     RVB_CUDA(cudaMemset(workspace, 0, workspace_bytes));
     e->eng.plan(*shape, workspace, workspace_bytes);
+    // the memsets above ran on the legacy default stream; the first forward may be issued on a non-blocking
+    // stream that is not ordered after it
+    RVB_CUDA(cudaDeviceSynchronize());
   });
 }
 
@@ -339,6 +342,23 @@ int rvb_vla_attention(const void* q_bf16, const void* kv_bf16, void* ctx_bf16, i
   return guarded([&] { vla_cross_attention(B16(q_bf16), B16(kv_bf16), B16(ctx_bf16), B, L, 1, q_rows == L ? 1 : 0, S(stream)); });
 }
 
+int rvb_vla_block(const void* q0_h16, const void* kvx_h16, const void* wo_h16, const void* w1_h16, const void* w2_h16,
+                  const float* bo, const float* b1, const float* b2, const float* ln1g, const float* ln1b, const float* ln2g,
+                  const float* ln2b, float eps, int B, int L, int q_shared, void* out_h16, int64_t out_pitch,
+                  void* y_tokens_h16, void* stream) {
+  return guarded([&] {
+    VlaBlock d;
+    d.B = B; d.L = L; d.q_shared = q_shared;
+    d.q0 = B16(q0_h16); d.kvx = B16(kvx_h16); d.kvx_pitch = 1288;
+    d.wo = B16(wo_h16); d.w1 = B16(w1_h16); d.w2 = B16(w2_h16);
+    d.bo = bo; d.b1 = b1; d.b2 = b2; d.ln1g = ln1g; d.ln1b = ln1b; d.ln2g = ln2g; d.ln2b = ln2b;
+    d.eps = eps; d.out = B16(out_h16); d.out_pitch = out_pitch; d.y_tokens = B16(y_tokens_h16);
+    VlaBlockPlan plan;
+    vla_block_make_plan(d, &plan);
+    vla_block_launch(plan, S(stream));
+  });
+}
+
 int rvb_lstm(const float* gx, const void* whh_bf16, const float* masks, int mask_stride, const float* hc_in,
              float* hc_out, float* h_scratch, float* y, int T, int N, void* stream) {
   return guarded([&] { lstm_forward(gx, B16(whh_bf16), masks, mask_stride, hc_in, hc_out, h_scratch, y, T, N, S(stream)); });
@@ -358,6 +378,21 @@ int rvb_rgb_pad_convert(const float* rgb, void* out_h16, int NB, int H, int W, i
 
 int rvb_rgb_pad_convert4(const float* rgb, void* out_h16, int NB, int H, int W, int Wp, void* stream) {
   return guarded([&] { rgb_pad_convert4(rgb, B16(out_h16), NB, H, W, Wp, S(stream)); });
+}
+
+int rvb_pack_weight(const float* w_f32, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                    const float* bn_var, float eps, void* out_h16, float* bias_out, int O, int I, int KH, int KW,
+                    int64_t out_pitch, void* stream) {
+  return guarded([&] { pack_weight(w_f32, bn_gamma, bn_beta, bn_mean, bn_var, eps, B16(out_h16), bias_out, O, I, KH, KW, out_pitch, S(stream)); });
+}
+
+int rvb_compare_many(const void* const* a_dev, const void* const* b_dev, const int64_t* words_dev, int n, int* mismatch_dev,
+                     void* stream) {
+  return guarded([&] { compare_many(a_dev, b_dev, reinterpret_cast<const long long*>(words_dev), n, mismatch_dev, S(stream)); });
+}
+
+int rvb_checksum(const void* dev_ptr, size_t bytes, uint64_t* out2_dev, void* stream) {
+  return guarded([&] { checksum(dev_ptr, bytes, reinterpret_cast<unsigned long long*>(out2_dev), S(stream)); });
 }
 
 int rvb_depth_stem(const float* depth, const float* w, void* out_bf16, int NB, int H, int W, void* stream) {

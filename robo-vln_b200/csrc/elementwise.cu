@@ -879,10 +879,9 @@ void gn_fused(const GnApply& a, cudaStream_t s) {
   d.res = a.res; d.res_stats = nullptr; d.res_gamma = a.res_gamma; d.res_beta = a.res_beta;
   d.out = a.out; d.out_pitch = a.out_pitch;
   const size_t smem = static_cast<size_t>(2) * GNF_THREADS * 8 * sizeof(float) + static_cast<size_t>(4) * a.C * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     RVB_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * GNF_THREADS * 8 * 4 + 4 * 2048 * 4));
-    attr = true;
   }
   launch_k(gn_fused_kernel, dim3(a.NB), dim3(GNF_THREADS), smem, s, d);
   RVB_CUDA(cudaGetLastError());

@@ -454,28 +454,45 @@ void Engine::plan_bert(Stage& st) {
 //   bert: [R*L,768] h16; kvin: [2*B*16,256] h16 (rgb rows then depth rows);
 //   pooled -> out[b*out_pitch + mod*256 + d]
 // ---------------------------------------------------------------------------------------
+static bool use_vla_fused() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_VLA_FUSED");
+    v = (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16* kvin, h16* out, int64_t out_pitch,
                               Stage* st_vis_rgb, Stage* st_vis_depth) {
   const int B = shp_.B, L = shp_.L;
   const int R = (shp_.instr_rows == 1) ? 1 : B;
   const int64_t MQ = static_cast<int64_t>(R) * L, MV = 2ll * B * 16, MX = 2ll * B * L;
+  // The fused block kernel (vla_block.cu) covers attention + fc_o + LN1 + FFN + LN2 + token mean for L <= 128; longer
+  // instructions (INSTRUCTION_ENCODER.max_length is 200) and ROBOVLN_VLA_FUSED=0 take the GEMM-by-GEMM path.
+  const bool fused = use_vla_fused() && use_ln_fused() && L <= 128;
   float* f32a = reinterpret_cast<float*>(alloc(std::max<int64_t>(MX, MV) * 256 * 4));
   float* f32q = reinterpret_cast<float*>(alloc(MQ * 256 * 4));   // query side has its own scratch: it may run concurrently
   h16* Q0 = reinterpret_cast<h16*>(alloc(MQ * 256 * 2));
   h16* qq = reinterpret_cast<h16*>(alloc(MQ * 256 * 2));
   h16* vis = reinterpret_cast<h16*>(alloc(MV * 256 * 2));
   h16* kv = reinterpret_cast<h16*>(alloc(MV * 512 * 2));
-  h16* ctx = reinterpret_cast<h16*>(alloc(MX * 256 * 2));
-  h16* X = reinterpret_cast<h16*>(alloc(MX * 256 * 2));
-  h16* hff = reinterpret_cast<h16*>(alloc(MX * 1024 * 2));
-  h16* Y = reinterpret_cast<h16*>(alloc(MX * 256 * 2));
+  h16* kvx = reinterpret_cast<h16*>(alloc(MV * 1288 * 2));
+  h16* ctx = reinterpret_cast<h16*>(alloc(fused ? 1024 : MX * 256 * 2));
+  h16* X = reinterpret_cast<h16*>(alloc(fused ? 1024 : MX * 256 * 2));
+  h16* hff = reinterpret_cast<h16*>(alloc(fused ? 1024 : MX * 1024 * 2));
+  // ROBOVLN_KEEP_TOKENS=1 (parity tests): the fused kernel also writes its token-level output for inspection
+  const char* kt = std::getenv("ROBOVLN_KEEP_TOKENS");
+  const bool keep_tokens = kt != nullptr && std::strcmp(kt, "1") == 0;
+  h16* Y = reinterpret_cast<h16*>(alloc((fused && !keep_tokens) ? 1024 : MX * 256 * 2));
   float* pe = reinterpret_cast<float*>(alloc(static_cast<size_t>(L) * 256 * 4));
   if (dry_) return;
   const std::string p = "hi.vla";
   const float* ln0w = Wf(p + ".ln0.w", {256});
   const float* ln0b = Wf(p + ".ln0.b", {256});
+  // sinusoid table: a constant of the plan (common/utils.py:167-176), written once here
+  sinusoid_table(pe, L, 256, nullptr);
   // query side (shared by both modalities; depends on BERT only -> stage stq)
-  stq.push_back([pe, L](cudaStream_t s) { sinusoid_table(pe, L, 256, s); return 1; });
   if (use_ln_fused()) {
     add_gemm(stq, with_ln(linear(bert, MQ, 768, 768, Wb(p + ".ins_fc.w", {256, 768}), 256, Wf(p + ".ins_fc.b", {256}),
                                  ACT_RELU, Q0, 256, 0), ln0w, ln0b, 1e-5f, pe, L));
@@ -487,17 +504,26 @@ void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16*
       return 1;
     });
   }
-  add_gemm(stq, linear(Q0, MQ, 256, 256, Wb(p + ".fc_q.w", {256, 256}), 256, Wf(p + ".fc_q.b", {256}), ACT_NONE, qq, 256, 0));
+  // fused: fc_q is folded into the key side (kvx = [K' | c | V], weight_prep.py); otherwise project the queries
+  if (!fused)
+    add_gemm(stq, linear(Q0, MQ, 256, 256, Wb(p + ".fc_q.w", {256, 256}), 256, Wf(p + ".fc_q.b", {256}), ACT_NONE, qq, 256, 0));
   // key/value side.  With per-modality stages given (the policy step), each modality's vis_fc (+LayerNorm) and
   // fc_k|fc_v run on the stream of the encoder that produced its kv input, before the join.
+  auto kv_proj = [&](Stage& dst, const h16* vin, int64_t rows, int64_t row0) {
+    if (fused)
+      add_gemm(dst, linear(vin, rows, 256, 256, Wb(p + ".kvx.w", {1288, 256}), 1288, Wf(p + ".kvx.b", {1288}), ACT_NONE,
+                           kvx + row0 * 1288, 1288, 0));
+    else
+      add_gemm(dst, linear(vin, rows, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}), ACT_NONE,
+                           kv + row0 * 512, 512, 0));
+  };
   if (use_ln_fused() && st_vis_rgb != nullptr && st_vis_depth != nullptr) {
     const int64_t MH = MV / 2;
     Stage* sts[2] = {st_vis_rgb, st_vis_depth};
     for (int mod = 0; mod < 2; ++mod) {
       add_gemm(*sts[mod], with_ln(linear(kvin + mod * MH * 256, MH, 256, 256, Wb(p + ".vis_fc.w", {256, 256}), 256,
                                          Wf(p + ".vis_fc.b", {256}), ACT_RELU, vis + mod * MH * 256, 256, 0), ln0w, ln0b, 1e-5f));
-      add_gemm(*sts[mod], linear(vis + mod * MH * 256, MH, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}),
-                                 ACT_NONE, kv + mod * MH * 512, 512, 0));
+      kv_proj(*sts[mod], vis + mod * MH * 256, MH, mod * MH);
     }
   } else {
     if (use_ln_fused()) {
@@ -511,7 +537,28 @@ void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16*
         return 1;
       });
     }
-    add_gemm(st, linear(vis, MV, 256, 256, Wb(p + ".fc_kv.w", {512, 256}), 512, Wf(p + ".fc_kv.b", {512}), ACT_NONE, kv, 512, 0));
+    kv_proj(st, vis, MV, 0);
+  }
+  if (fused) {
+    VlaBlock d;
+    d.B = B; d.L = L; d.q_shared = (R == 1) ? 1 : 0;
+    d.q0 = Q0; d.kvx = kvx; d.kvx_pitch = 1288;
+    d.wo = Wb(p + ".fc_o.w", {256, 256}); d.w1 = Wb(p + ".fc1.w", {1024, 256}); d.w2 = Wb(p + ".fc2.w", {256, 1024});
+    d.bo = Wf(p + ".fc_o.b", {256}); d.b1 = Wf(p + ".fc1.b", {1024}); d.b2 = Wf(p + ".fc2.b", {256});
+    d.ln1g = Wf(p + ".ln1.w", {256}); d.ln1b = Wf(p + ".ln1.b", {256});
+    d.ln2g = Wf(p + ".ln2.w", {256}); d.ln2b = Wf(p + ".ln2.b", {256});
+    d.eps = 1e-5f; d.out = out; d.out_pitch = out_pitch;
+    d.y_tokens = keep_tokens ? Y : nullptr;
+    vla_plans_.emplace_back(new VlaBlockPlan());
+    VlaBlockPlan* plan = vla_plans_.back().get();
+    vla_block_make_plan(d, plan);
+    Op op([plan](cudaStream_t s) { vla_block_launch(*plan, s); return 1; });
+    // algorithmic FLOPs of what it replaces: attention (QK^T, PV), fc_o, fc1, fc2 for 2*B*L query rows
+    op.flops = 2.0 * static_cast<double>(MX) * (2.0 * 16 * 256 + 256.0 * 256 + 2.0 * 1024 * 256);
+    op.name = "vla_block<tcgen05> envs=" + std::to_string(B) + " L=" + std::to_string(L) + " tiles=" + std::to_string(2 * B);
+    st.push_back(std::move(op));
+    if (&st == &st_hi_tail_) vla_tokens_ = keep_tokens ? Y : nullptr;   // in production the token-level output never leaves the SM
+    return;
   }
   const int q_shared = (R == 1) ? 1 : 0;
   st.push_back([qq, kv, ctx, B, L, q_shared](cudaStream_t s) { vla_cross_attention(qq, kv, ctx, B, L, 2, q_shared, s); return 1; });
@@ -659,6 +706,7 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
   arena_cap_ = bytes;
   drop_graphs();
   gemms_.clear();
+  vla_plans_.clear();
   for (Stage* s : {&st_rgb_, &st_depth_, &st_rgb_lo_, &st_depth_lo_, &st_bert_, &st_pre_, &st_hi_tail_, &st_lo_tail_,
                    &st_cm_only_, &st_rgb_post_hi_, &st_depth_post_hi_, &st_bert_post_, &st_rgb_post_lo_, &st_depth_post_lo_})
     s->clear();
@@ -1201,7 +1249,7 @@ bool Engine::get_buffer(const std::string& name, void** ptr, int* dtype, std::ve
   if (name == "rgb_layer4") { *ptr = rgb_feat_; *dtype = RVB_H16_CODE; *shape = {B, rgb_fh_, rgb_fw_, 2048}; return true; }
   if (name == "depth_tokens") { *ptr = tokens_d_; *dtype = RVB_H16_CODE; *shape = {B, 16, 192}; return true; }
   if (name == "bert") { *ptr = bert_out_; *dtype = RVB_H16_CODE; *shape = {R, L, 768}; return true; }
-  if (name == "vla_tokens") { *ptr = vla_tokens_; *dtype = RVB_H16_CODE; *shape = {2, B, L, 256}; return true; }
+  if (name == "vla_tokens" && vla_tokens_ != nullptr) { *ptr = vla_tokens_; *dtype = RVB_H16_CODE; *shape = {2, B, L, 256}; return true; }
   if (name == "kv_in") { *ptr = kvin_; *dtype = RVB_H16_CODE; *shape = {2, B * 16, 256}; return true; }
   if (name == "hi_rnn_in") { *ptr = concat_hi_; *dtype = RVB_H16_CODE; *shape = {B, 896}; return true; }
   if (name == "hi_rnn_out") { *ptr = y_hi_; *dtype = 0; *shape = {B, 512}; return true; }

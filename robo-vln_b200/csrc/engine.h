@@ -130,6 +130,7 @@ class Engine {
   uint8_t* arena_base_ = nullptr;
   size_t arena_off_ = 0, arena_cap_ = 0;
   std::vector<std::unique_ptr<GemmTcPlan>> gemms_;
+  std::vector<std::unique_ptr<VlaBlockPlan>> vla_plans_;
 
   // planned buffers
   h16 *tokens_r_ = nullptr, *cellmean_r_ = nullptr, *gmean_r_ = nullptr, *tokens_d_ = nullptr;

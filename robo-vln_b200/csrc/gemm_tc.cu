@@ -876,10 +876,9 @@ constexpr CUtensorMapDataType kH16Type = RVB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLO
 template <int BN, int CTAS, int EPI = 0>
 void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   using C = Cfg<BN, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
@@ -951,6 +950,12 @@ void tma_encode_2d_h16(CUtensorMap* map, const void* base, uint64_t cols, uint64
   const uint32_t box[2] = {box_cols, box_rows};
   const uint32_t ones[2] = {1, 1};
   encode_map(map, kH16Type, base, 2, dims, strides, box, ones);
+}
+
+void tma_encode_nd_h16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box) {
+  const uint32_t ones[5] = {1, 1, 1, 1, 1};
+  encode_map(map, kH16Type, base, rank, dims, strides_bytes, box, ones);
 }
 
 bool use_pdl() {

@@ -198,10 +198,9 @@ void lstm_forward(const float* gx, const h16* whh, const float* masks, int mask_
                   float* hc_out, float* h_scratch, float* y, int T, int N, cudaStream_t s) {
   RVB_CHECK(T >= 1 && N >= 1, "lstm: empty batch");
   RVB_CHECK(hc_in != hc_out, "lstm: hidden state in/out must not alias");
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     RVB_CUDA(cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM));
-    attr = true;
   }
   const long long NH = static_cast<long long>(N) * HID;
   for (int t = 0; t < T; ++t) {

@@ -64,6 +64,20 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   RVB_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
 }
 
+// cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) applies to the CURRENT device only, and one process
+// may drive several (the reference trainer keeps hi on cuda:0 and lo on cuda:1, hierarchical_trainer.py:292-296):
+// remember the opt-in per device, not per process.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 // ---------------------------------------------------------------------------------------
@@ -225,6 +239,33 @@ void sinusoid_table(float* pe, int L, int D, cudaStream_t s);
 // gemm_tc.cu: 2-D tensor map over a row-major 16-bit matrix [rows, cols] (pitch in bytes), 128B swizzle
 void tma_encode_2d_h16(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_cols,
                        uint32_t box_rows);
+void tma_encode_nd_h16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box);
+// vla_block.cu -- the fused cross-modal attention block (attention + fc_o + LN1 + FFN + LN2 + token mean), L <= 128
+struct VlaBlock {
+  int B = 0, L = 0, q_shared = 0;
+  const h16* q0 = nullptr;        // [R*L, 256] = LN0(relu(ins_fc(bert))) + PE, R = 1 (q_shared) or B
+  const h16* kvx = nullptr;       // [2*B*16, 1288]: per visual cell K'(4 heads x 256) | c(8) | V(256); rgb rows then depth rows
+  int64_t kvx_pitch = 1288;
+  const h16 *wo = nullptr, *w1 = nullptr, *w2 = nullptr;   // fc_o [256,256], fc1 [1024,256], fc2 [256,1024]
+  const float *bo = nullptr, *b1 = nullptr, *b2 = nullptr, *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  float eps = 1e-5f;
+  h16* out = nullptr;             // pooled [B, out_pitch]; modality m at column m*256
+  int64_t out_pitch = 512;
+  h16* y_tokens = nullptr;        // parity tests only: token-level output [2, B, L, 256]
+};
+struct VlaBlockPlan {
+  alignas(64) CUtensorMap tmQ0;
+  alignas(64) CUtensorMap tmKp;
+  alignas(64) CUtensorMap tmV;
+  alignas(64) CUtensorMap tmWo;
+  alignas(64) CUtensorMap tmW1;
+  alignas(64) CUtensorMap tmW2;
+  VlaBlock d;
+  bool valid = false;
+};
+void vla_block_make_plan(const VlaBlock& d, VlaBlockPlan* plan);
+void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s);
 // attention_tc.cu -- tcgen05 / TMEM / TMA self-attention for L <= 128 (ROBOVLN_ATTN=tc selects it in the engine)
 bool use_tc_attention();
 void bert_self_attention_tc(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s);
@@ -232,6 +273,13 @@ void bert_self_attention_tc(const h16* qkv, h16* ctx, int R, int L, int heads, c
 void bert_self_attention(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s);
 void vla_cross_attention(const h16* q, const h16* kv, h16* ctx, int B, int L, int n_mod, int q_shared,
                          cudaStream_t s);
+
+// prep.cu -- weight packing (BatchNorm fold + OIHW -> K-major h16), bulk buffer comparison, content checksum
+void pack_weight(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                 h16* out, float* bias_out, int O, int I, int KH, int KW, int64_t out_pitch, cudaStream_t s);
+void compare_many(const void* const* a_dev, const void* const* b_dev, const long long* words_dev, int n, int* mismatch_dev,
+                  cudaStream_t s);
+void checksum(const void* p, size_t bytes, unsigned long long* out2_dev, cudaStream_t s);
 
 // lstm.cu
 void lstm_forward(const float* gx, const h16* whh, const float* masks, int mask_stride, const float* hc_in,

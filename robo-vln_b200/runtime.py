@@ -6,6 +6,7 @@ stream; every computation of the forward pass happens inside librobovln_b200.so.
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Dict, Optional, Tuple
 
@@ -45,7 +46,15 @@ class HcmRuntime:
         self._shares = False
         self._shape_key = None
         self._workspace: Optional[torch.Tensor] = None
-        self._obs_sig = None
+        # Trunk-feature reuse (lo after hi on the SAME observations, hierarchical_trainer.py:1096-1100): decided on
+        # observation CONTENT -- a 128-bit checksum per frame tensor computed on the device (rvb_checksum) -- never on
+        # pointers or version counters.  `trunk_reuse = False` (or ROBOVLN_TRUNK_REUSE=0) always re-runs the trunks.
+        self.trunk_reuse = os.environ.get("ROBOVLN_TRUNK_REUSE", "1") != "0"
+        self._obs_chk: Optional[torch.Tensor] = None     # int64[4] on the device: content the feature buffers hold
+        self._obs_meta = None
+        self._feat_lo_weights = False
+        self._tail_params = []
+        self._tail_sig = None
 
     def __del__(self):
         try:
@@ -82,8 +91,28 @@ class HcmRuntime:
         lo = self.lo() if self.lo is not None else None
         return hi, lo
 
-    def sync_weights(self):
+    def _tail_sig_now(self):
+        return tuple((p.data_ptr(), p._version) for p in self._tail_params)
+
+    def _refresh_tails(self):
+        """The trainable tail changed (optimizer step, in-place edit) since it was packed: re-pack it INTO the
+        engine's existing tensors -- pointers, plans and captured graphs stay valid."""
+        hi, lo = self._modules()
+        WP.set_h16(self.dtype_name)
+        with torch.no_grad(), torch.cuda.device(self.device):
+            new = {}
+            if hi is not None:
+                new.update(WP.prep_hi_tail(hi.state_dict(keep_vars=True), self.device))
+            if lo is not None:
+                new.update(WP.prep_lo_tail(lo.state_dict(keep_vars=True), self.device))
+            for name, t in new.items():
+                self._tensors[name].copy_(t)
+        self._tail_sig = self._tail_sig_now()
+
+    def sync_weights(self, check_tail: bool = False):
         if not self._dirty:
+            if check_tail and self._tail_sig_now() != self._tail_sig:
+                self._refresh_tails()
             return
         hi, lo = self._modules()
         dev = self.device
@@ -135,11 +164,16 @@ class HcmRuntime:
         self._shares = shares
         self._dirty = False
         self._shape_key = None      # plans capture weight pointers
-        self._obs_sig = None
+        self._obs_chk = None
+        from .param_spec import FROZEN_PREFIXES
+
+        self._tail_params = [p for m in (hi, lo) if m is not None for n, p in m.named_parameters()
+                             if not n.startswith(FROZEN_PREFIXES)]
+        self._tail_sig = self._tail_sig_now()
 
     # ---- planning --------------------------------------------------------------------------
     def ensure_plan(self, B: int, N: int, L: int, instr_rows: int, rgb_hw, depth_hw):
-        self.sync_weights()
+        self.sync_weights(check_tail=True)
         key = (B, N, L, instr_rows, tuple(rgb_hw), tuple(depth_hw))
         if key == self._shape_key:
             return
@@ -156,7 +190,7 @@ class HcmRuntime:
             torch.cuda.synchronize()
             check(self.lib.hcm_plan(self.handle, ctypes.byref(shp), ctypes.c_void_p(aligned), need), "hcm_plan")
         self._shape_key = key
-        self._obs_sig = None
+        self._obs_chk = None
 
     # ---- helpers ---------------------------------------------------------------------------
     def _stream(self):
@@ -184,9 +218,27 @@ class HcmRuntime:
             self._rgb_fmt = fmt
         return t
 
-    @staticmethod
-    def _sig(rgb: torch.Tensor, depth: torch.Tensor):
-        return (rgb.data_ptr(), rgb._version, tuple(rgb.shape), depth.data_ptr(), depth._version, tuple(depth.shape))
+    def _checksum_obs(self, rgb: torch.Tensor, depth: torch.Tensor):
+        """(int64[4] device tensor, meta) -- content checksum of the two frame tensors (asynchronous), or (None, None)
+        when reuse is disabled or a tensor is not 16-byte aligned."""
+        if not self.trunk_reuse or (rgb.data_ptr() | depth.data_ptr()) & 15:
+            return None, None
+        out = torch.empty((4,), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            check(self.lib.rvb_checksum(_ptr(rgb), rgb.numel() * rgb.element_size(), ctypes.c_void_p(out.data_ptr()), st),
+                  "rvb_checksum")
+            check(self.lib.rvb_checksum(_ptr(depth), depth.numel() * depth.element_size(),
+                                        ctypes.c_void_p(out.data_ptr() + 16), st), "rvb_checksum")
+        return out, (tuple(rgb.shape), rgb.dtype, tuple(depth.shape))
+
+    def _same_obs(self, rgb: torch.Tensor, depth: torch.Tensor) -> bool:
+        """Do the engine's trunk-feature buffers hold the features of exactly these frames?  (one 32-byte
+        device->host comparison; only asked on the module-API path where hi and lo are called separately)"""
+        if self._obs_chk is None:
+            return False
+        chk, meta = self._checksum_obs(rgb, depth)
+        return chk is not None and meta == self._obs_meta and bool(torch.equal(chk, self._obs_chk))
 
     def launches(self) -> int:
         return int(self.lib.hcm_last_launch_count(self.handle))
@@ -213,7 +265,9 @@ class HcmRuntime:
             check(self.lib.hcm_forward_hi(self.handle, _ptr(rgb), _ptr(depth), _ptr(i_f32), _ptr(i_i64), _ptr(masks),
                                           masks.stride(0), _ptr(hidden), _ptr(logits), _ptr(hc_out), self._stream()),
                   "hcm_forward_hi")
-        self._obs_sig = self._sig(rgb, depth)
+        # lo may follow on the same frames: remember WHAT the feature buffers now hold (content, not pointers)
+        self._obs_chk, self._obs_meta = self._checksum_obs(rgb, depth) if (self._shares and self.lo is not None) else (None, None)
+        self._feat_lo_weights = False
         self._keep = (rgb, depth, i_f32, i_i64, masks, hidden)   # alive until the stream consumed them
         return logits, hc_out
 
@@ -224,9 +278,9 @@ class HcmRuntime:
         masks = masks.to(self.device, torch.float32)
         hidden = hidden.to(self.device, torch.float32).contiguous()
         sub_goal = sub_goal.to(self.device, torch.int64).contiguous().view(-1)
-        self.sync_weights()
+        self.sync_weights(check_tail=True)
         reuse = bool(self._shares and self._shape_key is not None and self._shape_key[0] == B
-                     and self._shape_key[1] == N and self._obs_sig == self._sig(rgb, depth))
+                     and self._shape_key[1] == N and self._same_obs(rgb, depth))
         if not reuse:
             hi, _ = self._modules()
             if self._shape_key is not None and self._shape_key[0] == B and self._shape_key[1] == N \
@@ -241,6 +295,9 @@ class HcmRuntime:
             check(self.lib.hcm_forward_lo(self.handle, _ptr(rgb), _ptr(depth), _ptr(masks), masks.stride(0),
                                           _ptr(sub_goal), _ptr(hidden), _ptr(act), _ptr(stop), _ptr(hc_out),
                                           int(reuse), self._stream()), "hcm_forward_lo")
+        if not reuse:       # the trunks just ran on these frames (with lo's weights)
+            self._obs_chk, self._obs_meta = self._checksum_obs(rgb, depth)
+            self._feat_lo_weights = True
         self._keep_lo = (rgb, depth, masks, hidden, sub_goal)
         return act, stop, hc_out
 
@@ -266,6 +323,7 @@ class HcmRuntime:
                                               masks.stride(0), _ptr(hidden_hi), _ptr(hidden_lo), _ptr(logits), _ptr(act),
                                               _ptr(stop), _ptr(hc_hi), _ptr(hc_lo), _ptr(sub), self._stream()),
                   "hcm_forward_policy")
+        self._obs_chk = None      # feature buffers overwritten; content not tracked on this path
         self._keep = (rgb, depth, i_f32, i_i64, masks, hidden_hi, hidden_lo)
         return logits, act, stop, hc_hi, hc_lo, sub
 
@@ -290,13 +348,13 @@ class HcmRuntime:
         if not (self._shape_key and self._shape_key[0] == B and self._shape_key[4] == tuple(rgb.shape[1:3])
                 and (not with_bert or (self._shape_key[2], self._shape_key[3]) == (L, rows))):
             self.ensure_plan(B, N, L, rows, rgb.shape[1:3], depth.shape[1:3])
-        sig = self._sig(rgb, depth)
-        fresh = not (sig == self._obs_sig and (self._shares or not use_lo_weights))
+        fresh = not ((self._shares or self._feat_lo_weights == bool(use_lo_weights)) and self._same_obs(rgb, depth))
         if fresh or with_bert:
             with torch.cuda.device(self.device):
                 check(self.lib.hcm_run_encoders(self.handle, _ptr(rgb), _ptr(depth), _ptr(i_f32), _ptr(i_i64),
                                                 int(with_bert), int(use_lo_weights), self._stream()), "hcm_run_encoders")
-            self._obs_sig = sig
+            self._obs_chk, self._obs_meta = self._checksum_obs(rgb, depth)
+            self._feat_lo_weights = bool(use_lo_weights)
             self._keep = (rgb, depth, i_f32, i_i64)
         out = {
             "rgb_feat": self.get_buffer("rgb_tokens")[:, :, :2048].float(),
@@ -333,6 +391,7 @@ class HcmRuntime:
                                               masks.stride(0), _ptr(hidden_hi), _ptr(hidden_lo), _ptr(logits), _ptr(act),
                                               _ptr(stop), _ptr(hc_hi), _ptr(hc_lo), buf, cap, self._stream()),
                   "hcm_profile_policy")
+        self._obs_chk = None
         return json.loads(buf.value.decode())
 
     def forward_policy_host(self, rgb, depth, instruction, masks, hidden_hi, hidden_lo, out=None):
@@ -364,6 +423,7 @@ class HcmRuntime:
                                                    _ptr(hidden_hi), _ptr(hidden_lo), _ptr(out["logits"]),
                                                    _ptr(out["actions"]), _ptr(out["stop"]), _ptr(out["hidden_hi"]),
                                                    _ptr(out["hidden_lo"]), self._stream()), "hcm_forward_policy_host")
+        self._obs_chk = None
         return out
 
     def cross_modal(self, bert: torch.Tensor, rgb_spatial: torch.Tensor, depth_spatial: torch.Tensor) -> torch.Tensor:

@@ -30,6 +30,12 @@ def _check_config(model_config):
         (g(getattr(model_config, "VISUAL_LING_ATTN", None), "h", 4), 4, "VISUAL_LING_ATTN.h"),
         (g(getattr(model_config, "VISUAL_LING_ATTN", None), "d_ff", 1024), 1024, "VISUAL_LING_ATTN.d_ff"),
         (g(getattr(model_config, "VISUAL_LING_ATTN", None), "N", 1), 1, "VISUAL_LING_ATTN.N"),
+        (g(getattr(model_config, "VISUAL_LING_ATTN", None), "vis_in_features", 256), 256, "VISUAL_LING_ATTN.vis_in_features"),
+        (g(getattr(model_config, "VISUAL_LING_ATTN", None), "ins_in_features", 768), 768, "VISUAL_LING_ATTN.ins_in_features"),
+        (g(getattr(model_config, "TRANSFORMER_INSTRUCTION_ENCODER", None), "d_in", 768), 768, "TRANSFORMER_INSTRUCTION_ENCODER.d_in"),
+        (g(getattr(model_config, "TRANSFORMER_INSTRUCTION_ENCODER", None), "d_model", 256), 256, "TRANSFORMER_INSTRUCTION_ENCODER.d_model"),
+        (g(getattr(model_config, "IMAGE_CROSS_MODAL_ENCODER", None), "d_model", 256), 256, "IMAGE_CROSS_MODAL_ENCODER.d_model"),
+        (g(getattr(model_config, "RGB_ENCODER", None), "resnet_output_size", 256), 256, "RGB_ENCODER.resnet_output_size"),
         (g(getattr(model_config, "SEQ2SEQ", None), "use_prev_action", False), False, "SEQ2SEQ.use_prev_action"),
         (g(getattr(model_config, "PROGRESS_MONITOR", None), "use", False), False, "PROGRESS_MONITOR.use"),
         (g(model_config, "ablate_depth", False), False, "ablate_depth"),
@@ -56,6 +62,7 @@ class Seq2Seq_HighLevel_CMA(HcmModuleBase):
         vla = getattr(model_config, "VISUAL_LING_ATTN", None) if model_config is not None else None
         self.dropout_p = float(getattr(vla, "dropout", 0.25)) if vla is not None else 0.25
         build_param_tree(self, hi_spec(num_actions))
+        self._init_frozen_encoders(model_config)
 
     def forward(self, batch):
         r"""(observations, rnn_hidden_states, prev_actions, masks) = batch

@@ -25,6 +25,7 @@ class Seq2Seq_LowLevel(HcmModuleBase):
         self.model_config = model_config
         self.batch_size = batch_size
         build_param_tree(self, lo_spec(num_actions, num_sub_tasks))
+        self._init_frozen_encoders(model_config)
 
     def forward(self, batch):
         r"""(observations, rnn_hidden_states, prev_actions, masks, discrete_actions) = batch
