@@ -109,7 +109,7 @@ class Engine {
   const float* Wf(const std::string& n, std::initializer_list<int64_t> s) const;
   void* alloc(size_t bytes);
   float* new_stats(int G);
-  void add_gemm(Stage& st, const ConvGemm& g, int force_bn = 0);
+  GemmTcPlan* add_gemm(Stage& st, const ConvGemm& g, int force_bn = 0);
   static void label(Stage& st, const std::string& prefix);
   static ConvGemm linear(const h16* in, int64_t M, int K, int64_t lda, const h16* w, int N, const float* bias, int act,
                          void* out, int64_t ldc, int out_f32, const h16* res = nullptr, int64_t ldr = 0,
@@ -131,6 +131,17 @@ class Engine {
   size_t arena_off_ = 0, arena_cap_ = 0;
   std::vector<std::unique_ptr<GemmTcPlan>> gemms_;
   std::vector<std::unique_ptr<VlaBlockPlan>> vla_plans_;
+  // stand-alone cross-modal stage (hcm_run_cross_modal): its planned launches, and input-side plans re-encoded on the
+  // caller's tensors (cached per distinct pointer set) so that no staging copy is needed
+  struct CmStage {
+    GemmTcPlan *insfc = nullptr, *visfc = nullptr, *kvx = nullptr;
+    VlaBlockPlan* vla = nullptr;
+    struct Entry {
+      const void* key[3];
+      std::unique_ptr<GemmTcPlan> insfc, visfc[2];
+    };
+    std::vector<Entry> cache;
+  } cm_;
 
   // planned buffers
   h16 *tokens_r_ = nullptr, *cellmean_r_ = nullptr, *gmean_r_ = nullptr, *tokens_d_ = nullptr;

@@ -196,7 +196,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             img = mt * p.nb;
           }
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        // k-block rotation: tiles that share an operand (same mu -> same A rows, same nt -> same weights) start
+        // their K walk at different blocks, so that concurrently running CTAs do not ask L2 for the same lines at
+        // the same moment.  The sum over k blocks is order independent (fp32 accumulation; the order is a function
+        // of the tile index, hence deterministic).
+        const int krot = p.krot ? (mu * 5 + nt * 3) % p.num_kb : 0;
+        for (int kseq = 0; kseq < p.num_kb; ++kseq) {
+          int kb = kseq + krot;
+          if (kb >= p.num_kb) kb -= p.num_kb;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const int tap = kb / p.cblocks;
           const int cb = kb - tap * p.cblocks;
@@ -1053,6 +1060,12 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
       dbg = e ? std::atoi(e) : 0;
     }
     p.dbg = dbg;
+    static int krot = -1;
+    if (krot < 0) {
+      const char* e = std::getenv("ROBOVLN_GEMM_KROT");
+      krot = (e != nullptr) ? std::atoi(e) : 0;
+    }
+    p.krot = (krot != 0 && g.window == 0) ? 1 : 0;
   }
 
   const uint32_t ones[4] = {1, 1, 1, 1};

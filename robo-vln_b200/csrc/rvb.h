@@ -174,6 +174,7 @@ struct GemmTcParams {
   int ln_xchg;       // 1: statistics exchanged through global memory (ln_ws / ln_cnt), independent CTAs
   void* ln_ws;
   int* ln_cnt;
+  int krot;          // 1: per-tile rotation of the k-block walk (L2 hot-spot avoidance)
   int nstages;       // pipeline stages in use (fewer when the residual slices take their place)
   int dbg;           // timing experiments only (ROBOVLN_EPI_DEBUG bit mask; results are wrong when set)
 };

@@ -9,7 +9,7 @@
 //   P   = softmax_16keys(S / 8)    registers <- TMEM (tcgen05.ld), un-normalised 16-bit P -> shared memory
 //   O_h = P_h . V_h                tcgen05.mma  M=128 N=64  K=16    V consumed MN-major straight from its TMA box
 //   ctx = O / rowsum               TMEM -> 16-bit shared-memory A operand (K-major, 128B swizzle)
-//   A   = ctx . Wo^T               tcgen05.mma  M=128 N=256 K=256   Wo streamed by TMA through a 4-slot ring
+//   A   = ctx . Wo^T               tcgen05.mma  M=128 N=256 K=256   Wo streamed by TMA through a 5-slot ring
 //   X   = LN1(Q0 + A + bo)         TMEM -> registers -> 16-bit shared-memory A operand (overwrites ctx)
 //   H_c = relu(X . W1_c^T + b1_c)  8 chunks of 128 hidden units, TMEM accumulators double-buffered,
 //   Y  += H_c . W2_c^T               so that chunk c's activation epilogue runs under the MMAs of chunks c+1 / c-1
@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "rvb.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace rvb {
@@ -39,14 +40,14 @@ namespace {
 
 constexpr int VB_THREADS = 320;
 constexpr int VB_EPI_WARPS = 8;
-constexpr int VB_NS = 4;                         // weight-ring slots
+constexpr int VB_NS = 5;                         // weight-ring slots
 constexpr int VB_SLOT = 16384;                   // bytes per slot: one [128 rows x 64 k] 16-bit block
 constexpr int VB_SUB = 16384;                    // one [128 rows x 64 cols] K-major sub-tile of an A operand
 constexpr int VB_OFF_A = 0;                      // bufA: Q0 (4 sub-tiles), later the two H chunk buffers (2 x 2 sub-tiles)
-constexpr int VB_OFF_B = 65536;                  // bufB: ctx -> X -> Y (4 sub-tiles)
-constexpr int VB_OFF_P = 131072;                 // P: [128 x 64] un-normalised probabilities (col = head*16 + key)
-constexpr int VB_OFF_V = VB_OFF_P + 16384;       // V: 4 heads x [16 keys x 64 dims]
-constexpr int VB_OFF_RING = VB_OFF_V + 8192;
+constexpr int VB_OFF_B = 65536;                  // bufB: (P, V) -> ctx -> X -> Y (4 sub-tiles)
+constexpr int VB_OFF_P = VB_OFF_B;               // P: [128 x 64] un-normalised probabilities (col = head*16 + key); dead once P.V
+constexpr int VB_OFF_V = VB_OFF_B + 16384;       // V: 4 heads x [16 keys x 64 dims];                                  has retired
+constexpr int VB_OFF_RING = 131072;
 constexpr int VB_OFF_MISC = VB_OFF_RING + VB_NS * VB_SLOT;
 constexpr int VB_MISC_BYTES = 4096;              // barriers, c[64], LayerNorm partials [2][128] float2, column partials
 constexpr int VB_SMEM = VB_OFF_MISC + VB_MISC_BYTES + 1024 /*align slack*/;
@@ -65,6 +66,7 @@ struct VlaBlockParams {
   h16* out;                     // pooled [B, out_pitch], modality m at column m*256
   long long out_pitch;
   h16* y_tokens;                // parity tests only: token-level output [2, B, L, 256]; null in production
+  int rotate;                   // 1: every CTA walks the weight blocks in its own rotated order (see below)
 };
 
 RVB_DEVICE void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -153,6 +155,12 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
   const int env = blockIdx.x, mod = blockIdx.y;
   const int cell_row0 = (mod * p.B + env) * 16;          // first of this tile's 16 visual-cell rows in kvx
   const int q_row0 = p.q_shared ? 0 : env * p.L;
+  // Every CTA streams the SAME 1.1 MB of weights; walking them in lock step makes all SMs ask the same L2 lines at
+  // the same moment (measured: ~0.75 us per 16 KB block, 4x the tensor-pipe time).  The sum over k blocks and over the
+  // FFN's hidden chunks is order independent, so CTA i starts at chunk (i mod 8) and k block ((i / 8) mod 4): at any
+  // instant the CTAs are spread over 32 different blocks.  (Deterministic: the order is a function of the CTA index.)
+  const int cta_id = p.rotate ? static_cast<int>(blockIdx.y * gridDim.x + blockIdx.x) : 0;
+  const int rc = cta_id & 7, rk = (cta_id >> 3) & 3;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmKp); tma_prefetch_desc(&tmV);
@@ -195,7 +203,7 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
         for (int nh = 0; nh < 2; ++nh) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[slot], VB_SLOT);
-          tma_load_2d(ring + slot * VB_SLOT, &tmWo, &full_bar[slot], kb * 64, nh * 128);
+          tma_load_2d(ring + slot * VB_SLOT, &tmWo, &full_bar[slot], ((kb + rk) & 3) * 64, ((nh + rc) & 1) * 128);
           next();
         }
       // FFN in MMA issue order
@@ -205,8 +213,10 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
         for (int u = 0; u < 4; ++u) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[slot], VB_SLOT);
-          if (!is_fc2) tma_load_2d(ring + slot * VB_SLOT, &tmW1, &full_bar[slot], u * 64, c * 128);                 // W1[c*128.., kb = u]
-          else tma_load_2d(ring + slot * VB_SLOT, &tmW2, &full_bar[slot], c * 128 + (u >> 1) * 64, (u & 1) * 128);    // W2[nh = u&1, k = c*128 + kb2*64]
+          const int cc = (c + rc) & 7;       // the hidden chunk this CTA processes at sequence position c
+          if (!is_fc2) tma_load_2d(ring + slot * VB_SLOT, &tmW1, &full_bar[slot], ((u + rk) & 3) * 64, cc * 128);    // W1[cc*128.., k block]
+          else tma_load_2d(ring + slot * VB_SLOT, &tmW2, &full_bar[slot], cc * 128 + (((u >> 1) + rk) & 1) * 64,
+                           (((u & 1) + (rk >> 1)) & 1) * 128);                                                        // W2[n half, k = cc*128 + kb2*64]
           next();
         }
       }
@@ -252,7 +262,7 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       mbar_wait(&one[4], 0);
       tc_fence_after();
       for (int kb = 0; kb < 4; ++kb)
-        for (int nh = 0; nh < 2; ++nh) unit(bufB + kb * VB_SUB, TM_H + nh * 128, idesc128, kb == 0);
+        for (int nh = 0; nh < 2; ++nh) unit(bufB + ((kb + rk) & 3) * VB_SUB, TM_H + ((nh + rc) & 1) * 128, idesc128, kb == 0);
       umma_commit(&one[5]);
       // ---- FFN
       mbar_wait(&one[6], 0);
@@ -266,13 +276,14 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
             mbar_wait(&hempty[b], static_cast<uint32_t>(((c >> 1) - 1) & 1));
             tc_fence_after();
           }
-          for (int kb = 0; kb < 4; ++kb) unit(bufB + kb * VB_SUB, TM_H + b * 128, idesc128, kb == 0);
+          for (int kb = 0; kb < 4; ++kb) unit(bufB + ((kb + rk) & 3) * VB_SUB, TM_H + b * 128, idesc128, kb == 0);
           umma_commit(&hfull[b]);
         } else {
           mbar_wait(&sfull[b], static_cast<uint32_t>((c >> 1) & 1));
           tc_fence_after();
           for (int u = 0; u < 4; ++u)
-            unit(bufA + b * 2 * VB_SUB + (u >> 1) * VB_SUB, TM_Y + (u & 1) * 128, idesc128, c == 0 && (u >> 1) == 0);
+            unit(bufA + b * 2 * VB_SUB + (((u >> 1) + rk) & 1) * VB_SUB, TM_Y + (((u & 1) + (rk >> 1)) & 1) * 128, idesc128,
+                 c == 0 && (u >> 1) == 0);
           umma_commit(&sempty[b]);
         }
       }
@@ -408,7 +419,7 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       if (lane == 0) mbar_arrive(&hempty[b]);           // accumulator drained: fc1(c + 2) may overwrite it
       if (c >= 2) mbar_wait(&sempty[b], static_cast<uint32_t>(((c >> 1) - 1) & 1));   // fc2(c - 2) has read this H buffer
       uint8_t* dst = bufA + (b * 2 + half) * VB_SUB + row * 128;
-      const float* bias = p.b1 + c * 128 + half * 64;
+      const float* bias = p.b1 + ((c + rc) & 7) * 128 + half * 64;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j * 8));
@@ -515,6 +526,8 @@ void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s) {
   p.kvx = d.kvx; p.kvx_pitch = d.kvx_pitch;
   p.bo = d.bo; p.b1 = d.b1; p.b2 = d.b2; p.ln1g = d.ln1g; p.ln1b = d.ln1b; p.ln2g = d.ln2g; p.ln2b = d.ln2b;
   p.eps = d.eps; p.out = d.out; p.out_pitch = d.out_pitch; p.y_tokens = d.y_tokens;
+  static const char* renv = std::getenv("ROBOVLN_VLA_ROTATE");
+  p.rotate = (renv != nullptr && std::strcmp(renv, "0") == 0) ? 0 : 1;
   launch_k(vla_block_kernel, dim3(d.B, 2), dim3(VB_THREADS), VB_SMEM, s, plan.tmQ0, plan.tmKp, plan.tmV, plan.tmWo, plan.tmW1,
            plan.tmW2, p);
   RVB_CUDA(cudaGetLastError());

@@ -178,3 +178,66 @@ def test_output_all_gather_world_size_2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_constructor_loads_ddppo_checkpoint_and_reports_random_encoders(tmp_path):
+    """Constructor parity (resnet_encoders.py:38-52, :151; seq2seq_highlevel_cma.py:45): DEPTH_ENCODER.ddppo_checkpoint is
+    loaded with the reference's key remap; pretrained BERT / ImageNet weights that are not available offline are
+    reported loudly instead of silently training on random frozen encoders."""
+    import warnings
+    from types import SimpleNamespace as NS
+
+    import robovln_b200 as R
+
+    donor = R.Seq2Seq_LowLevel(None, 2, 4, None, 1)
+    src = donor.depth_encoder.visual_encoder.state_dict()
+    g = torch.Generator().manual_seed(11)
+    ck = {"state_dict": {"actor_critic.net.visual_encoder." + k: torch.randn(v.shape, generator=g) for k, v in src.items()}}
+    ck["state_dict"]["actor_critic.net.prev_action_embedding.weight"] = torch.zeros(5, 32)     # ignored, as in the reference
+    path = str(tmp_path / "gibson-2plus-resnet50.pth")
+    torch.save(ck, path)
+    cfg = NS(DEPTH_ENCODER=NS(cnn_type="VlnResnetDepthEncoder", backbone="resnet50", output_size=128, ddppo_checkpoint=path))
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        hi = R.Seq2Seq_HighLevel_CMA(None, 4, cfg, 1)
+    for k, v in hi.depth_encoder.visual_encoder.state_dict().items():
+        assert torch.equal(v, ck["state_dict"]["actor_critic.net.visual_encoder." + k]), k
+    msgs = [str(w.message) for w in rec if issubclass(w.category, RuntimeWarning)]
+    assert any("RANDOM" in m and "rgb_encoder.cnn" in m and "embedding_layer" in m for m in msgs), msgs
+    assert not any("depth_encoder" in m for m in msgs)
+    assert hi.random_frozen_encoders and all("depth" not in s for s in hi.random_frozen_encoders)
+    # no checkpoint configured -> the depth trunk is reported too; a missing file raises like torch.load does
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        R.Seq2Seq_LowLevel(None, 2, 4, NS(DEPTH_ENCODER=NS(ddppo_checkpoint="NONE")), 1)
+    assert any("depth_encoder" in str(w.message) for w in rec)
+    with pytest.raises(FileNotFoundError):
+        R.Seq2Seq_LowLevel(None, 2, 4, NS(DEPTH_ENCODER=NS(ddppo_checkpoint=str(tmp_path / "missing.pth"))), 1)
+    # dims that are hard-wired into the kernels are validated instead of silently ignored
+    with pytest.raises(NotImplementedError, match="ins_in_features"):
+        R.Seq2Seq_HighLevel_CMA(None, 4, NS(VISUAL_LING_ATTN=NS(ins_in_features=512)), 1)
+    with pytest.raises(NotImplementedError, match="d_in"):
+        R.Seq2Seq_HighLevel_CMA(None, 4, NS(TRANSFORMER_INSTRUCTION_ENCODER=NS(d_in=512)), 1)
+
+
+def test_same_device_to_does_not_invalidate_the_runtime():
+    """hierarchical_trainer.py:517 calls low_level.to(device2) on every update: a move that changes nothing must not
+    mark the engine's packed weights dirty (it used to force a re-pack + re-plan per training step)."""
+    import robovln_b200 as R
+
+    class FakeRt:
+        device = torch.device("cpu")
+        dirty = 0
+
+        def mark_dirty(self):
+            self.dirty += 1
+
+    lo = R.Seq2Seq_LowLevel(None, 2, 4, None, 1)
+    rt = FakeRt()
+    lo.__dict__["_rt"] = rt
+    lo.to("cpu")
+    lo.to(torch.device("cpu"))
+    lo.float()
+    assert rt.dirty == 0
+    lo.double()            # storage really changed
+    assert rt.dirty == 1
