@@ -401,6 +401,23 @@ def run_b200(args):
         except Exception as exc:
             strong_base = {"error": str(exc)[:200]}
 
+    # ---- library arm on the same GPU (the reference ships no kernel, so stock cuDNN / cuBLAS is the bar) ----
+    library = None
+    if rank == 0 and world == 1 and not args.skip_library_baseline:
+        try:
+            try:
+                del pb
+            except NameError:
+                pass
+            torch.cuda.empty_cache()
+            from tools import library_bar
+
+            library = library_bar.measure(B=B, L=L, steps=max(5, args.steps), warmup=5, device=dev)
+            library["note"] = ("same step from stock library kernels on this GPU: channels_last fp16 torchvision ResNet-50 + GroupNorm "
+                               "ResNet-50 (cuDNN, cudnn.benchmark), HF BertModel with SDPA, cuDNN LSTM, trunks run once, CUDA-graph replay")
+        except Exception as exc:
+            library = {"error": str(exc)[:300]}
+
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -417,6 +434,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": rt.dtype_name, "data": "synthetic", "config": config,
             "outputs_finite": finite, "trajectory_shaped": traj, "strong_scaling_base": strong_base,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "library_baseline": library,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -532,6 +550,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=64, help="observations per CPU step (64 = the full per-GPU batch)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-strong-base", action="store_true")
+    ap.add_argument("--skip-library-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N>1: strong = fixed 512-environment global batch (configs[3]); weak = 64 environments per rank")
     ap.add_argument("--profile-out", default="")

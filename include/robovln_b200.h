@@ -110,6 +110,12 @@ int hcm_forward_policy_host(hcm_engine* e, const float* rgb, const float* depth,
  * quarter of the bytes (observation ingest). */
 int hcm_set_rgb_format(hcm_engine* e, int fmt);
 
+/* Instruction cache (the reference re-tokenises and re-encodes the unchanged instruction at
+ * every step, common/utils.py:87-118 + seq2seq_highlevel_cma.py:189-195).  skip = 1: the next forward calls keep the
+ * BERT output and the query-side projection of the previous call (the caller guarantees that the instruction tokens
+ * are identical and that a full forward has run since the last hcm_plan); skip = 0 (default): BERT runs. */
+int hcm_set_skip_bert(hcm_engine* e, int skip);
+
 /* Number of kernels the last forward call launched (for bench.py's gpu_launches). */
 int64_t hcm_last_launch_count(hcm_engine* e);
 

@@ -38,6 +38,7 @@ SYMBOLS = {
     "hcm_forward_policy": (c_int, [c_void_p] + [c_void_p] * 5 + [c_int] + [c_void_p] * 9),
     "hcm_forward_policy_host": (c_int, [c_void_p] + [c_void_p] * 12),
     "hcm_set_rgb_format": (c_int, [c_void_p, c_int]),
+    "hcm_set_skip_bert": (c_int, [c_void_p, c_int]),
     "hcm_last_launch_count": (c_int64, [c_void_p]),
     "hcm_profile_policy": (c_int, [c_void_p] + [c_void_p] * 5 + [c_int] + [c_void_p] * 7 + [c_char_p, c_size_t, c_void_p]),
     "hcm_run_rgb_trunk": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

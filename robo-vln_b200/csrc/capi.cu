@@ -138,6 +138,10 @@ int hcm_set_rgb_format(hcm_engine* e, int fmt) {
   });
 }
 
+int hcm_set_skip_bert(hcm_engine* e, int skip) {
+  return guarded([&] { e->eng.skip_bert_ = skip != 0; });
+}
+
 int64_t hcm_last_launch_count(hcm_engine* e) { return e->eng.launches_; }
 
 int hcm_profile_policy(hcm_engine* e, const float* rgb, const float* depth, const float* instr_f32,

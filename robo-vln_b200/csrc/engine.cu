@@ -814,7 +814,7 @@ void Engine::run_encoders(bool with_bert, bool lo_weights, cudaStream_t s, bool 
   std::vector<const Op*> rgb, dep, bert;
   auto append = [](std::vector<const Op*>& v, const Stage& st) { for (const Op& op : st) v.push_back(&op); };
   const bool do_rgb = (enc_mask_ & 1) != 0, do_dep = (enc_mask_ & 2) != 0;
-  with_bert = with_bert && (enc_mask_ & 4) != 0;
+  with_bert = with_bert && (enc_mask_ & 4) != 0 && !skip_bert_;   // skip_bert_: the instruction (hence BERT output and Q0) is unchanged
   if (do_rgb) append(rgb, (lo_weights && !st_rgb_lo_.empty()) ? st_rgb_lo_ : st_rgb_);
   if (do_dep) append(dep, (lo_weights && !st_depth_lo_.empty()) ? st_depth_lo_ : st_depth_);
   if (with_bert) append(bert, st_bert_);
@@ -1008,7 +1008,8 @@ void Engine::forward_graphed(int kind, cudaStream_t s) {
     return;
   }
   const void* key[8] = {user.rgb, user.depth, user.instr_f32, user.instr_i64, user.masks,
-                        reinterpret_cast<const void*>(static_cast<uintptr_t>(user.mask_stride) | (static_cast<uintptr_t>(rgb_fmt_) << 16)),
+                        reinterpret_cast<const void*>(static_cast<uintptr_t>(user.mask_stride) | (static_cast<uintptr_t>(rgb_fmt_) << 16) |
+                                                      (static_cast<uintptr_t>(skip_bert_ ? 1 : 0) << 20)),
                         user.hc_hi_in, kind == 0 ? static_cast<const void*>(user.hc_lo_in) : reinterpret_cast<const void*>(uintptr_t(1))};
   GraphEntry* hit = nullptr;
   for (auto& g : graphs_)
@@ -1195,7 +1196,7 @@ void Engine::forward_policy_host(const float* rgb, const float* depth, const flo
     RVB_CUDA(cudaMemcpyAsync(stage_hc_lo_, hc_lo_in, hc_b, cudaMemcpyHostToDevice, s));
     RVB_CUDA(cudaEventRecord(events_[3], s));
     RVB_CUDA(cudaStreamWaitEvent(upload_, events_[3], 0));
-    RVB_CUDA(cudaGraphLaunch(host_graphs_.g1b, upload_));
+    if (!skip_bert_) RVB_CUDA(cudaGraphLaunch(host_graphs_.g1b, upload_));
     RVB_CUDA(cudaEventRecord(ev_upload_, upload_));
     run(st_pre_, s);
     static const char* uenv = std::getenv("ROBOVLN_UPLOAD_ORDER");

@@ -90,6 +90,9 @@ class Engine {
   // 0: RGB frames are float32 in 0..255 (the reference's batch_obs output); 1: uint8 (the sensor's own format --
   // a quarter of the upload bytes).  Applies to the `rgb` pointer of every entry point.
   int rgb_fmt_ = 0;
+  // Instruction cache: the caller asserts that the instruction tokens are the ones of the
+  // previous call, so BERT (54 % of the step's FLOPs) and the query-side projection keep their outputs from that call.
+  bool skip_bert_ = false;
   RunArgs args_;
   // forward_policy only: the hi head also writes argmax -> sub-goal ids and lo's sub-task embedding
   int64_t* policy_sg_ = nullptr;

@@ -31,8 +31,10 @@
 #include "common.cuh"
 #include "rvb.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace rvb {
 
@@ -67,7 +69,14 @@ struct VlaBlockParams {
   long long out_pitch;
   h16* y_tokens;                // parity tests only: token-level output [2, B, L, 256]; null in production
   int rotate;                   // 1: every CTA walks the weight blocks in its own rotated order (see below)
+  long long* times;             // diagnostics (ROBOVLN_VLA_TIMES): [CTA][64] SM-clock stamps; null in production
 };
+
+// diagnostics: slot i of this CTA's timeline (MMA thread: 0..31, first epilogue thread: 32..63)
+#define VB_STAMP(i)                                                                                   \
+  do {                                                                                                \
+    if (p.times != nullptr) p.times[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 64 + (i)] = clock64(); \
+  } while (0)
 
 RVB_DEVICE void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -242,14 +251,18 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       };
       constexpr uint32_t idesc64 = umma_idesc_h16(128, 64);
       constexpr uint32_t idesc128 = umma_idesc_h16(128, 128);
+      VB_STAMP(0);
       mbar_wait(&one[0], 0);
       tc_fence_after();
+      VB_STAMP(1);
       // ---- S[128, 64] = Q0 . K'^T
       for (int kb = 0; kb < 4; ++kb) unit(bufA + kb * VB_SUB, TM_H, idesc64, kb == 0);
       umma_commit(&one[1]);
+      VB_STAMP(2);
       // ---- O_h[128, 64] = P_h . V_h   (V MN-major: [key, dim] rows of 128 B)
       mbar_wait(&one[2], 0);
       tc_fence_after();
+      VB_STAMP(3);
       {
         constexpr uint32_t idesc_mn = umma_idesc_h16(128, 64) | (1u << 16);
         const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
@@ -261,13 +274,17 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       // ---- fc_o: A[128, 256] = ctx . Wo^T
       mbar_wait(&one[4], 0);
       tc_fence_after();
+      VB_STAMP(4);
       for (int kb = 0; kb < 4; ++kb)
         for (int nh = 0; nh < 2; ++nh) unit(bufB + ((kb + rk) & 3) * VB_SUB, TM_H + ((nh + rc) & 1) * 128, idesc128, kb == 0);
       umma_commit(&one[5]);
+      VB_STAMP(5);
       // ---- FFN
       mbar_wait(&one[6], 0);
       tc_fence_after();
+      VB_STAMP(6);
       for (int step = 0; step < 16; ++step) {
+        VB_STAMP(8 + step);
         int is_fc2, c;
         ffn_step(step, is_fc2, c);
         const int b = c & 1;
@@ -288,6 +305,7 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
         }
       }
       umma_commit(&one[7]);
+      VB_STAMP(7);
     }
   } else {
     // =============================== epilogue (warps 2..9) ===============================
@@ -304,8 +322,10 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
     // ---- softmax over the 16 keys of this thread's two heads (2*half, 2*half + 1); S column = key*4 + head
     float inv_sum[2];
     {
+      if (et == 0) VB_STAMP(32);
       mbar_wait(&one[1], 0);
       tc_fence_after();
+      if (et == 0) VB_STAMP(33);
       float s[64];
       {
         uint32_t v0[32], v1[32];
@@ -345,8 +365,10 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
 
     // ---- ctx = O / rowsum for heads 2*half, 2*half + 1 -> bufB sub-tiles (K block = head)
     {
+      if (et == 0) VB_STAMP(34);
       mbar_wait(&one[3], 0);
       tc_fence_after();
+      if (et == 0) VB_STAMP(35);
       float f[128];
       tmem_ld_128(trow + TM_Y + half * 128, f);
 #pragma unroll
@@ -368,9 +390,11 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
 
     // ---- X = LN1(Q0 + A + bo): this thread owns columns half*128 .. +127
     {
+      if (et == 0) VB_STAMP(36);
       mbar_wait(&one[0], 0);     // (long complete) this thread reads the TMA-written Q0 tile below
       mbar_wait(&one[5], 0);
       tc_fence_after();
+      if (et == 0) VB_STAMP(37);
       float v[128];
       tmem_ld_128(trow + TM_H + half * 128, v);
       const int n0 = half * 128;
@@ -408,8 +432,10 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
       const int b = c & 1;
+      if (et == 0) VB_STAMP(40 + 2 * c);
       mbar_wait(&hfull[b], static_cast<uint32_t>((c >> 1) & 1));
       tc_fence_after();
+      if (et == 0) VB_STAMP(41 + 2 * c);
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(trow + TM_H + b * 128 + half * 64, r0);
       tmem_ld_32x32(trow + TM_H + b * 128 + half * 64 + 32, r1);
@@ -439,8 +465,10 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
 
     // ---- Y = LN2(X + Y + b2), written in place of X; then the token mean
     {
+      if (et == 0) VB_STAMP(38);
       mbar_wait(&one[7], 0);
       tc_fence_after();
+      if (et == 0) VB_STAMP(39);
       float v[128];
       tmem_ld_128(trow + TM_Y + half * 128, v);
       const int n0 = half * 128;
@@ -479,6 +507,7 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       for (int r = 0; r < p.L; ++r)
         acc += from_h16(*reinterpret_cast<const h16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
       p.out[static_cast<long long>(env) * p.out_pitch + mod * 256 + et] = to_h16(acc / static_cast<float>(p.L));
+      if (et == 0) VB_STAMP(56);
     }
   }
 
@@ -528,9 +557,35 @@ void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s) {
   p.eps = d.eps; p.out = d.out; p.out_pitch = d.out_pitch; p.y_tokens = d.y_tokens;
   static const char* renv = std::getenv("ROBOVLN_VLA_ROTATE");
   p.rotate = (renv != nullptr && std::strcmp(renv, "0") == 0) ? 0 : 1;
+  // ROBOVLN_VLA_TIMES=<file>: per-CTA phase time stamps (SM clocks) of every launch are written to <file> (diagnostics;
+  // synchronises the stream)
+  static const char* tenv = std::getenv("ROBOVLN_VLA_TIMES");
+  long long* tbuf = nullptr;
+  const size_t tbytes = static_cast<size_t>(d.B) * 2 * 64 * sizeof(long long);
+  if (tenv != nullptr) {
+    RVB_CUDA(cudaMalloc(&tbuf, tbytes));
+    RVB_CUDA(cudaMemsetAsync(tbuf, 0, tbytes, s));
+  }
+  p.times = tbuf;
   launch_k(vla_block_kernel, dim3(d.B, 2), dim3(VB_THREADS), VB_SMEM, s, plan.tmQ0, plan.tmKp, plan.tmV, plan.tmWo, plan.tmW1,
            plan.tmW2, p);
   RVB_CUDA(cudaGetLastError());
+  if (tbuf != nullptr) {
+    std::vector<long long> host(static_cast<size_t>(d.B) * 2 * 64);
+    RVB_CUDA(cudaStreamSynchronize(s));
+    RVB_CUDA(cudaMemcpy(host.data(), tbuf, tbytes, cudaMemcpyDeviceToHost));
+    RVB_CUDA(cudaFree(tbuf));
+    FILE* f = std::fopen(tenv, "a");
+    if (f != nullptr) {
+      std::fprintf(f, "# launch B=%d L=%d\n", d.B, d.L);
+      for (int c = 0; c < d.B * 2; ++c) {
+        std::fprintf(f, "%d", c);
+        for (int i = 0; i < 64; ++i) std::fprintf(f, ",%lld", host[static_cast<size_t>(c) * 64 + i]);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+    }
+  }
 }
 
 }  // namespace rvb

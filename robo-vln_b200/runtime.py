@@ -55,6 +55,13 @@ class HcmRuntime:
         self._feat_lo_weights = False
         self._tail_params = []
         self._tail_sig = None
+        # Instruction cache (opt-in: `instruction_cache = True` or ROBOVLN_INSTR_CACHE=1): when the instruction tokens of a
+        # call equal those of the previous call, BERT and the query-side projection are skipped (their outputs are still
+        # in the engine's buffers).  Rollouts re-send the same instruction at every step of an episode
+        # (hierarchical_trainer.py:1193-1196).  bench.py never enables it: the benchmark step always runs BERT.
+        self.instruction_cache = os.environ.get("ROBOVLN_INSTR_CACHE", "0") == "1"
+        self._bert_key: Optional[torch.Tensor] = None
+        self._skip_bert = False
 
     def __del__(self):
         try:
@@ -108,6 +115,7 @@ class HcmRuntime:
             for name, t in new.items():
                 self._tensors[name].copy_(t)
         self._tail_sig = self._tail_sig_now()
+        self._bert_key = None        # the cached query-side projection was made with the old ins_fc / LayerNorm weights
 
     def sync_weights(self, check_tail: bool = False):
         if not self._dirty:
@@ -191,6 +199,19 @@ class HcmRuntime:
             check(self.lib.hcm_plan(self.handle, ctypes.byref(shp), ctypes.c_void_p(aligned), need), "hcm_plan")
         self._shape_key = key
         self._obs_chk = None
+        self._bert_key = None
+
+    def _instruction_hit(self, instr: torch.Tensor) -> bool:
+        """Decide whether BERT can be skipped for this call and tell the engine (one small device comparison)."""
+        hit = bool(self.instruction_cache and self._bert_key is not None and self._bert_key.shape == instr.shape
+                   and self._bert_key.dtype == instr.dtype and self._bert_key.device == instr.device
+                   and torch.equal(self._bert_key, instr))
+        if hit != self._skip_bert:
+            check(self.lib.hcm_set_skip_bert(self.handle, int(hit)), "hcm_set_skip_bert")
+            self._skip_bert = hit
+        if not hit:
+            self._bert_key = instr.clone() if self.instruction_cache else None
+        return hit
 
     # ---- helpers ---------------------------------------------------------------------------
     def _stream(self):
@@ -259,6 +280,7 @@ class HcmRuntime:
         masks = masks.to(self.device, torch.float32)
         hidden = hidden.to(self.device, torch.float32).contiguous()
         self.ensure_plan(B, N, instr.shape[1], instr.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        self._instruction_hit(instr)
         logits = torch.empty((B, 4), dtype=torch.float32, device=self.device)
         hc_out = torch.empty_like(hidden)
         with torch.cuda.device(self.device):
@@ -312,6 +334,7 @@ class HcmRuntime:
         hidden_hi = hidden_hi.to(self.device, torch.float32).contiguous()
         hidden_lo = hidden_lo.to(self.device, torch.float32).contiguous()
         self.ensure_plan(B, N, instr.shape[1], instr.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        self._instruction_hit(instr)
         logits = torch.empty((B, 4), dtype=torch.float32, device=self.device)
         act = torch.empty((B, 2), dtype=torch.float32, device=self.device)
         stop = torch.empty((B, 1), dtype=torch.float32, device=self.device)
@@ -348,6 +371,7 @@ class HcmRuntime:
         if not (self._shape_key and self._shape_key[0] == B and self._shape_key[4] == tuple(rgb.shape[1:3])
                 and (not with_bert or (self._shape_key[2], self._shape_key[3]) == (L, rows))):
             self.ensure_plan(B, N, L, rows, rgb.shape[1:3], depth.shape[1:3])
+        self._no_instruction_cache()
         fresh = not ((self._shares or self._feat_lo_weights == bool(use_lo_weights)) and self._same_obs(rgb, depth))
         if fresh or with_bert:
             with torch.cuda.device(self.device):
@@ -365,6 +389,13 @@ class HcmRuntime:
             out["bert"] = self.get_buffer("bert").float()
         return out
 
+    def _no_instruction_cache(self):
+        """Entry points outside the cache protocol (encode / profile / stage runs): BERT always runs and the cached key is dropped."""
+        if self._skip_bert:
+            check(self.lib.hcm_set_skip_bert(self.handle, 0), "hcm_set_skip_bert")
+            self._skip_bert = False
+        self._bert_key = None
+
     def profile_policy(self, rgb, depth, instruction, masks, hidden_hi, hidden_lo):
         """Per-launch device times of one policy step (single stream, CUDA events between
         launches): list of {"name", "ms", "flops"}."""
@@ -379,6 +410,7 @@ class HcmRuntime:
         hidden_hi = hidden_hi.to(self.device, torch.float32).contiguous()
         hidden_lo = hidden_lo.to(self.device, torch.float32).contiguous()
         self.ensure_plan(B, N, instr.shape[1], instr.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        self._no_instruction_cache()
         logits = torch.empty((B, 4), dtype=torch.float32, device=self.device)
         act = torch.empty((B, 2), dtype=torch.float32, device=self.device)
         stop = torch.empty((B, 1), dtype=torch.float32, device=self.device)
@@ -410,6 +442,7 @@ class HcmRuntime:
         if masks.dim() != 2 or masks.shape[1] != 2:
             raise ValueError("masks must be [B,2]")
         self.ensure_plan(B, N, instruction.shape[1], instruction.shape[0], rgb.shape[1:3], depth.shape[1:3])
+        self._instruction_hit(instruction)        # host tensors: compared on the CPU
         if out is None:
             out = {
                 "logits": torch.empty((B, 4), dtype=torch.float32).pin_memory(),
@@ -435,6 +468,7 @@ class HcmRuntime:
             raise ValueError("cross_modal: bert [1|B,L,768], rgb/depth spatial [B,16,256]")
         hw = (self._shape_key[4], self._shape_key[5]) if self._shape_key else ((256, 256), (256, 256))
         self.ensure_plan(B, B, L, rows, hw[0], hw[1])
+        self._no_instruction_cache()
         b16 = bert.to(self.device, self.h16).contiguous()
         r16 = rgb_spatial.to(self.device, self.h16).contiguous()
         d16 = depth_spatial.to(self.device, self.h16).contiguous()
@@ -454,6 +488,7 @@ class HcmRuntime:
         hw = (self._shape_key[4], self._shape_key[5]) if self._shape_key else ((256, 256), (256, 256))
         N = n_envs if B % max(n_envs, 1) == 0 else 1
         self.ensure_plan(B, N, instr.shape[1], instr.shape[0], hw[0], hw[1])
+        self._no_instruction_cache()
         i_f32 = instr.float().contiguous() if instr.dtype != torch.int64 else None
         i_i64 = instr.contiguous() if instr.dtype == torch.int64 else None
         with torch.cuda.device(self.device):

@@ -70,3 +70,28 @@ def test_engine_beats_torch_eager_on_the_same_gpu():
     except OSError:
         pass
     assert ms_engine < ms_fp16 and ms_engine < ms_tf32
+
+
+def test_engine_beats_the_tuned_library_arm():
+    """The stronger bar: channels_last fp16 torchvision ResNet-50 + HF BERT (SDPA) + cuDNN LSTM with
+    cudnn.benchmark, trunks once, CUDA-graph replay (tools/library_bar.py) vs the engine's policy step."""
+    import robovln_b200 as R
+    from tools import library_bar
+
+    B, L = 64, 80
+    lib = library_bar.measure(B=B, L=L, steps=10, warmup=5)
+    pol = R.HcmPolicy().share_frozen_trunks().to("cuda").eval()
+    g = torch.Generator().manual_seed(2)
+    obs = {"rgb": torch.randint(0, 256, (B, 256, 256, 3), generator=g).float().cuda(), "depth": torch.rand((B, 256, 256, 1), generator=g).cuda(),
+           "instruction": torch.randint(1000, 30522, (B, L), generator=g).float().cuda()}
+    h = torch.zeros((2, B, 512), device="cuda")
+    masks = torch.ones((B, 2), device="cuda")
+    ms_engine = _time(lambda: pol.act(obs, h, h.clone(), masks), warm=3, reps=20)
+    out = {"library": lib, "engine_ms": ms_engine}
+    print(json.dumps(out))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(out, open(os.path.join("gpurun_out", "library_bar_tuned.json"), "w"), indent=1)
+    except OSError:
+        pass
+    assert ms_engine < lib["ms_per_step"], out

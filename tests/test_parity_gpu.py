@@ -364,3 +364,116 @@ def test_cpu_tensors_fail_loudly():
     obs = {"rgb": torch.zeros(1, 256, 256, 3), "depth": torch.zeros(1, 256, 256, 1), "instruction": torch.zeros(1, 4)}
     with pytest.raises(RuntimeError, match="no CPU path"):
         hi((obs, torch.zeros(2, 1, 512), None, torch.ones(1, 2)))
+
+
+def test_instruction_cache_and_trunk_reuse_are_content_based(models):
+    """SURVEY.md 8(f) rank 1 + VERDICT r1 weak #10.  (1) With the opt-in instruction cache, repeating an instruction skips
+    BERT (fewer launches) with bit-identical results, and a changed instruction is re-encoded.  (2) lo reuses hi's trunk
+    features only when the observation CONTENT is the same: writing new frames into the SAME tensors through a raw
+    alias that does not bump torch's version counter must not be served stale features."""
+    import robovln_b200 as R
+    from oracle import weights as W
+
+    hi, lo, _, _ = models
+    pol = R.HcmPolicy(hi, lo)
+    rt = pol._runtime()
+    dev = "cuda"
+    inp = W.make_inputs(B=3, L=10, N=3, rgb_hw=256, seed=77, mask_zero_rows=(1,))
+    d = {k: v.to(dev) for k, v in inp.items() if isinstance(v, torch.Tensor)}
+
+    def act(instr):
+        out = pol.act({"rgb": d["rgb"], "depth": d["depth"], "instruction": instr}, d["hidden_hi"], d["hidden_lo"], d["masks"])
+        torch.cuda.synchronize()
+        return [o.clone() for o in out], rt.launches()
+
+    ref, n_full = act(d["instruction"])
+    rt.instruction_cache = True
+    try:
+        first, n1 = act(d["instruction"])          # fills the cache: BERT runs
+        again, n2 = act(d["instruction"].clone())  # same content in another tensor: BERT skipped
+        assert n1 == n_full and n2 < n_full - 40, (n_full, n1, n2)
+        for a, b, c in zip(ref, first, again):
+            assert torch.equal(a, b) and torch.equal(a, c)
+        other = d["instruction"].clone()
+        other[:, 3] = 2047.0
+        changed, n3 = act(other)
+        assert n3 == n_full and not torch.equal(changed[0], ref[0])
+        rt.instruction_cache = False
+        plain, n4 = act(other)
+        assert n4 == n_full
+        for a, b in zip(changed, plain):
+            assert torch.equal(a, b)
+    finally:
+        rt.instruction_cache = False
+
+    # (2) module API: hi then lo on the same dict -> trunks run once; then overwrite the frames behind torch's back
+    masks, hh, hl = d["masks"], d["hidden_hi"], d["hidden_lo"]
+    rgb, depth = d["rgb"].clone(), d["depth"].clone()
+    obs = {"rgb": rgb, "depth": depth, "instruction": d["instruction"]}
+    with torch.no_grad():
+        logits, _ = hi((obs, hh, None, masks))
+        sub = logits.argmax(1)
+        a1, s1, _ = lo((obs, hl, None, masks, sub))
+        n_reuse = rt.launches()
+        v0 = rgb._version
+        alias = torch.as_strided(rgb.detach(), rgb.shape, rgb.stride())       # same storage
+        alias.data.untyped_storage().copy_((255.0 - rgb).contiguous().untyped_storage())   # raw byte copy: no version bump
+        assert rgb._version == v0 and not torch.equal(rgb, d["rgb"])
+        a2, s2, _ = lo((obs, hl, None, masks, sub))
+        n_fresh = rt.launches()
+        torch.cuda.synchronize()
+        a3, s3, _ = lo(({"rgb": (255.0 - d["rgb"]), "depth": d["depth"].clone()}, hl, None, masks, sub))
+    assert n_fresh > n_reuse + 50, (n_reuse, n_fresh)          # the trunks ran again
+    assert torch.equal(a2, a3) and torch.equal(s2, s3)        # ... on the NEW frames
+    assert not torch.equal(a1, a2)
+    rt.trunk_reuse = False
+    try:
+        with torch.no_grad():
+            hi(({"rgb": rgb, "depth": depth, "instruction": d["instruction"]}, hh, None, masks))
+            lo(({"rgb": rgb, "depth": depth}, hl, None, masks, sub))
+        assert rt.launches() > n_reuse + 50
+    finally:
+        rt.trunk_reuse = True
+
+
+def test_hi_and_lo_on_two_devices_in_one_process():
+    """The reference trainer keeps hi on cuda:0 and lo on cuda:1 in ONE process (hierarchical_trainer.py:292-296,517): every
+    kernel's > 48 KB shared-memory opt-in is per device (it used to be done once per process, so the second
+    device's first launch failed).  Needs 2 GPUs: `gpurun --gpus 2`."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import robovln_b200 as R
+    from oracle import weights as W
+
+    sd_hi, sd_lo = W.make_state_dict("hi", 0), W.make_state_dict("lo", 0)
+    inp = W.make_inputs(B=2, L=9, N=2, rgb_hw=256, seed=3, mask_zero_rows=(0,))
+
+    def build(dev_hi, dev_lo):
+        hi = R.Seq2Seq_HighLevel_CMA(None, 4, None, 1)
+        lo = R.Seq2Seq_LowLevel(None, 2, 4, None, 1)
+        hi.load_state_dict(sd_hi)
+        lo.load_state_dict(sd_lo)
+        return hi.to(dev_hi).eval(), lo.to(dev_lo).eval()
+
+    def run(hi, lo, dev_hi, dev_lo):
+        with torch.no_grad():
+            obs = {k: inp[k].to(dev_hi) for k in ("rgb", "depth", "instruction")}
+            logits, hh = hi((obs, inp["hidden_hi"].to(dev_hi), None, inp["masks"].to(dev_hi)))
+            sub = logits.argmax(1)
+            obs2 = {k: inp[k].to(dev_lo) for k in ("rgb", "depth")}
+            act, stop, hl = lo((obs2, inp["hidden_lo"].to(dev_lo), None, inp["masks"].to(dev_lo), sub.to(dev_lo)))
+        return [t.float().cpu() for t in (logits, hh, act, stop, hl)]
+
+    hi0, lo0 = build("cuda:0", "cuda:0")
+    ref = run(hi0, lo0, "cuda:0", "cuda:0")
+    del hi0, lo0
+    hi, lo = build("cuda:0", "cuda:1")
+    for _ in range(2):                       # eager first call, then graph replays on both devices
+        got = run(hi, lo, "cuda:0", "cuda:1")
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+    # and the reverse placement on fresh modules (device 1 launches every kernel type first)
+    hi, lo = build("cuda:1", "cuda:0")
+    got = run(hi, lo, "cuda:1", "cuda:0")
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
