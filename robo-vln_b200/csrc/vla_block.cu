@@ -51,8 +51,10 @@ constexpr int VB_OFF_P = VB_OFF_B;               // P: [128 x 64] un-normalised 
 constexpr int VB_OFF_V = VB_OFF_B + 16384;       // V: 4 heads x [16 keys x 64 dims];                                  has retired
 constexpr int VB_OFF_RING = 131072;
 constexpr int VB_OFF_MISC = VB_OFF_RING + VB_NS * VB_SLOT;
-constexpr int VB_MISC_BYTES = 4096;              // barriers, c[64], LayerNorm partials [2][128] float2, column partials
-constexpr int VB_SMEM = VB_OFF_MISC + VB_MISC_BYTES + 1024 /*align slack*/;
+constexpr int VB_MISC_BYTES = 4096;              // barriers, c[64], LayerNorm partials [2][128] float2
+constexpr int VB_OFF_PAR = VB_OFF_MISC + VB_MISC_BYTES;   // fp32 bo | ln1g | ln1b | b2 | ln2g | ln2b (256 each) | b1 (1024)
+constexpr int VB_PAR_FLOATS = 6 * 256 + 1024;
+constexpr int VB_SMEM = VB_OFF_PAR + VB_PAR_FLOATS * 4 + 1024 /*align slack*/;
 static_assert(VB_SMEM <= 232448, "vla_block: shared memory over the 227 KB limit");
 
 constexpr int TM_Y = 0;       // TMEM columns: O (P.V) and later the fc2 accumulator Y
@@ -121,20 +123,83 @@ RVB_DEVICE void ffn_step(int step, int& is_fc2, int& chunk) {
   else { is_fc2 = (step & 1) ? 0 : 1; chunk = (step & 1) ? (step + 1) >> 1 : (step >> 1) - 1; }
 }
 
-// LayerNorm over 256 columns of which this thread holds 128 (v, already bias + residual); the partner warp of the
-// same lane quadrant holds the other 128.  Returns (scale, shift) with y = v * scale + shift = (v - mean) * rstd.
-RVB_DEVICE void ln_pair_stats(const float (&v)[128], float2* xchg, int half, int row, int quad, float eps, float& a, float& b) {
+// LayerNorm epilogue over the 256 fp32 accumulator columns of this thread's row, of which this thread owns 128
+// (tcol = first of them); the partner warp of the same lane quadrant owns the other 128.
+//   v = acc + bias + residual (16-bit, swizzled K-major sub-tiles res0 / res0 + VB_SUB)        pass 1, written back to TMEM
+//   y = (v - mean) * rstd * gamma + beta -> 16-bit, same layout, dst0 / dst0 + VB_SUB            pass 2
+// Two passes over TMEM keep the live register set small, so the compiler can keep many shared-memory loads in flight
+// (holding all 128 values in registers measured 8.5k cycles per LayerNorm, latency bound).  Parameters come from the
+// shared-memory copy made at kernel start: with 218 KB of shared memory in use the L1 has ~10 KB left and global
+// parameter loads thrash it.
+template <class OnChunk>
+RVB_DEVICE void ln_epilogue(uint32_t tcol, const uint8_t* res0, uint8_t* dst0, const float* bias, const float* gamma,
+                            const float* beta, float2* xchg, int half, int row, int quad, float eps, OnChunk&& on_chunk) {
+  const int sw = row & 7;
   float s = 0.0f, q = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 128; ++j) { s += v[j]; q = fmaf(v[j], v[j], q); }
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t u[32];
+    tmem_ld_32x32(tcol + ch * 32, u);
+    uint4 r[4];
+    float4 bb[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      r[j] = *reinterpret_cast<const uint4*>(res0 + (ch >> 1) * VB_SUB + row * 128 + ((((ch & 1) * 4 + j) ^ sw) << 4));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(bias + ch * 32 + j * 4);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[4 * j] = __uint_as_float(u[4 * j]) + bb[j].x; f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) + bb[j].y;
+      f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) + bb[j].z; f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) + bb[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) add_chunk(&f[8 * j], r[j]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s += f[j];
+      q = fmaf(f[j], f[j], q);
+      u[j] = __float_as_uint(f[j]);
+    }
+    tmem_st_32x32(tcol + ch * 32, u);
+  }
+  tmem_st_wait();
   xchg[half * 128 + row] = make_float2(s, q);
   named_bar(1 + quad, 64);
   const float2 p0 = xchg[row], p1 = xchg[128 + row];     // fixed order: both halves compute identical totals
   named_bar(1 + quad, 64);                               // the slots may be rewritten by the next LayerNorm
   const float mean = (p0.x + p1.x) * (1.0f / 256.0f);
   const float var = fmaxf((p0.y + p1.y) * (1.0f / 256.0f) - mean * mean, 0.0f);
-  a = rsqrtf(var + eps);
-  b = -mean * a;
+  const float a = rsqrtf(var + eps);
+  const float b = -mean * a;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t u[32];
+    tmem_ld_32x32(tcol + ch * 32, u);
+    float4 gg[8], ee[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gg[j] = *reinterpret_cast<const float4*>(gamma + ch * 32 + j * 4);
+      ee[j] = *reinterpret_cast<const float4*>(beta + ch * 32 + j * 4);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g[8];
+      g[0] = fmaf(fmaf(__uint_as_float(u[8 * j]), a, b), gg[2 * j].x, ee[2 * j].x);
+      g[1] = fmaf(fmaf(__uint_as_float(u[8 * j + 1]), a, b), gg[2 * j].y, ee[2 * j].y);
+      g[2] = fmaf(fmaf(__uint_as_float(u[8 * j + 2]), a, b), gg[2 * j].z, ee[2 * j].z);
+      g[3] = fmaf(fmaf(__uint_as_float(u[8 * j + 3]), a, b), gg[2 * j].w, ee[2 * j].w);
+      g[4] = fmaf(fmaf(__uint_as_float(u[8 * j + 4]), a, b), gg[2 * j + 1].x, ee[2 * j + 1].x);
+      g[5] = fmaf(fmaf(__uint_as_float(u[8 * j + 5]), a, b), gg[2 * j + 1].y, ee[2 * j + 1].y);
+      g[6] = fmaf(fmaf(__uint_as_float(u[8 * j + 6]), a, b), gg[2 * j + 1].z, ee[2 * j + 1].z);
+      g[7] = fmaf(fmaf(__uint_as_float(u[8 * j + 7]), a, b), gg[2 * j + 1].w, ee[2 * j + 1].w);
+      const uint4 yq = pack_chunk(g);
+      *reinterpret_cast<uint4*>(dst0 + (ch >> 1) * VB_SUB + row * 128 + ((((ch & 1) * 4 + j) ^ sw) << 4)) = yq;
+      on_chunk(ch * 32 + j * 8, yq);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(VB_THREADS, 1)
@@ -159,6 +224,7 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
   float* s_c = reinterpret_cast<float*>(smem + VB_OFF_MISC + 256);          // [64] c[key*4 + head]
   float2* s_ln = reinterpret_cast<float2*>(smem + VB_OFF_MISC + 512);       // [2][128]
+  float* s_par = reinterpret_cast<float*>(smem + VB_OFF_PAR);               // bo | ln1g | ln1b | b2 | ln2g | ln2b | b1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x, mod = blockIdx.y;
@@ -317,6 +383,13 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
     const int et = threadIdx.x - 64;      // 0..255
     // c[key*4 + head] = K_h[key] . bq_h  (kvx columns 1024..1027 of each visual-cell row)
     if (et < 64) s_c[et] = from_h16(p.kvx[static_cast<long long>(cell_row0 + (et >> 2)) * p.kvx_pitch + 1024 + (et & 3)]);
+    {   // epilogue parameters -> shared memory (constant weights: 10 KB, read ~100 times per thread below)
+      const float* srcs[6] = {p.bo, p.ln1g, p.ln1b, p.b2, p.ln2g, p.ln2b};
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s_par[i * 256 + et] = __ldg(srcs[i] + et);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_par[6 * 256 + i * 256 + et] = __ldg(p.b1 + i * 256 + et);
+    }
     named_bar(5, VB_EPI_WARPS * 32);
 
     // ---- softmax over the 16 keys of this thread's two heads (2*half, 2*half + 1); S column = key*4 + head
@@ -395,33 +468,9 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       mbar_wait(&one[5], 0);
       tc_fence_after();
       if (et == 0) VB_STAMP(37);
-      float v[128];
-      tmem_ld_128(trow + TM_H + half * 128, v);
       const int n0 = half * 128;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {   // 16-byte chunks: sub-tile 2*half + j/8, chunk j%8
-        const uint4 r = *reinterpret_cast<const uint4*>(bufA + (2 * half + (j >> 3)) * VB_SUB + row * 128 + (((j & 7) ^ sw) << 4));
-        add_chunk(&v[j * 8], r);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bo + n0 + j * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bo + n0 + j * 8 + 4));
-        v[j * 8] += b0.x; v[j * 8 + 1] += b0.y; v[j * 8 + 2] += b0.z; v[j * 8 + 3] += b0.w;
-        v[j * 8 + 4] += b1.x; v[j * 8 + 5] += b1.y; v[j * 8 + 6] += b1.z; v[j * 8 + 7] += b1.w;
-      }
-      float a, b;
-      ln_pair_stats(v, s_ln, half, row, quad, p.eps, a, b);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float g[8];
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln1g + n0 + j * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln1g + n0 + j * 8 + 4));
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln1b + n0 + j * 8));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.ln1b + n0 + j * 8 + 4));
-        g[0] = fmaf(fmaf(v[j * 8], a, b), g0.x, e0.x); g[1] = fmaf(fmaf(v[j * 8 + 1], a, b), g0.y, e0.y);
-        g[2] = fmaf(fmaf(v[j * 8 + 2], a, b), g0.z, e0.z); g[3] = fmaf(fmaf(v[j * 8 + 3], a, b), g0.w, e0.w);
-        g[4] = fmaf(fmaf(v[j * 8 + 4], a, b), g1.x, e1.x); g[5] = fmaf(fmaf(v[j * 8 + 5], a, b), g1.y, e1.y);
-        g[6] = fmaf(fmaf(v[j * 8 + 6], a, b), g1.z, e1.z); g[7] = fmaf(fmaf(v[j * 8 + 7], a, b), g1.w, e1.w);
-        *reinterpret_cast<uint4*>(bufB + (2 * half + (j >> 3)) * VB_SUB + row * 128 + (((j & 7) ^ sw) << 4)) = pack_chunk(g);
-      }
+      ln_epilogue(trow + TM_H + n0, bufA + 2 * half * VB_SUB, bufB + 2 * half * VB_SUB, s_par + n0, s_par + 256 + n0,
+                  s_par + 512 + n0, s_ln, half, row, quad, p.eps, [](int, const uint4&) {});
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -445,11 +494,11 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       if (lane == 0) mbar_arrive(&hempty[b]);           // accumulator drained: fc1(c + 2) may overwrite it
       if (c >= 2) mbar_wait(&sempty[b], static_cast<uint32_t>(((c >> 1) - 1) & 1));   // fc2(c - 2) has read this H buffer
       uint8_t* dst = bufA + (b * 2 + half) * VB_SUB + row * 128;
-      const float* bias = p.b1 + ((c + rc) & 7) * 128 + half * 64;
+      const float* bias = s_par + 6 * 256 + ((c + rc) & 7) * 128 + half * 64;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j * 8 + 4));
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + j * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + j * 8 + 4);
         const uint32_t* src = (j < 4) ? &r0[j * 8] : &r1[(j - 4) * 8];
         float g[8];
         g[0] = fmaxf(__uint_as_float(src[0]) + b0.x, 0.0f); g[1] = fmaxf(__uint_as_float(src[1]) + b0.y, 0.0f);
@@ -469,43 +518,27 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
       mbar_wait(&one[7], 0);
       tc_fence_after();
       if (et == 0) VB_STAMP(39);
-      float v[128];
-      tmem_ld_128(trow + TM_Y + half * 128, v);
       const int n0 = half * 128;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const uint4 r = *reinterpret_cast<const uint4*>(bufB + (2 * half + (j >> 3)) * VB_SUB + row * 128 + (((j & 7) ^ sw) << 4));
-        add_chunk(&v[j * 8], r);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b2 + n0 + j * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b2 + n0 + j * 8 + 4));
-        v[j * 8] += b0.x; v[j * 8 + 1] += b0.y; v[j * 8 + 2] += b0.z; v[j * 8 + 3] += b0.w;
-        v[j * 8 + 4] += b1.x; v[j * 8 + 5] += b1.y; v[j * 8 + 6] += b1.z; v[j * 8 + 7] += b1.w;
-      }
-      float a, b;
-      ln_pair_stats(v, s_ln, half, row, quad, p.eps, a, b);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float g[8];
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln2g + n0 + j * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln2g + n0 + j * 8 + 4));
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln2b + n0 + j * 8));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.ln2b + n0 + j * 8 + 4));
-        g[0] = fmaf(fmaf(v[j * 8], a, b), g0.x, e0.x); g[1] = fmaf(fmaf(v[j * 8 + 1], a, b), g0.y, e0.y);
-        g[2] = fmaf(fmaf(v[j * 8 + 2], a, b), g0.z, e0.z); g[3] = fmaf(fmaf(v[j * 8 + 3], a, b), g0.w, e0.w);
-        g[4] = fmaf(fmaf(v[j * 8 + 4], a, b), g1.x, e1.x); g[5] = fmaf(fmaf(v[j * 8 + 5], a, b), g1.y, e1.y);
-        g[6] = fmaf(fmaf(v[j * 8 + 6], a, b), g1.z, e1.z); g[7] = fmaf(fmaf(v[j * 8 + 7], a, b), g1.w, e1.w);
-        const uint4 yq = pack_chunk(g);
-        *reinterpret_cast<uint4*>(bufB + (2 * half + (j >> 3)) * VB_SUB + row * 128 + (((j & 7) ^ sw) << 4)) = yq;
-        if (p.y_tokens != nullptr && row < p.L)
-          *reinterpret_cast<uint4*>(p.y_tokens + ((static_cast<long long>(mod) * p.B + env) * p.L + row) * 256 + n0 + j * 8) = yq;
-      }
+      h16* ytok = (p.y_tokens != nullptr && row < p.L) ? p.y_tokens + ((static_cast<long long>(mod) * p.B + env) * p.L + row) * 256 + n0 : nullptr;
+      ln_epilogue(trow + TM_Y + n0, bufB + 2 * half * VB_SUB, bufB + 2 * half * VB_SUB, s_par + 768 + n0, s_par + 1024 + n0,
+                  s_par + 1280 + n0, s_ln, half, row, quad, p.eps, [ytok](int col, const uint4& yq) {
+                    if (ytok != nullptr) *reinterpret_cast<uint4*>(ytok + col) = yq;
+                  });
       named_bar(5, VB_EPI_WARPS * 32);
       // column `et` over the valid token rows (16-bit Y, fp32 sum, fixed order)
       const uint8_t* colp = bufB + (et >> 6) * VB_SUB + (et & 7) * 2;
       const int chunk = (et & 63) >> 3;
-      float acc = 0.0f;
-      for (int r = 0; r < p.L; ++r)
-        acc += from_h16(*reinterpret_cast<const h16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
+      float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // rows r = 4i + k go to accumulator k: independent chains, fixed order
+      int r = 0;
+      for (; r + 8 <= p.L; r += 8) {
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = from_h16(*reinterpret_cast<const h16*>(colp + (r + k) * 128 + ((chunk ^ k) << 4)));   // (r + k) & 7 == k
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc4[k & 3] += x[k];
+      }
+      for (; r < p.L; ++r) acc4[r & 3] += from_h16(*reinterpret_cast<const h16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
+      const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       p.out[static_cast<long long>(env) * p.out_pitch + mod * 256 + et] = to_h16(acc / static_cast<float>(p.L));
       if (et == 0) VB_STAMP(56);
     }

@@ -71,3 +71,34 @@ def test_golden_features_are_nontrivial(golden_dir):
     assert (rgb > 0).mean() > 0.2 and rgb.std() > 0.05
     assert (dep > 0).mean() > 0.2 and dep.std() > 0.05
     assert np.abs(g["hi.logits"][0] - g["hi.logits"][1]).max() > 1e-3
+
+
+def test_16bit_operand_rounding_floor(sds):
+    """How much error 16-bit OPERANDS alone cost on this path, measured with PyTorch's own mixed-precision kernels on the
+    CPU (torch.autocast: conv / linear / matmul inputs and outputs rounded to the 16-bit type, fp32 accumulation and
+    fp32 normalisation layers -- the same roundings the engine performs), against the fp32 oracle on BASELINE cfg1.
+
+    fp16 (11-bit significand) stays well inside north_star's 1e-2; bf16 (8-bit significand) does NOT: the recurrent state
+    is off by ~2.5e-2 with PyTorch's own bf16 kernels.  The 1e-2 "bf16" tolerance is therefore a property of the number
+    format on this 100+-layer path, not of an implementation -- which is why the engine's default operand type is fp16
+    (same width, same tensor-core rate) and why the bf16 build is held to the bf16 floor measured here
+    (tests/test_parity_gpu.py::test_bf16_build_end_to_end)."""
+    hi_sd, lo_sd = sds
+    inp = W.make_inputs(**CASES["cfg1_b2_l20"])
+
+    def run():
+        with torch.no_grad():
+            logits, hh = O.hi_forward(hi_sd, inp["rgb"], inp["depth"], inp["instruction"], inp["hidden_hi"], inp["masks"])
+            act, stop, hl = O.lo_forward(lo_sd, inp["rgb"], inp["depth"], inp["hidden_lo"], inp["masks"], inp["sub_goal"])
+        return {"logits": logits.float(), "hidden_hi": hh.float(), "actions": act.float(), "stop": stop.float(), "hidden_lo": hl.float()}
+
+    ref = run()
+    errs = {}
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        with torch.autocast("cpu", dtype=dt):
+            got = run()
+        errs[name] = {k: float((got[k] - ref[k]).abs().max()) for k in ref}
+    print("16-bit operand rounding floor (torch.autocast on the CPU oracle):", errs)
+    assert max(errs["fp16"].values()) < 1e-2, errs
+    assert max(errs["bf16"]["hidden_hi"], errs["bf16"]["hidden_lo"]) > 1e-2, errs       # inherent to 8-bit significands
+    assert max(errs["bf16"].values()) < 6e-2, errs

@@ -321,8 +321,11 @@ def test_graph_replay_matches_eager(models):
 def test_bf16_build_end_to_end(golden_dir):
     """librobovln_b200_bf16.so through the same modules (ROBOVLN_DTYPE=bf16).  bf16 rounding
     (8-bit significand) amplified by the 54-layer GroupNorm trunk and 12 BERT layers reaches
-    ~2.5e-2 on the LSTM state with these random weights, so this build is held to 5e-2 on the
-    outputs / 1e-1 on intermediates; the fp16 default build is the one held to north_star's 1e-2."""
+    ~2.5e-2 on the LSTM state with these random weights -- and so does PyTorch's OWN bf16 path: the bound applied
+    here is the "bf16 operand floor" measured live with torch.autocast(bfloat16) on the CPU oracle
+    (tests/test_oracle_golden.py::test_16bit_operand_rounding_floor explains why north_star's 1e-2 is out of reach
+    for any bf16-operand implementation of this path).  The engine's bf16 build must be at least as accurate as
+    1.5x that floor (and never worse than 5e-2); the fp16 default build is the one held to 1e-2."""
     import robovln_b200 as R
     from oracle import weights as W
     from oracle.make_golden import CASES
@@ -350,6 +353,19 @@ def test_bf16_build_end_to_end(golden_dir):
         _out(act, gold["lo.actions"], "lo.actions", 5e-2)
         _out(stop, gold["lo.stop"], "lo.stop", 5e-2)
         _out(hid_lo, gold["lo.hidden"], "lo.hidden", 5e-2)
+        # the bf16 operand floor: PyTorch's own bf16 mixed precision on the same model and inputs
+        from oracle import hcm_oracle as O
+
+        sd_hi, sd_lo = W.make_state_dict("hi", 0), W.make_state_dict("lo", 0)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            f_logits, f_hh = O.hi_forward(sd_hi, inp["rgb"], inp["depth"], inp["instruction"], inp["hidden_hi"], inp["masks"])
+            f_act, f_stop, f_hl = O.lo_forward(sd_lo, inp["rgb"], inp["depth"], inp["hidden_lo"], inp["masks"], inp["sub_goal"])
+        for name, got, floor_out, ref in (("hi.logits", logits, f_logits, gold["hi.logits"]), ("hi.hidden", hid_hi, f_hh, gold["hi.hidden"]),
+                                          ("lo.actions", act, f_act, gold["lo.actions"]), ("lo.stop", stop, f_stop, gold["lo.stop"]),
+                                          ("lo.hidden", hid_lo, f_hl, gold["lo.hidden"])):
+            floor = float(np.abs(floor_out.float().numpy() - ref).max())
+            err = float(np.abs(got.float().cpu().numpy() - ref).max())
+            assert err <= max(1.5 * floor, 1e-2), f"{name}: engine bf16 err {err:.3e} vs torch bf16 autocast floor {floor:.3e}"
     finally:
         if old is None:
             os.environ.pop("ROBOVLN_DTYPE", None)
@@ -477,3 +493,37 @@ def test_hi_and_lo_on_two_devices_in_one_process():
     got = run(hi, lo, "cuda:1", "cuda:0")
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
+
+
+def test_fp16_range_headroom():
+    """fp16's range (65504) against large activations (VERDICT r1 weak #1b).  The RGB trunk is the only sub-network on the
+    path that is not re-normalised layer by layer (eval-mode BatchNorm is folded into the convs), so its activation scale
+    is set by the weights.  Scale the stem so that the layer-4 features reach >= 1e4 -- two to three orders above what a
+    trained ResNet-50 produces -- and require the same relative accuracy as at scale 1: every intermediate store
+    saturates instead of overflowing (common.cuh sat_h), and nothing in between loses precision."""
+    import robovln_b200 as R
+    from oracle import hcm_oracle as O
+    from oracle import weights as W
+
+    sd = W.make_state_dict("hi", 0)
+    inp = W.make_inputs(B=2, L=8, N=2, rgb_hw=256, seed=9, mask_zero_rows=())
+    with torch.no_grad():
+        base = float(O.rgb_trunk(sd, "rgb_encoder.", inp["rgb"][:1]).abs().max())
+    scale = 1.2e4 / base
+    sd = dict(sd)
+    sd["rgb_encoder.cnn.conv1.weight"] = sd["rgb_encoder.cnn.conv1.weight"] * scale
+    sd["rgb_encoder.cnn.bn1.bias"] = sd["rgb_encoder.cnn.bn1.bias"] * scale
+    sd["rgb_encoder.cnn.bn1.running_mean"] = sd["rgb_encoder.cnn.bn1.running_mean"] * scale
+    with torch.no_grad():
+        ref = O.rgb_encoder_hi(sd, inp["rgb"])                    # [B,2112,4,4]
+    assert float(ref.abs().max()) >= 5e3, float(ref.abs().max())
+    hi = R.Seq2Seq_HighLevel_CMA(None, 4, None, 1)
+    hi.load_state_dict(sd)
+    hi.cuda().eval()
+    assert hi.runtime().dtype_name == "fp16"
+    obs = {k: inp[k].cuda() for k in ("rgb", "depth", "instruction")}
+    with torch.no_grad():
+        hi((obs, inp["hidden_hi"].cuda(), None, inp["masks"].cuda()))
+    tok = hi.runtime().get_buffer("rgb_tokens").float().cpu()      # [B,16,2112]
+    assert torch.isfinite(tok).all()
+    _mid(tok.permute(0, 2, 1).reshape(2, 2112, 4, 4)[:, :2048], ref[:, :2048], "rgb features at 1e4 scale")
