@@ -505,17 +505,24 @@ def run_train(args):
     tgt_act = torch.rand((T, 2), generator=g).to(dev)
     tgt_stop = (torch.rand((T, 1), generator=g) > 0.9).float().to(dev)
     sub = torch.randint(0, 5, (T,), generator=g).to(dev)
-    params = [p for m in (hi, lo) for p in m.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-3)
+    # optimizers as the reference configures them (hierarchical_trainer.py:329-334): AdamW for hi, Adam (L2 decay) for lo --
+    # here the fused single-launch versions (robo-vln_b200/optim.py); losses with the trainer's masking, fused (losses.py)
+    opt_hi = R.optim.FusedAdamW([p for p in hi.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-3)
+    opt_lo = R.optim.FusedAdam([p for p in lo.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-3)
+    sensor = (tgt_hi + 1).float()                 # vln_oracle_action_sensor column: 0 = ignore, k = sub-goal k - 1
+    h0 = torch.zeros((2, 1, 512), device=dev)
 
     def step():
-        opt.zero_grad(set_to_none=True)
+        opt_hi.zero_grad(set_to_none=True)
+        opt_lo.zero_grad(set_to_none=True)
         obs = {"rgb": rgb, "depth": depth, "instruction": ids}
-        logits, _ = hi((obs, torch.zeros((2, 1, 512), device=dev), None, masks))
-        F.cross_entropy(logits, tgt_hi, ignore_index=-1).backward()
-        act, stop, _ = lo((obs, torch.zeros((2, 1, 512), device=dev), None, masks, sub))
-        (F.mse_loss(act, tgt_act) + F.binary_cross_entropy_with_logits(stop, tgt_stop)).backward()
-        opt.step()       # the engine runs only the FROZEN encoders in train mode: no re-pack of its weights per step
+        logits, _ = hi((obs, h0, None, masks))
+        R.losses.hi_loss(logits, sensor).backward()
+        opt_hi.step()
+        act, stop, _ = lo((obs, h0, None, masks, sub))
+        la, ls = R.losses.lo_loss(act, stop, tgt_act, tgt_stop)
+        (la + ls).backward()
+        opt_lo.step()    # the engine runs only the FROZEN encoders in train mode: no re-pack of its weights per step
         return logits
 
     for _ in range(max(args.warmup, 3)):
@@ -534,7 +541,8 @@ def run_train(args):
         "obs_per_sec": obs_s, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "dtype": hi.runtime().dtype_name, "data": "synthetic",
         "config": {"workload": "cfg5: DAgger inner loop, trajectory T=%d (N=1), shared %d-token instruction, hi fwd+CE+bwd, "
-                               "lo fwd+MSE+BCE+bwd, AdamW step; frozen encoders on the engine, trainable tail in torch autograd" % (T, L)},
+                               "lo fwd+MSE+BCE+bwd, fused AdamW (hi) / Adam (lo) steps and fused losses; frozen encoders on the engine, "
+                               "trainable tail's linear / LSTM backward in torch autograd" % (T, L)},
         "outputs_finite": bool(torch.isfinite(out).all().item()),
     }), flush=True)
 

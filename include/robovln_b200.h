@@ -207,6 +207,26 @@ int rvb_maxpool3x3s2(const void* in_bf16, void* out_bf16, int NB, int H, int W, 
 int rvb_rgb_stem_im2col(const float* rgb, void* out_bf16, int NB, int H, int W, int Kpitch, void* stream);
 int rvb_depth_stem(const float* depth, const float* w, void* out_bf16, int NB, int H, int W, void* stream);
 
+/* ---- DAgger update tail (csrc/train.cu; robo_vln_baselines/hierarchical_trainer.py:492-560) --------------------
+ * rvb_hi_loss: logits.masked_fill_(oracle == 0, 0); CrossEntropyLoss(ignore_index=-1)(logits, oracle - 1) (:506-511).
+ *   oracle = the vln_oracle_action_sensor column (float32 or int64, one of the two pointers); loss_out2 = {loss, #rows
+ *   counted}; dlogits (optional) = d loss / d logits [T, C].
+ * rvb_lo_loss: actions.masked_fill_(corrected == 0, 0); MSELoss + BCEWithLogitsLoss over oracle_stop != -1 (:539-553).
+ *   loss_out3 = {action loss, stop loss, #stop rows counted}; d_actions [T, A] / d_stop [T] (optional) = gradient of their sum.
+ * rvb_fused_adam: one launch updates n_tensors fp32 tensors (device arrays of device pointers; chunk_start = prefix sum
+ *   of ceil(numel / rvb_adam_chunk_elems()), n_tensors + 1 entries).  decoupled = 1: torch.optim.AdamW (hi, :329);
+ *   0: torch.optim.Adam with L2 weight decay (lo, :332).  step_size = lr / (1 - beta1^step),
+ *   bias_correction2_sqrt = sqrt(1 - beta2^step), computed by the caller in double precision as torch does. */
+int rvb_hi_loss(const float* logits, const float* oracle_f32, const int64_t* oracle_i64, int T, int C, float* loss_out2,
+                float* dlogits, void* stream);
+int rvb_lo_loss(const float* actions, const float* corrected, const float* stop_logit, const float* oracle_stop, int T, int A,
+                float* loss_out3, float* d_actions, float* d_stop, void* stream);
+int rvb_fused_adam(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                   const int64_t* numel, const int64_t* chunk_start, int n_tensors, int64_t total_chunks, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int decoupled, float step_size, float bias_correction2_sqrt,
+                   void* stream);
+int rvb_adam_chunk_elems(void);
+
 /* ---- host-side plumbing kernels (csrc/prep.cu) --------------------------------------------
  * rvb_pack_weight: fp32 parameter [O, I, KH, KW] (nn.Conv2d / nn.Linear layout, the reference's state_dict) ->
  *   16-bit [O, KH*KW*I] with k = (r*KW + s)*I + c, rows `out_pitch` elements apart (0 = dense); with bn_* given,

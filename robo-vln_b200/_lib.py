@@ -64,6 +64,11 @@ SYMBOLS = {
     "rvb_bert_attention_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_vla_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_vla_block": (c_int, [c_void_p] * 12 + [c_float, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "rvb_hi_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rvb_lo_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rvb_fused_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_float,
+                               c_float, c_float, c_int, c_float, c_float, c_void_p]),
+    "rvb_adam_chunk_elems": (c_int, []),
     "rvb_lstm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                          c_void_p]),
     "rvb_maxpool3x3s2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

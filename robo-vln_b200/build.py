@@ -20,7 +20,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "lstm.cu", "prep.cu", "vla_block.cu", "engine.cu", "capi.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "lstm.cu", "prep.cu", "vla_block.cu", "train.cu", "engine.cu", "capi.cu"]
 HEADERS = ["common.cuh", "h16.h", "rvb.h", "engine.h", os.path.join("..", "..", "include", "robovln_b200.h")]
 VARIANTS = {"fp16": ("librobovln_b200.so", ["-DRVB_BF16=0"]), "bf16": ("librobovln_b200_bf16.so", ["-DRVB_BF16=1"])}
 

@@ -363,6 +363,30 @@ int rvb_vla_block(const void* q0_h16, const void* kvx_h16, const void* wo_h16, c
   });
 }
 
+int rvb_hi_loss(const float* logits, const float* oracle_f32, const int64_t* oracle_i64, int T, int C, float* loss_out2,
+                float* dlogits, void* stream) {
+  return guarded([&] { hi_loss(logits, oracle_f32, oracle_i64, T, C, loss_out2, dlogits, S(stream)); });
+}
+
+int rvb_lo_loss(const float* actions, const float* corrected, const float* stop_logit, const float* oracle_stop, int T, int A,
+                float* loss_out3, float* d_actions, float* d_stop, void* stream) {
+  return guarded([&] { lo_loss(actions, corrected, stop_logit, oracle_stop, T, A, loss_out3, d_actions, d_stop, S(stream)); });
+}
+
+int rvb_fused_adam(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                   const int64_t* numel, const int64_t* chunk_start, int n_tensors, int64_t total_chunks, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int decoupled, float step_size, float bias_correction2_sqrt,
+                   void* stream) {
+  return guarded([&] {
+    fused_adam(reinterpret_cast<float* const*>(params), reinterpret_cast<const float* const*>(grads),
+               reinterpret_cast<float* const*>(exp_avg), reinterpret_cast<float* const*>(exp_avg_sq),
+               reinterpret_cast<const long long*>(numel), reinterpret_cast<const long long*>(chunk_start), n_tensors, total_chunks, lr,
+               beta1, beta2, eps, weight_decay, decoupled, step_size, bias_correction2_sqrt, S(stream));
+  });
+}
+
+int rvb_adam_chunk_elems(void) { return adam_chunk_elems(); }
+
 int rvb_lstm(const float* gx, const void* whh_bf16, const float* masks, int mask_stride, const float* hc_in,
              float* hc_out, float* h_scratch, float* y, int T, int N, void* stream) {
   return guarded([&] { lstm_forward(gx, B16(whh_bf16), masks, mask_stride, hc_in, hc_out, h_scratch, y, T, N, S(stream)); });

@@ -282,6 +282,16 @@ void compare_many(const void* const* a_dev, const void* const* b_dev, const long
                   cudaStream_t s);
 void checksum(const void* p, size_t bytes, unsigned long long* out2_dev, cudaStream_t s);
 
+// train.cu -- DAgger update tail: fused losses (value + gradient in one launch) and multi-tensor Adam / AdamW
+void hi_loss(const float* logits, const float* oracle_f, const int64_t* oracle_i, int T, int C, float* loss_out, float* dlogits,
+             cudaStream_t s);
+void lo_loss(const float* actions, const float* corrected, const float* stop, const float* oracle_stop, int T, int A, float* loss_out,
+             float* d_actions, float* d_stop, cudaStream_t s);
+void fused_adam(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                const long long* numel, const long long* chunk_start, int n_tensors, long long total_chunks, float lr, float b1,
+                float b2, float eps, float wd, int decoupled, float step_size, float bc2_sqrt, cudaStream_t s);
+int adam_chunk_elems();
+
 // lstm.cu
 void lstm_forward(const float* gx, const h16* whh, const float* masks, int mask_stride, const float* hc_in,
                   float* hc_out, float* h_scratch, float* y, int T, int N, cudaStream_t s);
