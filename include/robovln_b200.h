@@ -201,6 +201,9 @@ int rvb_vla_block(const void* q0_h16, const void* kvx_h16, const void* wo_h16, c
                   const float* bo, const float* b1, const float* b2, const float* ln1g, const float* ln1b,
                   const float* ln2g, const float* ln2b, float eps, int B, int L, int q_shared, void* out_h16,
                   int64_t out_pitch, void* y_tokens_h16, void* stream);
+/* which implementation rvb_vla_block / the engine launch: 0 = default (the CTA-pair kernel; ROBOVLN_VLA_PAIR=0 selects the
+ * other), 1 = one CTA per (environment, modality) tile, 2 = one 2-CTA cluster (cta_group::2 MMAs) per environment */
+int rvb_vla_block_variant(int variant);
 int rvb_lstm(const float* gx, const void* whh_bf16, const float* masks, int mask_stride,
              const float* hc_in, float* hc_out, float* h_scratch, float* y, int T, int N, void* stream);
 int rvb_maxpool3x3s2(const void* in_bf16, void* out_bf16, int NB, int H, int W, int C, void* stream);
@@ -222,8 +225,8 @@ int rvb_hi_loss(const float* logits, const float* oracle_f32, const int64_t* ora
 int rvb_lo_loss(const float* actions, const float* corrected, const float* stop_logit, const float* oracle_stop, int T, int A,
                 float* loss_out3, float* d_actions, float* d_stop, void* stream);
 int rvb_fused_adam(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
-                   const int64_t* numel, const int64_t* chunk_start, int n_tensors, int64_t total_chunks, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int decoupled, float step_size, float bias_correction2_sqrt,
+                   const int64_t* numel, const int64_t* chunk_start, int n_tensors, int64_t total_chunks, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int decoupled, double step_size, double bias_correction2_sqrt,
                    void* stream);
 int rvb_adam_chunk_elems(void);
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librobovln_b200.so")
@@ -64,10 +64,11 @@ SYMBOLS = {
     "rvb_bert_attention_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_vla_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "rvb_vla_block": (c_int, [c_void_p] * 12 + [c_float, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "rvb_vla_block_variant": (c_int, [c_int]),
     "rvb_hi_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rvb_lo_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "rvb_fused_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_float,
-                               c_float, c_float, c_int, c_float, c_float, c_void_p]),
+    "rvb_fused_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_double, c_double, c_double,
+                               c_double, c_double, c_int, c_double, c_double, c_void_p]),
     "rvb_adam_chunk_elems": (c_int, []),
     "rvb_lstm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                          c_void_p]),

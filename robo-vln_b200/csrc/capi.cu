@@ -363,6 +363,13 @@ int rvb_vla_block(const void* q0_h16, const void* kvx_h16, const void* wo_h16, c
   });
 }
 
+int rvb_vla_block_variant(int variant) {
+  return guarded([&] {
+    RVB_CHECK(variant >= 0 && variant <= 2, "rvb_vla_block_variant: 0 = default, 1 = single-CTA tiles, 2 = CTA pair");
+    g_vla_variant = variant;
+  });
+}
+
 int rvb_hi_loss(const float* logits, const float* oracle_f32, const int64_t* oracle_i64, int T, int C, float* loss_out2,
                 float* dlogits, void* stream) {
   return guarded([&] { hi_loss(logits, oracle_f32, oracle_i64, T, C, loss_out2, dlogits, S(stream)); });
@@ -374,8 +381,8 @@ int rvb_lo_loss(const float* actions, const float* corrected, const float* stop_
 }
 
 int rvb_fused_adam(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
-                   const int64_t* numel, const int64_t* chunk_start, int n_tensors, int64_t total_chunks, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int decoupled, float step_size, float bias_correction2_sqrt,
+                   const int64_t* numel, const int64_t* chunk_start, int n_tensors, int64_t total_chunks, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int decoupled, double step_size, double bias_correction2_sqrt,
                    void* stream) {
   return guarded([&] {
     fused_adam(reinterpret_cast<float* const*>(params), reinterpret_cast<const float* const*>(grads),

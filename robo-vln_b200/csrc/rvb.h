@@ -267,6 +267,7 @@ struct VlaBlockPlan {
 };
 void vla_block_make_plan(const VlaBlock& d, VlaBlockPlan* plan);
 void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s);
+extern int g_vla_variant;   // 0: ROBOVLN_VLA_PAIR (default pair); 1: one CTA per (env, modality) tile; 2: CTA pair per environment
 // attention_tc.cu -- tcgen05 / TMEM / TMA self-attention for L <= 128 (ROBOVLN_ATTN=tc selects it in the engine)
 bool use_tc_attention();
 void bert_self_attention_tc(const h16* qkv, h16* ctx, int R, int L, int heads, cudaStream_t s);
@@ -288,8 +289,8 @@ void hi_loss(const float* logits, const float* oracle_f, const int64_t* oracle_i
 void lo_loss(const float* actions, const float* corrected, const float* stop, const float* oracle_stop, int T, int A, float* loss_out,
              float* d_actions, float* d_stop, cudaStream_t s);
 void fused_adam(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                const long long* numel, const long long* chunk_start, int n_tensors, long long total_chunks, float lr, float b1,
-                float b2, float eps, float wd, int decoupled, float step_size, float bc2_sqrt, cudaStream_t s);
+                const long long* numel, const long long* chunk_start, int n_tensors, long long total_chunks, double lr, double b1,
+                double b2, double eps, double wd, int decoupled, double step_size, double bc2_sqrt, cudaStream_t s);
 int adam_chunk_elems();
 
 // lstm.cu

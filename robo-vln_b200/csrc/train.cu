@@ -125,8 +125,8 @@ constexpr int ADAM_CHUNK = 4096;   // elements per CTA
 // torch/optim/adam.py _single_tensor_adam (amsgrad = False, maximize = False), fp32:
 //   decoupled (AdamW): p *= 1 - lr*wd      else (Adam): g += wd * p
 //   m = lerp(m, g, 1 - b1);  v = v*b2 + (1 - b2) g*g;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
-__global__ void __launch_bounds__(256) fused_adam_kernel(AdamList L, int n_tensors, float lr, float b1, float b2, float eps, float wd,
-                                                         int decoupled, float step_size, float bc2_sqrt) {
+__global__ void __launch_bounds__(256) fused_adam_kernel(AdamList L, int n_tensors, float decay_mul, float omb1, float b2, float omb2,
+                                                         float eps, float wd, int decoupled, float step_size, float bc2_sqrt) {
   // binary search: tensor whose chunk range holds blockIdx.x
   int lo = 0, hi = n_tensors;
   while (hi - lo > 1) {
@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(256) fused_adam_kernel(AdamList L, int n_tenso
   float* __restrict__ v = L.exp_avg_sq[t];
   for (long long i = base + threadIdx.x; i < std::min<long long>(base + ADAM_CHUNK, n); i += blockDim.x) {
     float pi = p[i], gi = g[i];
-    if (decoupled) pi *= 1.0f - lr * wd;
+    if (decoupled) pi *= decay_mul;
     else if (wd != 0.0f) gi = fmaf(wd, pi, gi);
-    const float mi = m[i] + (1.0f - b1) * (gi - m[i]);
-    const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;
+    const float mi = m[i] + omb1 * (gi - m[i]);
+    const float vi = v[i] * b2 + omb2 * (gi * gi);
     m[i] = mi;
     v[i] = vi;
     p[i] = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
@@ -169,12 +169,14 @@ void lo_loss(const float* actions, const float* corrected, const float* stop, co
 }
 
 void fused_adam(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                const long long* numel, const long long* chunk_start, int n_tensors, long long total_chunks, float lr, float b1,
-                float b2, float eps, float wd, int decoupled, float step_size, float bc2_sqrt, cudaStream_t s) {
+                const long long* numel, const long long* chunk_start, int n_tensors, long long total_chunks, double lr, double b1,
+                double b2, double eps, double wd, int decoupled, double step_size, double bc2_sqrt, cudaStream_t s) {
   RVB_CHECK(n_tensors >= 1 && total_chunks >= 1 && total_chunks < (1ll << 31), "fused_adam: bad arguments");
   AdamList L{params, grads, exp_avg, exp_avg_sq, numel, chunk_start};
-  launch_k(fused_adam_kernel, dim3(static_cast<unsigned>(total_chunks)), dim3(256), 0, s, L, n_tensors, lr, b1, b2, eps, wd, decoupled,
-           step_size, bc2_sqrt);
+  // scalar constants are formed in double precision and rounded once, exactly as torch passes Python floats to its kernels
+  launch_k(fused_adam_kernel, dim3(static_cast<unsigned>(total_chunks)), dim3(256), 0, s, L, n_tensors, static_cast<float>(1.0 - lr * wd),
+           static_cast<float>(1.0 - b1), static_cast<float>(b2), static_cast<float>(1.0 - b2), static_cast<float>(eps),
+           static_cast<float>(wd), decoupled, static_cast<float>(step_size), static_cast<float>(bc2_sqrt));
   RVB_CUDA(cudaGetLastError());
 }
 

@@ -552,6 +552,372 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
   }
 }
 
+
+// =====================================================================================================================
+// CTA-pair form (cta_group::2): the two modalities of ONE environment share a 2-CTA cluster (rank 0 = RGB tile,
+// rank 1 = depth tile).  Every weight GEMM is one M=256 UMMA across the pair -- each CTA stages its own 128 query rows
+// (A) and HALF of every weight block (B) -- which halves, per SM, both the L2->SM weight traffic and the shared-memory
+// bandwidth the MMA needs (the 1-CTA form above is bound by exactly that: 32 KB of operand reads + 16 KB of TMA writes
+// per 256 tensor-pipe cycles), and lets the FFN run with 256-wide hidden chunks (N = 256 MMAs).
+//   S  : [Q0; Q0] . [K'_rgb ; K'_depth]^T   M=256 N=128: each CTA stages ITS OWN K' as its half of B and reads back ITS
+//        64 columns of the result (the other 64 are the queries against the other modality's keys: ignored)
+//   O_h: P . [V_rgb,h | V_depth,h]          M=256 N=128 K=16, same trick with the MN-major V tiles
+//   fc_o, fc1 (4 chunks of 256), fc2        M=256 N=256, B half = weight rows [rank*128, +128) of the block
+// The leader (rank 0) issues every MMA; completion is broadcast to both CTAs (tcgen05.commit multicast); the epilogue
+// warps of both CTAs report to the leader's barriers through the cluster shared-memory window.
+// =====================================================================================================================
+RVB_DEVICE void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t mbar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+constexpr int VP_NS = 5;
+
+__global__ void __launch_bounds__(VB_THREADS, 1)
+vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmKp,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmWo,
+                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const VlaBlockParams p) {
+  extern __shared__ uint8_t vb_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vb_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bufA = smem + VB_OFF_A;
+  uint8_t* bufB = smem + VB_OFF_B;
+  uint8_t* sP = smem + VB_OFF_P;
+  uint8_t* sV = smem + VB_OFF_V;
+  uint8_t* ring = smem + VB_OFF_RING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + VB_OFF_MISC);
+  uint64_t* full_bar = bars;                 // [VP_NS]  leader only: bytes of both CTAs' halves
+  uint64_t* empty_bar = bars + VP_NS;        // [VP_NS]  both CTAs (multicast commit)
+  uint64_t* in_bar = bars + 2 * VP_NS;       // local: Q0 + V landed
+  uint64_t* in_both = in_bar + 1;            // leader: both CTAs' inputs landed (2 arrivals)
+  uint64_t* s_done = in_bar + 2;             // multicast commits ...
+  uint64_t* o_done = in_bar + 3;
+  uint64_t* fco_done = in_bar + 4;
+  uint64_t* y_done = in_bar + 5;
+  uint64_t* hfull = in_bar + 6;
+  uint64_t* sempty = in_bar + 7;
+  uint64_t* p_ready = in_bar + 8;            // leader: arrivals of all 16 epilogue warps of the pair ...
+  uint64_t* ctx_ready = in_bar + 9;
+  uint64_t* x_ready = in_bar + 10;
+  uint64_t* hempty = in_bar + 11;
+  uint64_t* sfull = in_bar + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 13);
+  float* s_c = reinterpret_cast<float*>(smem + VB_OFF_MISC + 256);
+  float2* s_ln = reinterpret_cast<float2*>(smem + VB_OFF_MISC + 512);
+  float* s_par = reinterpret_cast<float*>(smem + VB_OFF_PAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();               // 0 = RGB tile (leader), 1 = depth tile
+  const int env = static_cast<int>(blockIdx.x >> 1), mod = static_cast<int>(rank);
+  const int cell_row0 = (mod * p.B + env) * 16;
+  const int q_row0 = p.q_shared ? 0 : env * p.L;
+  auto leader_addr = [](uint64_t* bar) { return mapa_u32(smem_u32(bar), 0); };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmKp); tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    for (int i = 0; i < VP_NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(in_bar, 1); mbar_init(in_both, 2);
+    mbar_init(s_done, 1); mbar_init(o_done, 1); mbar_init(fco_done, 1); mbar_init(y_done, 1); mbar_init(hfull, 1); mbar_init(sempty, 1);
+    mbar_init(p_ready, 2 * VB_EPI_WARPS); mbar_init(ctx_ready, 2 * VB_EPI_WARPS); mbar_init(x_ready, 2 * VB_EPI_WARPS);
+    mbar_init(hempty, 2 * VB_EPI_WARPS); mbar_init(sfull, 2 * VB_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers exist before any remote arrive / multicast commit / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  RVB_PDL_PROLOGUE();
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ===============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(in_bar, 4 * VB_SUB + 4 * 2048);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(bufA + kb * VB_SUB, &tmQ0, in_bar, kb * 64, q_row0);
+      for (int h = 0; h < 4; ++h) tma_load_2d(sV + h * 2048, &tmV, in_bar, 1032 + h * 64, cell_row0);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto next = [&]() { if (++slot == VP_NS) { slot = 0; phase ^= 1; } };
+      // every unit: wait until the pair's MMAs have retired the slot, then stage THIS CTA's half; the bytes of both
+      // halves are credited to the leader's full barrier, which the leader arms
+      auto begin_unit = [&](uint32_t bytes_per_cta) -> uint32_t {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[slot], 2 * bytes_per_cta);
+        return leader_addr(&full_bar[slot]);
+      };
+      for (int kb = 0; kb < 4; ++kb) {                      // S: this tile's K' block [64 (key, head) x 64 k]
+        const uint32_t fb = begin_unit(8192);
+        tma_load_3d_2sm(ring + slot * VB_SLOT, &tmKp, fb, kb * 64, 0, cell_row0);
+        next();
+      }
+      for (int kb = 0; kb < 4; ++kb) {                      // fc_o: Wo rows [rank*128, +128), k block kb
+        const uint32_t fb = begin_unit(VB_SLOT);
+        tma_load_2d_2sm(ring + slot * VB_SLOT, &tmWo, fb, kb * 64, static_cast<int>(rank) * 128);
+        next();
+      }
+      for (int step = 0; step < 8; ++step) {                // FFN in MMA issue order: fc1(0), {fc1(c+1), fc2(c)}, fc2(3)
+        const int is_fc2 = (step == 7) ? 1 : (step == 0 ? 0 : ((step & 1) ? 0 : 1));
+        const int c = (step == 0) ? 0 : (step == 7 ? 3 : ((step & 1) ? (step + 1) >> 1 : (step >> 1) - 1));
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t fb = begin_unit(VB_SLOT);
+          if (!is_fc2) tma_load_2d_2sm(ring + slot * VB_SLOT, &tmW1, fb, kb * 64, c * 256 + static_cast<int>(rank) * 128);
+          else tma_load_2d_2sm(ring + slot * VB_SLOT, &tmW2, fb, c * 256 + kb * 64, static_cast<int>(rank) * 128);
+          next();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader) ===============================
+    if (lane == 0) {
+      mbar_wait(in_bar, 0);                                  // this CTA's Q0 / V have landed
+      mbar_arrive_cluster(leader_addr(in_both));
+      if (rank == 0) {
+        int slot = 0;
+        uint32_t phase = 0;
+        auto next = [&]() { if (++slot == VP_NS) { slot = 0; phase ^= 1; } };
+        auto unit = [&](const uint8_t* a_sub, uint32_t d_col, uint32_t idesc, bool first) {
+          mbar_wait(&full_bar[slot], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(a_sub));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + slot * VB_SLOT));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16kind_2sm(tmem_base + d_col, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                             static_cast<uint32_t>(!(first && k == 0)));
+          umma_commit_2sm(&empty_bar[slot]);
+          next();
+        };
+        constexpr uint32_t idesc_s = umma_idesc_h16(256, 128);
+        constexpr uint32_t idesc_w = umma_idesc_h16(256, 256);
+        VB_STAMP(0);
+        mbar_wait(in_both, 0);
+        tc_fence_after();
+        VB_STAMP(1);
+        for (int kb = 0; kb < 4; ++kb) unit(bufA + kb * VB_SUB, 0, idesc_s, kb == 0);          // S -> columns [0, 128)
+        umma_commit_2sm(s_done);
+        VB_STAMP(2);
+        mbar_wait(p_ready, 0);
+        tc_fence_after();
+        VB_STAMP(3);
+        {
+          constexpr uint32_t idesc_mn = umma_idesc_h16(256, 128) | (1u << 16);
+          const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
+          for (int h = 0; h < 4; ++h)                                                            // O_h -> columns [h*128, +128)
+            umma_f16kind_2sm(tmem_base + h * 128, pdesc + static_cast<uint64_t>(h * 2), umma_desc_sw128(smem_u32(sV + h * 2048)),
+                             idesc_mn, 0u);
+          umma_commit_2sm(o_done);
+        }
+        mbar_wait(ctx_ready, 0);
+        tc_fence_after();
+        VB_STAMP(4);
+        for (int kb = 0; kb < 4; ++kb) unit(bufB + kb * VB_SUB, TM_H, idesc_w, kb == 0);        // fc_o -> columns [256, 512)
+        umma_commit_2sm(fco_done);
+        VB_STAMP(5);
+        mbar_wait(x_ready, 0);
+        tc_fence_after();
+        VB_STAMP(6);
+        for (int step = 0; step < 8; ++step) {
+          VB_STAMP(8 + step);
+          const int is_fc2 = (step == 7) ? 1 : (step == 0 ? 0 : ((step & 1) ? 0 : 1));
+          const int c = (step == 0) ? 0 : (step == 7 ? 3 : ((step & 1) ? (step + 1) >> 1 : (step >> 1) - 1));
+          if (!is_fc2) {
+            if (c >= 1) {      // both CTAs' epilogues have drained the (single) fc1 accumulator of chunk c - 1
+              mbar_wait(hempty, static_cast<uint32_t>((c - 1) & 1));
+              tc_fence_after();
+            }
+            for (int kb = 0; kb < 4; ++kb) unit(bufB + kb * VB_SUB, TM_H, idesc_w, kb == 0);
+            umma_commit_2sm(hfull);
+          } else {
+            mbar_wait(sfull, static_cast<uint32_t>(c & 1));
+            tc_fence_after();
+            for (int kb = 0; kb < 4; ++kb) unit(bufA + kb * VB_SUB, TM_Y, idesc_w, c == 0 && kb == 0);
+            umma_commit_2sm(sempty);
+          }
+        }
+        umma_commit_2sm(y_done);
+        VB_STAMP(7);
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..9 of both CTAs) ===============================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int sw = row & 7;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int et = threadIdx.x - 64;
+    const uint32_t l_p_ready = leader_addr(p_ready), l_ctx_ready = leader_addr(ctx_ready), l_x_ready = leader_addr(x_ready),
+                   l_hempty = leader_addr(hempty), l_sfull = leader_addr(sfull);
+    if (et < 64) s_c[et] = from_h16(p.kvx[static_cast<long long>(cell_row0 + (et >> 2)) * p.kvx_pitch + 1024 + (et & 3)]);
+    {
+      const float* srcs[6] = {p.bo, p.ln1g, p.ln1b, p.b2, p.ln2g, p.ln2b};
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s_par[i * 256 + et] = __ldg(srcs[i] + et);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_par[6 * 256 + i * 256 + et] = __ldg(p.b1 + i * 256 + et);
+    }
+    named_bar(5, VB_EPI_WARPS * 32);
+
+    // ---- softmax: this tile's scores are columns [rank*64, +64) of S (column = key*4 + head within the tile)
+    float inv_sum[2];
+    {
+      if (et == 0) VB_STAMP(32);
+      mbar_wait(s_done, 0);
+      tc_fence_after();
+      if (et == 0) VB_STAMP(33);
+      float s[64];
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(trow + rank * 64, v0);
+        tmem_ld_32x32(trow + rank * 64 + 32, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s[j] = __uint_as_float(v0[j]); s[32 + j] = __uint_as_float(v1[j]); }
+      }
+      const float scale = 0.125f * 1.4426950408889634f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = 2 * half + hh;
+        float x[16];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          x[k] = (half == 0 ? s[k * 4 + hh] : s[k * 4 + 2 + hh]) + s_c[k * 4 + h];
+          mx = fmaxf(mx, x[k]);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          x[k] = exp2f((x[k] - mx) * scale);
+          sum += x[k];
+        }
+        inv_sum[hh] = 1.0f / sum;
+        *reinterpret_cast<uint4*>(sP + row * 128 + (((2 * h) ^ sw) << 4)) = pack_chunk(&x[0]);
+        *reinterpret_cast<uint4*>(sP + row * 128 + (((2 * h + 1) ^ sw) << 4)) = pack_chunk(&x[8]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_p_ready);
+    }
+
+    // ---- ctx = O / rowsum: head h of this tile = TMEM columns [h*128 + rank*64, +64)
+    {
+      if (et == 0) VB_STAMP(34);
+      mbar_wait(o_done, 0);
+      tc_fence_after();
+      if (et == 0) VB_STAMP(35);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = 2 * half + hh;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(trow + h * 128 + rank * 64, v0);
+        tmem_ld_32x32(trow + h * 128 + rank * 64 + 32, v1);
+        tmem_ld_wait();
+        uint8_t* dst = bufB + h * VB_SUB + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float g[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(j < 4 ? v0[j * 8 + e] : v1[(j - 4) * 8 + e]) * inv_sum[hh];
+          *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = pack_chunk(g);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_ctx_ready);
+    }
+
+    // ---- X = LN1(Q0 + A + bo)
+    {
+      if (et == 0) VB_STAMP(36);
+      mbar_wait(in_bar, 0);
+      mbar_wait(fco_done, 0);
+      tc_fence_after();
+      if (et == 0) VB_STAMP(37);
+      const int n0 = half * 128;
+      ln_epilogue(trow + TM_H + n0, bufA + 2 * half * VB_SUB, bufB + 2 * half * VB_SUB, s_par + n0, s_par + 256 + n0,
+                  s_par + 512 + n0, s_ln, half, row, quad, p.eps, [](int, const uint4&) {});
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_x_ready);
+    }
+
+    // ---- H_c = relu(fc1 chunk + b1), 4 chunks of 256 hidden units; this thread owns 128 of them = sub-tiles 2*half, 2*half+1
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      if (et == 0) VB_STAMP(40 + 2 * c);
+      mbar_wait(hfull, static_cast<uint32_t>(c & 1));
+      tc_fence_after();
+      if (et == 0) VB_STAMP(41 + 2 * c);
+      float f[128];
+      tmem_ld_128(trow + TM_H + half * 128, f);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_hempty);          // drained: fc1(c + 1) may overwrite the accumulator
+      if (c >= 1) mbar_wait(sempty, static_cast<uint32_t>((c - 1) & 1));   // fc2(c - 1) has read the H buffer
+      const float* bias = s_par + 6 * 256 + c * 256 + half * 128;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + j * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + j * 8 + 4);
+        float g[8];
+        g[0] = fmaxf(f[j * 8] + b0.x, 0.0f); g[1] = fmaxf(f[j * 8 + 1] + b0.y, 0.0f);
+        g[2] = fmaxf(f[j * 8 + 2] + b0.z, 0.0f); g[3] = fmaxf(f[j * 8 + 3] + b0.w, 0.0f);
+        g[4] = fmaxf(f[j * 8 + 4] + b1.x, 0.0f); g[5] = fmaxf(f[j * 8 + 5] + b1.y, 0.0f);
+        g[6] = fmaxf(f[j * 8 + 6] + b1.z, 0.0f); g[7] = fmaxf(f[j * 8 + 7] + b1.w, 0.0f);
+        *reinterpret_cast<uint4*>(bufA + (2 * half + (j >> 3)) * VB_SUB + row * 128 + (((j & 7) ^ sw) << 4)) = pack_chunk(g);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_sfull);
+    }
+
+    // ---- Y = LN2(X + Y + b2) in place of X, then the token mean
+    {
+      if (et == 0) VB_STAMP(38);
+      mbar_wait(y_done, 0);
+      tc_fence_after();
+      if (et == 0) VB_STAMP(39);
+      const int n0 = half * 128;
+      h16* ytok = (p.y_tokens != nullptr && row < p.L) ? p.y_tokens + ((static_cast<long long>(mod) * p.B + env) * p.L + row) * 256 + n0 : nullptr;
+      ln_epilogue(trow + TM_Y + n0, bufB + 2 * half * VB_SUB, bufB + 2 * half * VB_SUB, s_par + 768 + n0, s_par + 1024 + n0,
+                  s_par + 1280 + n0, s_ln, half, row, quad, p.eps, [ytok](int col, const uint4& yq) {
+                    if (ytok != nullptr) *reinterpret_cast<uint4*>(ytok + col) = yq;
+                  });
+      named_bar(5, VB_EPI_WARPS * 32);
+      const uint8_t* colp = bufB + (et >> 6) * VB_SUB + (et & 7) * 2;
+      const int chunk = (et & 63) >> 3;
+      float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      int r = 0;
+      for (; r + 8 <= p.L; r += 8) {
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = from_h16(*reinterpret_cast<const h16*>(colp + (r + k) * 128 + ((chunk ^ k) << 4)));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc4[k & 3] += x[k];
+      }
+      for (; r < p.L; ++r) acc4[r & 3] += from_h16(*reinterpret_cast<const h16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
+      const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+      p.out[static_cast<long long>(env) * p.out_pitch + mod * 256 + et] = to_h16(acc / static_cast<float>(p.L));
+      if (et == 0) VB_STAMP(56);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer may still be reading this CTA's half of a weight block / using its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 void vla_block_make_plan(const VlaBlock& d, VlaBlockPlan* plan) {
@@ -576,11 +942,27 @@ void vla_block_make_plan(const VlaBlock& d, VlaBlockPlan* plan) {
   plan->valid = true;
 }
 
+// 0: environment default (ROBOVLN_VLA_PAIR, default 1 = CTA-pair kernel); 1: one CTA per tile; 2: CTA pair per environment
+int g_vla_variant = 0;
+
+static bool use_pair_kernel() {
+  if (g_vla_variant != 0) return g_vla_variant == 2;
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ROBOVLN_VLA_PAIR");
+    v = (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s) {
   RVB_CHECK(plan.valid, "vla_block: plan not built");
-  static PerDeviceOnce attr_once;
-  if (attr_once.first())
-    RVB_CUDA(cudaFuncSetAttribute(vla_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM));
+  const bool pair = use_pair_kernel();
+  static PerDeviceOnce attr_once[2];
+  if (attr_once[pair ? 1 : 0].first()) {
+    if (pair) RVB_CUDA(cudaFuncSetAttribute(vla_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM));
+    else RVB_CUDA(cudaFuncSetAttribute(vla_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VB_SMEM));
+  }
   const VlaBlock& d = plan.d;
   VlaBlockParams p;
   std::memset(&p, 0, sizeof(p));
@@ -589,7 +971,7 @@ void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s) {
   p.bo = d.bo; p.b1 = d.b1; p.b2 = d.b2; p.ln1g = d.ln1g; p.ln1b = d.ln1b; p.ln2g = d.ln2g; p.ln2b = d.ln2b;
   p.eps = d.eps; p.out = d.out; p.out_pitch = d.out_pitch; p.y_tokens = d.y_tokens;
   static const char* renv = std::getenv("ROBOVLN_VLA_ROTATE");
-  p.rotate = (renv != nullptr && std::strcmp(renv, "0") == 0) ? 0 : 1;
+  p.rotate = (renv != nullptr && std::strcmp(renv, "1") == 0) ? 1 : 0;   // measured: no effect on B200 (the L2 serves same-line readers fine)
   // ROBOVLN_VLA_TIMES=<file>: per-CTA phase time stamps (SM clocks) of every launch are written to <file> (diagnostics;
   // synchronises the stream)
   static const char* tenv = std::getenv("ROBOVLN_VLA_TIMES");
@@ -600,8 +982,37 @@ void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s) {
     RVB_CUDA(cudaMemsetAsync(tbuf, 0, tbytes, s));
   }
   p.times = tbuf;
-  launch_k(vla_block_kernel, dim3(d.B, 2), dim3(VB_THREADS), VB_SMEM, s, plan.tmQ0, plan.tmKp, plan.tmV, plan.tmWo, plan.tmW1,
-           plan.tmW2, p);
+  if (pair) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * d.B, 1, 1);
+    cfg.blockDim = dim3(VB_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = VB_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[3];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (g_launch_prio != 0) {
+      attr[na].id = cudaLaunchAttributePriority;
+      attr[na].val.priority = g_launch_prio;
+      ++na;
+    }
+    if (use_pdl()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    RVB_CUDA(cudaLaunchKernelEx(&cfg, vla_pair_kernel, plan.tmQ0, plan.tmKp, plan.tmV, plan.tmWo, plan.tmW1, plan.tmW2, p));
+  } else {
+    launch_k(vla_block_kernel, dim3(d.B, 2), dim3(VB_THREADS), VB_SMEM, s, plan.tmQ0, plan.tmKp, plan.tmV, plan.tmWo, plan.tmW1,
+             plan.tmW2, p);
+  }
   RVB_CUDA(cudaGetLastError());
   if (tbuf != nullptr) {
     std::vector<long long> host(static_cast<size_t>(d.B) * 2 * 64);
@@ -610,7 +1021,7 @@ void vla_block_launch(const VlaBlockPlan& plan, cudaStream_t s) {
     RVB_CUDA(cudaFree(tbuf));
     FILE* f = std::fopen(tenv, "a");
     if (f != nullptr) {
-      std::fprintf(f, "# launch B=%d L=%d\n", d.B, d.L);
+      std::fprintf(f, "# launch B=%d L=%d pair=%d\n", d.B, d.L, pair ? 1 : 0);
       for (int c = 0; c < d.B * 2; ++c) {
         std::fprintf(f, "%d", c);
         for (int i = 0; i < 64; ++i) std::fprintf(f, ",%lld", host[static_cast<size_t>(c) * 64 + i]);

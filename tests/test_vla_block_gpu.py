@@ -55,10 +55,13 @@ def _reference(q0, vis, w, B, L, shared):
     return tok, torch.cat([tok[0].mean(1), tok[1].mean(1)], 1)
 
 
+@pytest.mark.parametrize("variant", [2, 1], ids=["pair", "single"])
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 @pytest.mark.parametrize("B,L,shared", [(1, 80, False), (3, 20, False), (5, 128, False), (7, 33, True), (64, 80, False), (160, 80, True)])
-def test_vla_block_kernel(B, L, shared, dtype):
+def test_vla_block_kernel(B, L, shared, dtype, variant):
     from tests.gpu_util import H16, P, check, lib, stream
+
+    check(lib(dtype).rvb_vla_block_variant(variant), "rvb_vla_block_variant", dtype)
 
     dev = "cuda"
     h = H16[dtype]
@@ -95,3 +98,4 @@ def test_vla_block_kernel(B, L, shared, dtype):
     # production launch (no token dump): the pooled output is bit-identical, run to run and with / without the dump
     assert torch.equal(run(None), pooled)
     assert torch.equal(run(None), pooled)
+    check(lib(dtype).rvb_vla_block_variant(0), "rvb_vla_block_variant", dtype)
