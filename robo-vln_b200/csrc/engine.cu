@@ -1263,17 +1263,31 @@ void Engine::run_cross_modal(const void* bert, const void* rgb_sp, const void* d
         gv.out = reinterpret_cast<h16*>(gv.out) + mod * MH * 256;
         hit->visfc[mod].reset(new GemmTcPlan());
         gemm_tc_make_plan(gv, hit->visfc[mod].get(), 0);
+        ConvGemm gk = cm_.kvx->desc;            // this modality's half of the K' | c | V projection
+        gk.in = reinterpret_cast<const h16*>(gv.out);
+        gk.W = static_cast<int>(MH);
+        gk.out = reinterpret_cast<h16*>(gk.out) + mod * MH * 1288;
+        hit->kvx[mod].reset(new GemmTcPlan());
+        gemm_tc_make_plan(gk, hit->kvx[mod].get(), 0);
       }
     }
+    // query side on the caller's stream; each modality's key/value side (vis_fc + LayerNorm, then K' | c | V) on its own
+    // engine stream; joined before the block kernel
+    RVB_CUDA(cudaEventRecord(events_[0], s));
+    for (int mod = 0; mod < 2; ++mod) {
+      RVB_CUDA(cudaStreamWaitEvent(side_[mod], events_[0], 0));
+      gemm_tc_launch(*hit->visfc[mod], side_[mod]);
+      gemm_tc_launch(*hit->kvx[mod], side_[mod]);
+      RVB_CUDA(cudaEventRecord(events_[1 + mod], side_[mod]));
+    }
     gemm_tc_launch(*hit->insfc, s);
-    gemm_tc_launch(*hit->visfc[0], s);
-    gemm_tc_launch(*hit->visfc[1], s);
-    gemm_tc_launch(*cm_.kvx, s);
+    RVB_CUDA(cudaStreamWaitEvent(s, events_[1], 0));
+    RVB_CUDA(cudaStreamWaitEvent(s, events_[2], 0));
     VlaBlockPlan vp = *cm_.vla;
     vp.d.out = reinterpret_cast<h16*>(pooled);
     vp.d.out_pitch = 512;
     vla_block_launch(vp, s);
-    launches_ = 5;
+    launches_ = 6;
     (void)R; (void)L;
     return;
   }

@@ -141,7 +141,7 @@ class Engine {
     VlaBlockPlan* vla = nullptr;
     struct Entry {
       const void* key[3];
-      std::unique_ptr<GemmTcPlan> insfc, visfc[2];
+      std::unique_ptr<GemmTcPlan> insfc, visfc[2], kvx[2];
     };
     std::vector<Entry> cache;
   } cm_;

@@ -136,10 +136,14 @@ RVB_DEVICE void ln_epilogue(uint32_t tcol, const uint8_t* res0, uint8_t* dst0, c
                             const float* beta, float2* xchg, int half, int row, int quad, float eps, OnChunk&& on_chunk) {
   const int sw = row & 7;
   float s = 0.0f, q = 0.0f;
+  // TMEM loads are double-buffered in registers: chunk ch + 1 is in flight while chunk ch is being processed
+  // (tcgen05.wait::ld has no per-load granularity, so the wait for ch + 1 sits after the arithmetic of ch)
+  uint32_t u[2][32];
+  tmem_ld_32x32(tcol, u[0]);
+  tmem_ld_wait();
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
-    uint32_t u[32];
-    tmem_ld_32x32(tcol + ch * 32, u);
+    if (ch < 3) tmem_ld_32x32(tcol + (ch + 1) * 32, u[(ch + 1) & 1]);
     uint4 r[4];
     float4 bb[8];
 #pragma unroll
@@ -147,22 +151,23 @@ RVB_DEVICE void ln_epilogue(uint32_t tcol, const uint8_t* res0, uint8_t* dst0, c
       r[j] = *reinterpret_cast<const uint4*>(res0 + (ch >> 1) * VB_SUB + row * 128 + ((((ch & 1) * 4 + j) ^ sw) << 4));
 #pragma unroll
     for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(bias + ch * 32 + j * 4);
-    tmem_ld_wait();
     float f[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      f[4 * j] = __uint_as_float(u[4 * j]) + bb[j].x; f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) + bb[j].y;
-      f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) + bb[j].z; f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) + bb[j].w;
+      f[4 * j] = __uint_as_float(u[ch & 1][4 * j]) + bb[j].x; f[4 * j + 1] = __uint_as_float(u[ch & 1][4 * j + 1]) + bb[j].y;
+      f[4 * j + 2] = __uint_as_float(u[ch & 1][4 * j + 2]) + bb[j].z; f[4 * j + 3] = __uint_as_float(u[ch & 1][4 * j + 3]) + bb[j].w;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) add_chunk(&f[8 * j], r[j]);
+    uint32_t w[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       s += f[j];
       q = fmaf(f[j], f[j], q);
-      u[j] = __float_as_uint(f[j]);
+      w[j] = __float_as_uint(f[j]);
     }
-    tmem_st_32x32(tcol + ch * 32, u);
+    tmem_st_32x32(tcol + ch * 32, w);
+    if (ch < 3) tmem_ld_wait();
   }
   tmem_st_wait();
   xchg[half * 128 + row] = make_float2(s, q);
@@ -173,32 +178,34 @@ RVB_DEVICE void ln_epilogue(uint32_t tcol, const uint8_t* res0, uint8_t* dst0, c
   const float var = fmaxf((p0.y + p1.y) * (1.0f / 256.0f) - mean * mean, 0.0f);
   const float a = rsqrtf(var + eps);
   const float b = -mean * a;
+  tmem_ld_32x32(tcol, u[0]);
+  tmem_ld_wait();
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
-    uint32_t u[32];
-    tmem_ld_32x32(tcol + ch * 32, u);
+    if (ch < 3) tmem_ld_32x32(tcol + (ch + 1) * 32, u[(ch + 1) & 1]);
     float4 gg[8], ee[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       gg[j] = *reinterpret_cast<const float4*>(gamma + ch * 32 + j * 4);
       ee[j] = *reinterpret_cast<const float4*>(beta + ch * 32 + j * 4);
     }
-    tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      const uint32_t* uc = &u[ch & 1][8 * j];
       float g[8];
-      g[0] = fmaf(fmaf(__uint_as_float(u[8 * j]), a, b), gg[2 * j].x, ee[2 * j].x);
-      g[1] = fmaf(fmaf(__uint_as_float(u[8 * j + 1]), a, b), gg[2 * j].y, ee[2 * j].y);
-      g[2] = fmaf(fmaf(__uint_as_float(u[8 * j + 2]), a, b), gg[2 * j].z, ee[2 * j].z);
-      g[3] = fmaf(fmaf(__uint_as_float(u[8 * j + 3]), a, b), gg[2 * j].w, ee[2 * j].w);
-      g[4] = fmaf(fmaf(__uint_as_float(u[8 * j + 4]), a, b), gg[2 * j + 1].x, ee[2 * j + 1].x);
-      g[5] = fmaf(fmaf(__uint_as_float(u[8 * j + 5]), a, b), gg[2 * j + 1].y, ee[2 * j + 1].y);
-      g[6] = fmaf(fmaf(__uint_as_float(u[8 * j + 6]), a, b), gg[2 * j + 1].z, ee[2 * j + 1].z);
-      g[7] = fmaf(fmaf(__uint_as_float(u[8 * j + 7]), a, b), gg[2 * j + 1].w, ee[2 * j + 1].w);
+      g[0] = fmaf(fmaf(__uint_as_float(uc[0]), a, b), gg[2 * j].x, ee[2 * j].x);
+      g[1] = fmaf(fmaf(__uint_as_float(uc[1]), a, b), gg[2 * j].y, ee[2 * j].y);
+      g[2] = fmaf(fmaf(__uint_as_float(uc[2]), a, b), gg[2 * j].z, ee[2 * j].z);
+      g[3] = fmaf(fmaf(__uint_as_float(uc[3]), a, b), gg[2 * j].w, ee[2 * j].w);
+      g[4] = fmaf(fmaf(__uint_as_float(uc[4]), a, b), gg[2 * j + 1].x, ee[2 * j + 1].x);
+      g[5] = fmaf(fmaf(__uint_as_float(uc[5]), a, b), gg[2 * j + 1].y, ee[2 * j + 1].y);
+      g[6] = fmaf(fmaf(__uint_as_float(uc[6]), a, b), gg[2 * j + 1].z, ee[2 * j + 1].z);
+      g[7] = fmaf(fmaf(__uint_as_float(uc[7]), a, b), gg[2 * j + 1].w, ee[2 * j + 1].w);
       const uint4 yq = pack_chunk(g);
       *reinterpret_cast<uint4*>(dst0 + (ch >> 1) * VB_SUB + row * 128 + ((((ch & 1) * 4 + j) ^ sw) << 4)) = yq;
       on_chunk(ch * 32 + j * 8, yq);
     }
+    if (ch < 3) tmem_ld_wait();
   }
 }
 
@@ -890,7 +897,9 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
                   s_par + 1280 + n0, s_ln, half, row, quad, p.eps, [ytok](int col, const uint4& yq) {
                     if (ytok != nullptr) *reinterpret_cast<uint4*>(ytok + col) = yq;
                   });
+      if (et == 0) VB_STAMP(57);
       named_bar(5, VB_EPI_WARPS * 32);
+      if (et == 0) VB_STAMP(58);
       const uint8_t* colp = bufB + (et >> 6) * VB_SUB + (et & 7) * 2;
       const int chunk = (et & 63) >> 3;
       float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
