@@ -57,6 +57,18 @@ def make_batch(seed, lens, ilens):
     return [synthetic_episode(g, T, L) for T, L in zip(lens, ilens)]
 
 
+INGEST_VOCAB = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "walk", "past", "the", "sofa", "and", "stop", "at", "door", "turn",
+                "left", "right", "##s", "##ing", "kitchen", ",", "."]
+INGEST_TEXTS = ["Walk past the sofa and stop at the door.", "Turn left, walking past the kitchen doors.", "unknownword turns right"]
+
+
+def ingest_observation(i: int, text: str):
+    """One simulator observation as habitat hands it to transform_obs (uint8 RGB frame, float depth, instruction dict)."""
+    g = np.random.default_rng(100 + i)
+    return {"rgb": g.integers(0, 256, (8, 8, 3), dtype=np.uint8), "depth": g.random((8, 8, 1), dtype=np.float32),
+            "instruction": {"text": text, "tokens": [int(x) for x in g.integers(1, 50, 6)]}, "progress": np.float32(0.25 * i)}
+
+
 CASES = {"b1": ([7], [5]), "b3_ragged": ([5, 9, 3], [6, 4, 8]), "b2_equal": ([4, 4], [3, 3])}
 
 
@@ -88,6 +100,34 @@ def main():
     for n, bs in ((10, 3), (7, 1), (100, 16)):
         random.seed(1234 + n)
         out[f"block_shuffle.{n}.{bs}"] = np.array(tr["_block_shuffle"](list(range(n)), bs))
+    # observation ingest (common/utils.py:18-118) with a tiny WordPiece vocabulary at the path the reference hard-codes
+    import tempfile
+
+    from tokenizers import BertWordPieceTokenizer
+
+    ut2 = extract(os.path.join(REF, "common", "utils.py"), ["get_bert_tokens", "_to_tensor", "batch_obs_data_collect", "batch_obs", "transform_obs"])
+    ut2["BertWordPieceTokenizer"] = BertWordPieceTokenizer
+    ut2["List"], ut2["Dict"], ut2["Optional"] = __import__("typing").List, __import__("typing").Dict, __import__("typing").Optional
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "vocab_files"))
+        with open(os.path.join(tmp, "vocab_files", "bert-base-uncased-vocab.txt"), "w") as fh:
+            fh.write("\n".join(INGEST_VOCAB) + "\n")
+        os.chdir(tmp)
+        try:
+            for i, text in enumerate(INGEST_TEXTS):
+                obs = ingest_observation(i, text)
+                got = ut2["transform_obs"](obs, "instruction", is_bert=True)
+                out[f"ingest.{i}.instruction"] = np.array(got["instruction"], dtype=np.int64)
+                out[f"ingest.{i}.glove_tokens"] = np.array(got["glove_tokens"], dtype=np.int64)
+                b = ut2["batch_obs"](got)
+                for k, v in b.items():
+                    out[f"ingest.{i}.batch.{k}"] = v.numpy()
+            steps = [ut2["transform_obs"](ingest_observation(i, INGEST_TEXTS[0]), "instruction", is_bert=True) for i in range(3)]
+            for k, v in ut2["batch_obs_data_collect"](steps).items():
+                out[f"ingest.collect.{k}"] = v.numpy()
+        finally:
+            os.chdir(cwd)
     path = os.path.join(ROOT, "tests", "golden", "data_path.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays")

@@ -133,7 +133,8 @@ RVB_DEVICE void ffn_step(int step, int& is_fc2, int& chunk) {
 // parameter loads thrash it.
 template <class OnChunk>
 RVB_DEVICE void ln_epilogue(uint32_t tcol, const uint8_t* res0, uint8_t* dst0, const float* bias, const float* gamma,
-                            const float* beta, float2* xchg, int half, int row, int quad, float eps, OnChunk&& on_chunk) {
+                            const float* beta, float2* xchg, int half, int row, int quad, float eps, OnChunk&& on_chunk,
+                            long long* stamps = nullptr) {
   const int sw = row & 7;
   float s = 0.0f, q = 0.0f;
   // TMEM loads are double-buffered in registers: chunk ch + 1 is in flight while chunk ch is being processed
@@ -170,10 +171,12 @@ RVB_DEVICE void ln_epilogue(uint32_t tcol, const uint8_t* res0, uint8_t* dst0, c
     if (ch < 3) tmem_ld_wait();
   }
   tmem_st_wait();
+  if (stamps != nullptr) stamps[0] = clock64();
   xchg[half * 128 + row] = make_float2(s, q);
   named_bar(1 + quad, 64);
   const float2 p0 = xchg[row], p1 = xchg[128 + row];     // fixed order: both halves compute identical totals
   named_bar(1 + quad, 64);                               // the slots may be rewritten by the next LayerNorm
+  if (stamps != nullptr) stamps[1] = clock64();
   const float mean = (p0.x + p1.x) * (1.0f / 256.0f);
   const float var = fmaxf((p0.y + p1.y) * (1.0f / 256.0f) - mean * mean, 0.0f);
   const float a = rsqrtf(var + eps);
@@ -848,7 +851,8 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
       if (et == 0) VB_STAMP(37);
       const int n0 = half * 128;
       ln_epilogue(trow + TM_H + n0, bufA + 2 * half * VB_SUB, bufB + 2 * half * VB_SUB, s_par + n0, s_par + 256 + n0,
-                  s_par + 512 + n0, s_ln, half, row, quad, p.eps, [](int, const uint4&) {});
+                  s_par + 512 + n0, s_ln, half, row, quad, p.eps, [](int, const uint4&) {},
+                  (p.times != nullptr && et == 0) ? p.times + static_cast<long long>(blockIdx.x) * 64 + 61 : nullptr);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -896,7 +900,7 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
       ln_epilogue(trow + TM_Y + n0, bufB + 2 * half * VB_SUB, bufB + 2 * half * VB_SUB, s_par + 768 + n0, s_par + 1024 + n0,
                   s_par + 1280 + n0, s_ln, half, row, quad, p.eps, [ytok](int col, const uint4& yq) {
                     if (ytok != nullptr) *reinterpret_cast<uint4*>(ytok + col) = yq;
-                  });
+                  }, (p.times != nullptr && et == 0) ? p.times + static_cast<long long>(blockIdx.x) * 64 + 59 : nullptr);
       if (et == 0) VB_STAMP(57);
       named_bar(5, VB_EPI_WARPS * 32);
       if (et == 0) VB_STAMP(58);

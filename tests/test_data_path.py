@@ -132,3 +132,33 @@ def test_store_dataset_and_prefetch_round_trip(tmp_path):
     assert n_rows == 11
     with pytest.raises(ImportError, match="lmdb"):
         D.IWTrajectoryDataset(str(tmp_path / "not_a_store"), use_iw=False)
+
+
+def test_observation_ingest_matches_reference(gold, tmp_path):
+    """robo-vln_b200/obs.py against the UNMODIFIED common/utils.py functions (transform_obs -> batch_obs /
+    batch_obs_data_collect) on the same simulator-style observations and the same tiny WordPiece vocabulary; the
+    tokenizer is built once and the token ids of a repeated instruction come from the cache."""
+    from oracle.make_golden_data import INGEST_TEXTS, INGEST_VOCAB, ingest_observation
+    from robovln_b200 import obs as OB
+
+    vocab = tmp_path / "vocab.txt"
+    vocab.write_text("\n".join(INGEST_VOCAB) + "\n")
+    before = dict(OB.stats)
+    for i, text in enumerate(INGEST_TEXTS):
+        o = OB.transform_obs(ingest_observation(i, text), "instruction", is_bert=True, vocab_file=str(vocab))
+        assert o["instruction"] == gold[f"ingest.{i}.instruction"].tolist()
+        assert list(o["glove_tokens"]) == gold[f"ingest.{i}.glove_tokens"].tolist()
+        b = OB.batch_obs(o)
+        assert set(b.keys()) == {k.split(".batch.")[1] for k in gold.files if k.startswith(f"ingest.{i}.batch.")}
+        for k, v in b.items():
+            _eq(v, gold[f"ingest.{i}.batch.{k}"], f"batch_obs[{k}]")
+        b8 = OB.batch_obs(o, keep_uint8=True)                  # the sensor's uint8 frame is kept; same numbers
+        assert b8["rgb"].dtype == torch.uint8 and np.array_equal(b8["rgb"].float().numpy(), gold[f"ingest.{i}.batch.rgb"])
+    steps = [OB.transform_obs(ingest_observation(i, INGEST_TEXTS[0]), "instruction", is_bert=True, vocab_file=str(vocab)) for i in range(3)]
+    for k, v in OB.batch_obs_data_collect(steps).items():
+        _eq(v, gold[f"ingest.collect.{k}"], f"batch_obs_data_collect[{k}]")
+    assert OB.stats["tokenizer_builds"] - before["tokenizer_builds"] <= 1          # once per vocabulary, not once per step
+    assert OB.stats["token_cache_hits"] - before["token_cache_hits"] >= 3           # the repeated instruction
+    # non-BERT branch (GloVe token ids pass through)
+    o = OB.transform_obs(ingest_observation(0, INGEST_TEXTS[0]), "instruction", is_bert=False)
+    assert o["instruction"] == ingest_observation(0, INGEST_TEXTS[0])["instruction"]["tokens"] and "glove_tokens" not in o

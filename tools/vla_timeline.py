@@ -10,7 +10,7 @@ for l in lines:
     launches[-1].append([int(x) for x in l.strip().split(',')])
 t = np.array(launches[-1])[:, 1:].astype(np.int64)
 names = {0: 'mma:start', 1: 'mma:inputs landed', 2: 'mma:S issued', 3: 'mma:P ready', 4: 'mma:ctx ready', 5: 'mma:fc_o issued', 6: 'mma:X ready', 7: 'mma:all issued',
-         32: 'epi:start', 33: 'epi:S done', 34: 'epi:softmax done', 35: 'epi:O done', 36: 'epi:ctx written', 37: 'epi:fc_o done', 38: 'epi:ffn epilogues done', 39: 'epi:Y done', 56: 'epi:end', 57: 'epi:LN2 written', 58: 'epi:LN2 barrier'}
+         32: 'epi:start', 33: 'epi:S done', 34: 'epi:softmax done', 35: 'epi:O done', 36: 'epi:ctx written', 37: 'epi:fc_o done', 38: 'epi:ffn epilogues done', 39: 'epi:Y done', 56: 'epi:end', 57: 'epi:LN2 written', 58: 'epi:LN2 barrier', 59: 'epi:LN2 pass1 done', 60: 'epi:LN2 stats exchanged', 61: 'epi:LN1 pass1 done', 62: 'epi:LN1 stats exchanged'}
 for s in range(16): names[8 + s] = f'mma:ffn step{s} begin'
 for c in range(8): names[40 + 2 * c] = f'epi:chunk{c} wait'; names[41 + 2 * c] = f'epi:chunk{c} hfull'
 ctas = [int(a) for a in sys.argv[2:]] or [0]
