@@ -45,6 +45,10 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+if os.environ.get("ROBOVLN_BUILD_STAMPS") == "1":        # phase-stamp instrumentation for tools/gemm_timeline.py (diagnostic builds only)
+    NVCC_FLAGS.append("-DRVB_GEMM_STAMPS=1")
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:
