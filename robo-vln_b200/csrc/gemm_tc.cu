@@ -51,12 +51,8 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;  // 320
-// Epilogue staging: [0, 32 KiB) one 128 x 128B chunk buffer per epilogue group; [32, 64 KiB) either the SECOND buffer of
-// each group (double-buffered stores: a TMA store queues behind the ~150 KB of operand loads in flight and takes ~2-4k
-// cycles to read its staging buffer -- measured with tools/gemm_timeline.py: the epilogue, not the MMA main loop, bounded
-// every multi-tile GEMM of the step), or the residual-prefetch slices, or the LayerNorm exchange buffer.
-constexpr int STAGING_BYTES = 4 * 16384;
-constexpr int SMEM_STAGE_BUDGET = 163840;             // 160 KiB of pipeline stages
+constexpr int STAGING_BYTES = 2 * 16384;              // one 128 x 128B chunk buffer per epilogue group
+constexpr int SMEM_STAGE_BUDGET = 196608;             // 192 KiB of pipeline stages
 
 // CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (2-CTA cluster) owns a 256 x BN
 // tile; each CTA stages its 128 rows of A and HALF of B (BN/2 rows) per K block, which doubles
@@ -70,7 +66,8 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// phase stamps for tools/gemm_timeline.py: compiled in only with -DRVB_GEMM_STAMPS=1 (ROBOVLN_BUILD_STAMPS=1 python build.py)
+// phase stamps for tools/gemm_timeline.py: compiled in only with -DRVB_GEMM_STAMPS=1 (ROBOVLN_BUILD_STAMPS=1 python build.py).
+// Only stamps that follow an mbarrier wait are meaningful: clock reads float freely among independent ALU instructions.
 #if defined(RVB_GEMM_STAMPS) && RVB_GEMM_STAMPS
 #define GT_STAMP(i)                                                                                  \
   do {                                                                                               \
@@ -155,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* ln_bar = rbar_base + NUM_EPI_WARPS;  // [2] LayerNorm exchange: row sums / centred sums of squares
   // residual-prefetch mode: the pipeline runs with fewer stages and the B buffers of the unused
   // stages hold eight 4 KiB residual slices (32 rows x 128 B, one per epilogue warp)
-  uint8_t* res_slices = smem_c + 32768;
+  uint8_t* res_slices = smem_b + nstages * C::B_STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -320,9 +317,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = (quad == 2 && lane == 0);  // first thread of the group (warps 2 and 6)
     uint8_t* stage_buf = smem_c + group * 16384;
     uint8_t* my_row = stage_buf + row_in_tile * 128;
-    // double-buffered staging (plain epilogue only): chunk i is staged while the store of chunk i - 1 is still being read
-    const bool dbuf = !LN && !GN && p.dbuf != 0;
-    int sbuf = 0;
     const int sw = row_in_tile & 7;
     // columns per chunk: one 128-byte row segment of the output type
     const int chunk_cols = p.out_f32 ? 32 : 64;
@@ -388,18 +382,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
-      // fp32-output GEMMs (the pre-LayerNorm sums of BERT): this thread's residual values for its NEXT chunk are always in
-      // flight while the current chunk is processed (row-strided global loads: ~800 cycles each when left in the loop);
-      // the first chunk's are fetched before the accumulator is waited for
-      uint4 rcur[4];
-      const bool res_pre = !LN && !GN && p.out_f32 && p.tma_store && res_row != nullptr;
-      auto load_res = [&](int ch_, uint4 (&dst)[4]) {
-        const int nn = n0 + ch_ * 32;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = (ch_ < BN / 32 && nn < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + nn) + j) : make_uint4(0, 0, 0, 0);
-      };
-      if (res_pre) load_res(group, rcur);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (tile == unit && warp == 2 && lane == 0) GT_STAMP(6);
@@ -552,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // and accumulates (sum, sum of squares) in fp32; the partials of the 2 groups x ncl CTAs are pushed
         // into every CTA of the cluster (DSMEM) and folded in a fixed order -> mean, rstd (one exchange).
         // Pass 2 normalises, applies gamma / beta (+ positional table) and stores through TMA.
-        float2* ln_buf = reinterpret_cast<float2*>(smem_c + 32768);   // [2 parity][ncl][2 group][128]
+        float2* ln_buf = reinterpret_cast<float2*>(smem_a + nstages * A_STAGE_BYTES);   // [2 parity][ncl][2 group][128]
         const int par = ln_tile_count & 1;
         auto ln_slot = [&](int src, int grp) { return ln_buf + (((par * ncl + src) * 2 + grp) * BLOCK_M); };
         // pass 1
@@ -707,19 +689,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int c0 = ch * chunk_cols;
           const int n = n0 + c0;
           if (n >= p.N) break;  // uniform across the group
-          // the staging buffer is free once the store issued from it has been read out: the previous store (single
-          // buffer) or the one before it (double buffer: at most one younger store may still be in flight)
+          // the staging buffer is free once the previous store from it has been read out
           if (store_pending) {
-            if (p.plain) {   // per-warp stores: only this warp's own stores matter
-              if (lane == 0) { if (dbuf) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            if (p.plain) {   // per-warp stores: only this warp's previous store has to have drained
+              if (lane == 0) tma_store_wait_read<0>();
               __syncwarp();
             } else {
-              if (leader) { if (dbuf) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+              if (leader) tma_store_wait_read<0>();
               named_bar_sync(1 + group, 128);
             }
           }
-          uint8_t* const cur_buf = stage_buf + (dbuf ? sbuf * 32768 : 0);
-          uint8_t* const my_row = cur_buf + row_in_tile * 128;
           if (p.out_f32) {
             uint32_t v[32];
             __syncwarp();
@@ -728,21 +707,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (res_pre) {
-              uint4 rnext[4];
-              load_res(ch + 2, rnext);        // next chunk of this warp (zeros past the tile)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 t;
-                t = unpack_h2(rcur[j].x); f[8 * j] += t.x; f[8 * j + 1] += t.y;
-                t = unpack_h2(rcur[j].y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
-                t = unpack_h2(rcur[j].z); f[8 * j + 4] += t.x; f[8 * j + 5] += t.y;
-                t = unpack_h2(rcur[j].w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-            }
-            epilogue_math(f, p, n, res_pre ? nullptr : res_row);
+            epilogue_math(f, p, n, res_row);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -806,18 +771,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // tile as soon as it is staged -- no cross-warp barrier, the eight warps run decoupled
             __syncwarp();
             if (lane == 0 && !(p.dbg & 1)) {
-              tma_store_4d(&tmC, cur_buf + quad * 4096, n, mt * BLOCK_M + quad * 32, 0, 0);
+              tma_store_4d(&tmC, stage_buf + quad * 4096, n, mt * BLOCK_M + quad * 32, 0, 0);
               tma_store_commit();
             }
           } else {
             named_bar_sync(1 + group, 128);
             if (leader) {
-              tma_store_4d(&tmC, cur_buf, n, 0, h0, img);
+              tma_store_4d(&tmC, stage_buf, n, 0, h0, img);
               tma_store_commit();
             }
           }
           store_pending = true;
-          sbuf ^= 1;
         }
         // every TMEM read of this warp for this accumulator has completed (wait::ld above)
         tc_fence_before();
@@ -882,7 +846,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) GT_STAMP(9);
   if (CTAS == 2 || ncl > 1) cluster_sync_all();   // the peer may still be using this CTA's barriers / TMEM half / smem
   if (warp == 1) {
     tc_fence_after();
@@ -974,31 +937,33 @@ void launch_bn(const GemmTcPlan& plan, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  // ROBOVLN_GEMM_TIMES=<file>: per-CTA phase stamps of every launch (diagnostics; synchronises the stream)
+#if defined(RVB_GEMM_STAMPS) && RVB_GEMM_STAMPS
+  // ROBOVLN_GEMM_TIMES=<file>: per-CTA phase stamps of every launch (diagnostic builds only; synchronises the stream)
   static const char* tenv = std::getenv("ROBOVLN_GEMM_TIMES");
-  if (tenv == nullptr) {
-    RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS, EPI>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
+  if (tenv != nullptr) {
+    GemmTcParams pp = plan.p;
+    const size_t tbytes = static_cast<size_t>(plan.grid) * 16 * sizeof(long long);
+    RVB_CUDA(cudaMalloc(&pp.times, tbytes));
+    RVB_CUDA(cudaMemsetAsync(pp.times, 0, tbytes, stream));
+    RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS, EPI>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, pp));
+    RVB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<long long> host(static_cast<size_t>(plan.grid) * 16);
+    RVB_CUDA(cudaMemcpy(host.data(), pp.times, tbytes, cudaMemcpyDeviceToHost));
+    RVB_CUDA(cudaFree(pp.times));
+    if (FILE* f = std::fopen(tenv, "a")) {
+      std::fprintf(f, "# gemm BN=%d CTAS=%d EPI=%d M=%d N=%d num_kb=%d grid=%d tiles=%d act=%d out_f32=%d res=%d\n", BN, CTAS, EPI, plan.p.M,
+                   plan.p.N, plan.p.num_kb, plan.grid, plan.p.m_tiles * plan.p.n_tiles, plan.p.act, plan.p.out_f32, plan.p.res != nullptr);
+      for (int c = 0; c < plan.grid; ++c) {
+        std::fprintf(f, "%d", c);
+        for (int i = 0; i < 16; ++i) std::fprintf(f, ",%lld", host[static_cast<size_t>(c) * 16 + i]);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+    }
     return;
   }
-  GemmTcParams pp = plan.p;
-  const size_t tbytes = static_cast<size_t>(plan.grid) * 16 * sizeof(long long);
-  RVB_CUDA(cudaMalloc(&pp.times, tbytes));
-  RVB_CUDA(cudaMemsetAsync(pp.times, 0, tbytes, stream));
-  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS, EPI>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, pp));
-  RVB_CUDA(cudaStreamSynchronize(stream));
-  std::vector<long long> host(static_cast<size_t>(plan.grid) * 16);
-  RVB_CUDA(cudaMemcpy(host.data(), pp.times, tbytes, cudaMemcpyDeviceToHost));
-  RVB_CUDA(cudaFree(pp.times));
-  if (FILE* f = std::fopen(tenv, "a")) {
-    std::fprintf(f, "# gemm BN=%d CTAS=%d EPI=%d M=%d N=%d num_kb=%d grid=%d tiles=%d act=%d out_f32=%d res=%d\n", BN, CTAS, EPI, plan.p.M,
-                 plan.p.N, plan.p.num_kb, plan.grid, plan.p.m_tiles * plan.p.n_tiles, plan.p.act, plan.p.out_f32, plan.p.res != nullptr);
-    for (int c = 0; c < plan.grid; ++c) {
-      std::fprintf(f, "%d", c);
-      for (int i = 0; i < 16; ++i) std::fprintf(f, ",%lld", host[static_cast<size_t>(c) * 16 + i]);
-      std::fprintf(f, "\n");
-    }
-    std::fclose(f);
-  }
+#endif
+  RVB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CTAS, EPI>, plan.tmA, plan.tmB, plan.tmC, plan.tmR, plan.p));
 }
 
 bool use_pair_mma() {
@@ -1288,15 +1253,9 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   {
     const int b_stage = (best_bn / best_ctas) * BLOCK_K * 2;
     const int max_stages = std::min(8, SMEM_STAGE_BUDGET / (A_STAGE_BYTES + b_stage));
-    // the residual slices (32 KiB) / the LayerNorm statistics exchange (12 KB) live in the second half of the staging
-    // area; plans that need neither double-buffer their output stores there
-    p.nstages = max_stages;
-    static int dbuf_env = -1;
-    if (dbuf_env < 0) {
-      const char* e = std::getenv("ROBOVLN_EPI_DBUF");
-      dbuf_env = (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
-    }
-    p.dbuf = (dbuf_env && p.tma_store && !p.res_tma && !ln && !gn) ? 1 : 0;
+    // the residual slices (32 KiB) live in the B buffers of the stages given up
+    p.nstages = p.res_tma ? max_stages - (32768 + b_stage - 1) / b_stage : max_stages;
+    if (ln) p.nstages = max_stages - 1;   // the A buffer of the stage given up holds the statistics exchange (12 KB)
     RVB_CHECK(p.nstages >= 2, "gemm: too few pipeline stages");
   }
   if (p.res_tma) {

@@ -174,7 +174,6 @@ struct GemmTcParams {
   int ln_xchg;       // 1: statistics exchanged through global memory (ln_ws / ln_cnt), independent CTAs
   void* ln_ws;
   int* ln_cnt;
-  int dbuf;          // 1: output stores double-buffered in the staging area (plain epilogue without residual prefetch)
   int krot;          // 1: per-tile rotation of the k-block walk (L2 hot-spot avoidance)
   int nstages;       // pipeline stages in use (fewer when the residual slices take their place)
   long long* times;  // diagnostics (ROBOVLN_GEMM_TIMES): [CTA][16] SM-clock stamps of the first tile's phases; null in production

@@ -1,11 +1,12 @@
-"""Phase timeline of gemm_tc_kernel on the BERT-shaped problems of the step (ROBOVLN_GEMM_TIMES=<file> must be set):
+"""Phase timeline of gemm_tc_kernel on the BERT-shaped problems of the step.  Needs a library built with the stamps compiled in
+(ROBOVLN_BUILD_STAMPS=1 python robo-vln_b200/build.py) and ROBOVLN_GEMM_TIMES=<file>:
    run:      ROBOVLN_GEMM_TIMES=gpurun_out/gemm_times.csv python tools/gemm_timeline.py run
    analyse:  python tools/gemm_timeline.py show gpurun_out/gemm_times.csv"""
 import os, sys
 import numpy as np
 
 NAMES = ["kernel start", "setup done (barriers, TMEM)", "first TMA issued", "tile 0 loads issued", "first operands landed", "tile 0 MMAs issued",
-         "tile 0 accumulator complete", "tile 0 epilogue done", "all epilogues done", "kernel end"]
+         "tile 0 accumulator complete", "tile 0 epilogue done", "all epilogues done"]
 
 
 def run():
