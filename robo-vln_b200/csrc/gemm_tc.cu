@@ -114,6 +114,35 @@ RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, cons
   }
 }
 
+// epilogue_math with the bias of the 32 columns arriving lane-distributed (lane l holds bias[n + l]).  With > 200 KB of
+// shared memory carved out the L1 holds nothing, so the per-thread bias loads of epilogue_math are L2 round trips on
+// the epilogue's critical path: measured (tools/gemm_timeline.py + ROBOVLN_EPI_DEBUG=2) 3.8k of the 7.7k epilogue cycles
+// of a 128 x 256 bias-only tile.  The lane-distributed copy is fetched once per tile BEFORE the accumulator is waited for.
+RVB_DEVICE void epilogue_math_b(float (&f)[32], const GemmTcParams& p, int n, const h16* res_row, float bias_lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+  if (res_row != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (n + j < p.N) {
+        const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res_row + n + j));
+        float2 t;
+        t = unpack_h2(r4.x); f[j] += t.x; f[j + 1] += t.y;
+        t = unpack_h2(r4.y); f[j + 2] += t.x; f[j + 3] += t.y;
+        t = unpack_h2(r4.z); f[j + 4] += t.x; f[j + 5] += t.y;
+        t = unpack_h2(r4.w); f[j + 6] += t.x; f[j + 7] += t.y;
+      }
+    }
+  }
+  if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+  }
+}
+
 template <int BN, int CTAS, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -382,6 +411,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
+      // plain epilogue: this warp's bias values for the whole tile, lane-distributed -- 32-column slot s of the warp's
+      // columns lives in bl[s] (16-bit output: chunk group + 2i = slots 2i, 2i + 1; fp32 output: chunk group + 2i = slot i)
+      constexpr int BSLOTS = (!LN && !GN) ? (BN / 64 < 2 ? 2 : BN / 64) : 1;
+      float bl[BSLOTS];
+      uint4 rcur[4];
+      const bool res_pre = !LN && !GN && p.out_f32 && p.tma_store && res_row != nullptr;
+      auto load_res = [&](int ch_, uint4 (&dst)[4]) {   // fp32 output: residual of one 32-column chunk of this thread's row
+        const int nn = n0 + ch_ * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = (ch_ < BN / 32 && nn < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + nn) + j) : make_uint4(0, 0, 0, 0);
+      };
+      if constexpr (!LN && !GN) {
+#pragma unroll
+        for (int s_ = 0; s_ < BSLOTS; ++s_) {
+          // slot -> first column: 16-bit: chunk (group + 2*(s_/2)) * 64 + (s_%2) * 32; fp32: chunk (group + 2*s_) * 32
+          const int col = p.out_f32 ? (group + 2 * s_) * 32 : (group + 2 * (s_ >> 1)) * 64 + (s_ & 1) * 32;
+          const int nn = n0 + col + lane;
+          bl[s_] = (p.bias != nullptr && col < BN && nn < p.N) ? __ldg(p.bias + nn) : 0.0f;
+        }
+        if (res_pre) load_res(group, rcur);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (tile == unit && warp == 2 && lane == 0) GT_STAMP(6);
@@ -707,7 +758,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            epilogue_math(f, p, n, res_row);
+            if (res_pre) {     // the next chunk's residual is in flight while this one is processed
+              uint4 rnext[4];
+              load_res(ch + 2, rnext);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 t;
+                t = unpack_h2(rcur[j].x); f[8 * j] += t.x; f[8 * j + 1] += t.y;
+                t = unpack_h2(rcur[j].y); f[8 * j + 2] += t.x; f[8 * j + 3] += t.y;
+                t = unpack_h2(rcur[j].z); f[8 * j + 4] += t.x; f[8 * j + 5] += t.y;
+                t = unpack_h2(rcur[j].w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+            }
+            {
+              float bsel = 0.0f;
+#pragma unroll
+              for (int s_ = 0; s_ < BSLOTS; ++s_)
+                if (s_ == ((ch - group) >> 1)) bsel = bl[s_];
+              epilogue_math_b(f, p, n, res_pre ? nullptr : res_row, bsel);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -753,7 +824,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   t = unpack_h2(rv[j].w); f[8 * j + 6] += t.x; f[8 * j + 7] += t.y;
                 }
               }
-              if (!(p.dbg & 2)) epilogue_math(f, p, n + half * 32, p.res_tma ? nullptr : res_row);
+              if (!(p.dbg & 2)) {
+                float bsel = 0.0f;
+#pragma unroll
+                for (int s_ = 0; s_ < BSLOTS; ++s_)
+                  if (s_ == (ch - group) + half) bsel = bl[s_];      // slot 2 * ((ch - group) / 2) + half
+                epilogue_math_b(f, p, n + half * 32, p.res_tma ? nullptr : res_row, bsel);
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint4 q;
