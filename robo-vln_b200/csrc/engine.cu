@@ -77,7 +77,13 @@ GemmTcPlan* Engine::add_gemm(Stage& st, const ConvGemm& g, int force_bn) {
   if (dry_) return nullptr;
   gemms_.emplace_back(new GemmTcPlan());
   GemmTcPlan* plan = gemms_.back().get();
-  gemm_tc_make_plan(g, plan, force_bn);
+  ConvGemm gg = g;
+  gg.extra_rounds = extra_rounds_;
+  gemm_tc_make_plan(gg, plan, force_bn);
+  // stage-level cap on the persistent grid (depth trunk, ROBOVLN_DEPTH_GRID): fewer CTAs walk more tiles each, which
+  // trades kernel latency (the depth chain is off the critical path) for less per-CTA set-up / drain time on SMs the
+  // RGB trunk and BERT could be using
+  if (grid_cap_ > 0 && plan->ctas == 1 && !plan->p.ln && plan->grid > grid_cap_) plan->grid = grid_cap_;
   Op op([plan](cudaStream_t s) { gemm_tc_launch(*plan, s); return 1; });
   // algorithmic K (the window-mode stem multiplies 7 x 64 padded columns for 7 x 7 x 3 real taps)
   const double K = g.window ? 147.0 : static_cast<double>(g.KH) * g.KW * g.Cin;
@@ -736,16 +742,32 @@ size_t Engine::plan(const hcm_shape& shp, void* workspace, size_t bytes) {
   stage_hc_lo_ = reinterpret_cast<float*>(alloc(2ull * shp.N * 512 * 4));
 
   const std::string trunk_ns = have_hi_ ? "hi" : "lo";
+  // extra tile rounds per encoder stream (ROBOVLN_GRID_ROUNDS = "rgb,depth,bert"): fewer, longer-lived CTAs per kernel
+  int er[3] = {1, 1, 1};
+  if (const char* e = std::getenv("ROBOVLN_GRID_ROUNDS")) std::sscanf(e, "%d,%d,%d", &er[0], &er[1], &er[2]);
+  extra_rounds_ = er[0];
   plan_rgb_trunk(trunk_ns, st_rgb_);
-  plan_depth_trunk(trunk_ns, st_depth_);
+  extra_rounds_ = er[1];
+  {
+    static const char* dg = std::getenv("ROBOVLN_DEPTH_GRID");
+    grid_cap_ = dg != nullptr ? std::atoi(dg) : 0;   // with balanced grids (gemm_tc_make_plan) a cap no longer helps: 3.68 (off) vs 3.71 ms/step (64)
+    plan_depth_trunk(trunk_ns, st_depth_);
+    grid_cap_ = 0;
+  }
+  extra_rounds_ = 0;
   if (have_hi_ && have_lo_ && !lo_shares_trunks_) {
     // lo has its own (different) frozen trunks: a second pair of trunk stages writing the same
     // feature buffers, used only by hcm_forward_lo(reuse_trunks = 0)
+    extra_rounds_ = er[0];
     plan_rgb_trunk("lo", st_rgb_lo_);
+    extra_rounds_ = er[1];
     plan_depth_trunk("lo", st_depth_lo_);
+    extra_rounds_ = 0;
   }
   if (have_hi_) {
+    extra_rounds_ = er[2];
     plan_bert(st_bert_);
+    extra_rounds_ = 0;
     plan_hi_tail(st_pre_, st_hi_tail_);
     // stand-alone cross-modal stage on caller tensors (BASELINE.json configs[2])
     cm_bert_in_ = reinterpret_cast<h16*>(alloc(static_cast<size_t>(shp.instr_rows == 1 ? 1 : B) * shp.L * 768 * 2));

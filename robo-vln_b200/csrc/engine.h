@@ -92,6 +92,8 @@ class Engine {
   int rgb_fmt_ = 0;
   // Instruction cache: the caller asserts that the instruction tokens are the ones of the
   // previous call, so BERT (54 % of the step's FLOPs) and the query-side projection keep their outputs from that call.
+  int extra_rounds_ = 0;   // persistent-grid policy of the stage being planned (ConvGemm::extra_rounds)
+  int grid_cap_ = 0;   // > 0 while a stage whose GEMM grids are capped is being planned
   bool skip_bert_ = false;
   RunArgs args_;
   // forward_policy only: the hi head also writes argmax -> sub-goal ids and lo's sub-task embedding

@@ -1346,7 +1346,14 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   }
 
   const long long units = static_cast<long long>((p.m_tiles + best_ctas - 1) / best_ctas) * p.n_tiles;
-  plan->grid = static_cast<int>(std::min<long long>(units, sms / best_ctas)) * best_ctas;
+  // balanced persistent grid: with R = ceil(units / slots) rounds, ceil(units / R) CTAs (or pairs) finish in the same R
+  // tile times as a full grid would, and the CTAs not launched do not pay the ~3 us set-up (descriptor fetch, first
+  // operand latency) on SMs that the other two streams of the step can use.  g.extra_rounds > 0 goes further and
+  // trades kernel latency for SM time: the step is bound by the SM time of its three concurrent streams, not by
+  // the length of any one chain
+  const long long slots = sms / best_ctas;
+  const long long rounds = (units + slots - 1) / slots + (ln ? 0 : g.extra_rounds);
+  plan->grid = static_cast<int>((units + rounds - 1) / rounds) * best_ctas;
   if (ln) plan->grid = std::min(p.m_tiles, sms / p.n_tiles) * p.n_tiles;   // whole clusters / whole row blocks of n_tiles CTAs
   plan->valid = true;
 }

@@ -115,6 +115,8 @@ struct ConvGemm {
   // m_tiles*4 ints that are zero before the first launch (monotonic counters: never reset).
   void* ln_ws = nullptr;
   int* ln_cnt = nullptr;
+  // persistent-grid policy: the grid is sized for ceil(units / slots) + extra_rounds tile rounds (gemm_tc_make_plan)
+  int extra_rounds = 0;
   // GroupNorm folded into the store, for feature maps small enough that every 128-row M tile holds WHOLE
   // samples (gn_hw = H*W of the output in {16, 64}) and every N tile whole groups:
   //   out = relu?( GN_groups(acc) * gn_gamma + gn_beta + res )     (res: plain h16 residual, optional)
