@@ -169,7 +169,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ float gn_x[GN ? 2 * 8 * 16 : 1];   // GroupNorm: (sum, sumsq) x 8 groups per epilogue warp, double-buffered
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  // resident-B mode: [nstages A buffers][num_kb B blocks]; otherwise [STAGES A buffers][STAGES B buffers]
+  uint8_t* smem_b = smem + (p.b_res ? nstages : STAGES) * A_STAGE_BYTES;
   uint8_t* smem_c = smem + STAGES * C::STAGE_BYTES;  // 2 x 16 KiB staging, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + STAGING_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
@@ -227,6 +228,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (CTAS == 1 && p.b_res && unit < total_tiles) {   // the whole weight matrix of this (single) N tile, once
+        mbar_arrive_expect_tx(&rbar_base[0], static_cast<uint32_t>(p.num_kb) * C::B_STAGE_BYTES);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          tma_load_2d(smem_b + kb * C::B_STAGE_BYTES, &tmB, &rbar_base[0], tap * p.Cin + cb * BLOCK_K, 0);
+        }
+      }
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         const int mu = tile / p.n_tiles;
         const int nt = tile - mu * p.n_tiles;
@@ -272,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + C::B_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + (p.b_res ? 0u : static_cast<uint32_t>(C::B_STAGE_BYTES)));
           if (p.plain) {
             tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, mt * BLOCK_M, 0, 0);
           } else if (p.window2) {
@@ -282,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int s = tap - r * p.KW;
             tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, s - p.pad, h0 * p.stride + r - p.pad, img);
           }
-          tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cb * BLOCK_K, nt * BN);
+          if (!p.b_res) tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cb * BLOCK_K, nt * BN);
           if (tile == unit && kseq == 0) GT_STAMP(2);
           if (++stage == nstages) {
             stage = 0;
@@ -300,6 +309,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (CTAS == 1 && p.b_res && unit < total_tiles) mbar_wait(&rbar_base[0], 0);   // resident weights have landed
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -309,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           if (tile == unit && kb == 0) GT_STAMP(4);
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (p.b_res ? kb : stage) * C::B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 elements = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
@@ -1333,6 +1343,22 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
     // the residual slices (32 KiB) live in the B buffers of the stages given up
     p.nstages = p.res_tma ? max_stages - (32768 + b_stage - 1) / b_stage : max_stages;
     if (ln) p.nstages = max_stages - 1;   // the A buffer of the stage given up holds the statistics exchange (12 KB)
+    // resident B: a launch with ONE N tile multiplies every M tile by the same weights; when they fit beside at least
+    // three A stages they are loaded once per CTA and the ring carries A only.  The 64- and 128-wide convs of the trunk
+    // fronts re-fetched 8-16 KB of weights per 16 KB of activations -- a third to a half of their L2 -> SM traffic.
+    static int bres_env = -1;
+    if (bres_env < 0) {
+      const char* e = std::getenv("ROBOVLN_B_RESIDENT");
+      bres_env = (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
+    }
+    const int b_total = p.num_kb * b_stage;
+    const int a_stages_left = (SMEM_STAGE_BUDGET - b_total) / A_STAGE_BYTES;
+    p.b_res = (bres_env && best_ctas == 1 && p.n_tiles == 1 && !p.res_tma && !ln && !gn && p.m_tiles > 1 && b_total <= SMEM_STAGE_BUDGET &&
+               a_stages_left >= 3) ? 1 : 0;
+    if (p.b_res) {
+      p.nstages = std::min(max_stages, a_stages_left);   // the barrier arrays hold Cfg::STAGES = max_stages entries
+      p.krot = 0;   // the MMA issuer indexes the resident blocks by k block: the producer must walk them in order
+    }
     RVB_CHECK(p.nstages >= 2, "gemm: too few pipeline stages");
   }
   if (p.res_tma) {

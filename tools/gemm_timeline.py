@@ -23,6 +23,10 @@ def run():
              ("ao", x768, mk((768, 768), 768 ** -0.5, 6), dict(bias=mk((768,), 0.1, 7, torch.float32), res=res, out_f32=True)),
              ("ff1", x768, mk((3072, 768), 768 ** -0.5, 8), dict(bias=mk((3072,), 0.1, 9, torch.float32), act=2)),
              ("ff2", x3072, mk((768, 3072), 3072 ** -0.5, 10), dict(bias=mk((768,), 0.1, 11, torch.float32), res=res, out_f32=True))]
+    if len(sys.argv) > 2 and sys.argv[2] == "conv":
+        xc = mk((64, 64, 64, 64), 1.0, 31)
+        cases = [("l1conv2", xc, mk((64, 576), 576 ** -0.5, 32), dict(KH=3, KW=3, stride=1, pad=1, bias=mk((64,), 0.1, 33, torch.float32), act=1)),
+                 ("l1conv1", mk((1, 1, 262144, 256), 1.0, 34), mk((64, 256), 256 ** -0.5, 35), dict(bias=mk((64,), 0.1, 36, torch.float32), act=1))]
     for name, x, w, kw in cases:
         for _ in range(3):
             conv_gemm(x, w, **kw)
