@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -510,41 +511,43 @@ def run_train(args):
     # here the fused single-launch versions (robo-vln_b200/optim.py); losses with the trainer's masking, fused (losses.py)
     opt_hi = R.optim.FusedAdamW([p for p in hi.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-3)
     opt_lo = R.optim.FusedAdam([p for p in lo.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-3)
-    sensor = (tgt_hi + 1).float()                 # vln_oracle_action_sensor column: 0 = ignore, k = sub-goal k - 1
+    sensor = (tgt_hi + 1).float().view(T, 1)      # vln_oracle_action_sensor column: 0 = ignore, k = sub-goal k - 1
     h0 = torch.zeros((2, 1, 512), device=dev)
+    prev = torch.zeros((T, 2), device=dev)
 
-    def step():
-        opt_hi.zero_grad(set_to_none=True)
-        opt_lo.zero_grad(set_to_none=True)
-        obs = {"rgb": rgb, "depth": depth, "instruction": ids}
-        logits, _ = hi((obs, h0, None, masks))
-        R.losses.hi_loss(logits, sensor).backward()
-        opt_hi.step()
-        act, stop, _ = lo((obs, h0, None, masks, sub))
-        la, ls = R.losses.lo_loss(act, stop, tgt_act, tgt_stop)
-        (la + ls).backward()
-        opt_lo.step()    # the engine runs only the FROZEN encoders in train mode: no re-pack of its weights per step
-        return logits
+    def timed(upd, steps, warmup):
+        def step():
+            # _update_agent's call (hierarchical_trainer.py:492-560): the dict is rebuilt per step because the update
+            # consumes 'instruction' and rewrites the sensor column, as the reference does
+            obs = {"rgb": rgb, "depth": depth, "instruction": ids, "vln_oracle_action_sensor": sensor}
+            return upd.update(obs, prev, masks, tgt_act, tgt_stop, h0, h0, None)
+        for _ in range(max(warmup, 3)):
+            out = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, out
 
-    for _ in range(max(args.warmup, 3)):
-        out = step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    graphed = R.trainer.DaggerUpdater(hi, lo, opt_hi, opt_lo, graph=True)
+    ms, out = timed(graphed, args.steps, args.warmup)
+    eager_ms, _ = timed(R.trainer.DaggerUpdater(hi, lo, opt_hi, opt_lo, graph=False), max(args.steps // 2, 3), 3)
     obs_s = T / (ms * 1e-3)
     print(json.dumps({
         "metric": "dagger_step_tokens_and_pixels_per_sec", "value": obs_s * (L + 2 * 256 * 256), "unit": "tokens+pixels/s",
         "obs_per_sec": obs_s, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "eager_tail_ms_per_step": eager_ms, "graphs_captured": sum(g is not None for g in graphed._graphs.values()),
+        "graph_errors": graphed.graph_errors,
         "higher_is_better": True, "dtype": hi.runtime().dtype_name, "data": "synthetic",
-        "config": {"workload": "cfg5: DAgger inner loop, trajectory T=%d (N=1), shared %d-token instruction, hi fwd+CE+bwd, "
-                               "lo fwd+MSE+BCE+bwd, fused AdamW (hi) / Adam (lo) steps and fused losses; frozen encoders on the engine, "
-                               "trainable tail's linear / LSTM backward in torch autograd" % (T, L)},
-        "outputs_finite": bool(torch.isfinite(out).all().item()),
+        "config": {"workload": "cfg5: DAgger update (trainer.DaggerUpdater.update = _update_agent), trajectory T=%d (N=1), shared %d-token "
+                               "instruction: frozen encoders once on the engine; per model the trainable tail's forward + fused loss + "
+                               "backward (torch autograd: linear / attention / cuDNN LSTM) replayed from a CUDA graph, then the fused "
+                               "AdamW (hi) / Adam (lo) step; losses read back on the host every step as the reference does" % (T, L)},
+        "losses": [float(v) for v in out[0][:3]],
+        "outputs_finite": bool(all(math.isfinite(float(v)) for v in out[0][:3])),
     }), flush=True)
 
 

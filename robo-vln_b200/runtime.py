@@ -381,12 +381,12 @@ class HcmRuntime:
             self._feat_lo_weights = bool(use_lo_weights)
             self._keep = (rgb, depth, i_f32, i_i64)
         out = {
-            "rgb_feat": self.get_buffer("rgb_tokens")[:, :, :2048].float(),
-            "rgb_gmean": self.get_buffer("rgb_gmean").float(),
-            "depth_feat": self.get_buffer("depth_tokens")[:, :, :128].float(),
+            "rgb_feat": self.get_buffer("rgb_tokens", sync=False)[:, :, :2048].float(),
+            "rgb_gmean": self.get_buffer("rgb_gmean", sync=False).float(),
+            "depth_feat": self.get_buffer("depth_tokens", sync=False)[:, :, :128].float(),
         }
         if with_bert:
-            out["bert"] = self.get_buffer("bert").float()
+            out["bert"] = self.get_buffer("bert", sync=False).float()
         return out
 
     def _no_instruction_cache(self):
@@ -496,8 +496,9 @@ class HcmRuntime:
         self._keep = (i_f32, i_i64)
         return self.get_buffer("bert").float()
 
-    def get_buffer(self, name: str) -> torch.Tensor:
-        """Copy of an internal stage buffer (parity tests)."""
+    def get_buffer(self, name: str, sync: bool = True) -> torch.Tensor:
+        """Copy of an internal stage buffer (parity tests; sync=False: ordered on the current stream only, for callers
+        that keep working on that stream)."""
         ptr = ctypes.c_void_p()
         dt = ctypes.c_int()
         nd = ctypes.c_int()
@@ -513,5 +514,6 @@ class HcmRuntime:
         with torch.cuda.device(self.device):
             check(self.lib.hcm_copy_buffer(self.handle, name.encode(), _ptr(out), numel * out.element_size(),
                                            self._stream()), f"hcm_copy_buffer({name})")
-            torch.cuda.synchronize()
+            if sync:
+                torch.cuda.synchronize()
         return out

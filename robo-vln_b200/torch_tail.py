@@ -62,7 +62,15 @@ def visual_ling_attn(m, ins: torch.Tensor, vis: torch.Tensor, p_drop: float, tra
     return F.layer_norm(X + drop(Y), (d,), f.layer_norm.weight, f.layer_norm.bias, 1e-5)
 
 
-def lstm_state_encoder(rnn, x: torch.Tensor, hidden: torch.Tensor, masks: torch.Tensor):
+def segment_starts(masks: torch.Tensor, N: int):
+    """First steps of the LSTM segments of a [T*N] mask vector: t = 0 and every t where any environment is reset
+    (one host read of the masks; CUDA-graph callers compute it before capture and pass it in)."""
+    T = masks.numel() // N
+    m = masks.reshape(T, N)
+    return [0] + ([t + 1 for t, v in enumerate((m[1:] == 0.0).any(dim=1).tolist()) if v] if T > 1 else [])
+
+
+def lstm_state_encoder(rnn, x: torch.Tensor, hidden: torch.Tensor, masks: torch.Tensor, starts=None):
     """rnn = module.state_encoder.rnn (parameter container); x [T*N, I], hidden [2,N,H], masks [T*N].
     RNNStateEncoder.seq_forward (rnn_state_encoder.py:85-136): the trajectory is cut at t = 0 and at every step
     where any environment is reset, (h, c) are multiplied by the masks of the segment's first step, and each
@@ -71,7 +79,8 @@ def lstm_state_encoder(rnn, x: torch.Tensor, hidden: torch.Tensor, masks: torch.
     N, H = hidden.shape[1], hidden.shape[2]
     T = x.shape[0] // N
     m = masks.view(T, N)
-    starts = [0] + ([t + 1 for t, v in enumerate((m[1:] == 0.0).any(dim=1).tolist()) if v] if T > 1 else [])
+    if starts is None:
+        starts = segment_starts(masks, N)
     xs = x.view(T, N, -1)
     weights = [rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0]   # cuDNN re-packs them per call (warning is benign)
     h, c = hidden[0:1], hidden[1:2]
@@ -86,7 +95,7 @@ def lstm_state_encoder(rnn, x: torch.Tensor, hidden: torch.Tensor, masks: torch.
     return y.reshape(T * N, H), torch.cat([h, c], 0)
 
 
-def hi_tail(mod, rgb_feat, depth_feat, bert, hidden, masks, p_drop: float = 0.25):
+def hi_tail(mod, rgb_feat, depth_feat, bert, hidden, masks, p_drop: float = 0.25, starts=None):
     """rgb_feat [B,16,2048], depth_feat [B,16,128], bert [1|B,L,768] (all constants, fp32);
     hidden [2,N,512]; masks [B,2] -> (logits [B,4], hidden [2,N,512])."""
     B = rgb_feat.shape[0]
@@ -103,11 +112,11 @@ def hi_tail(mod, rgb_feat, depth_feat, bert, hidden, masks, p_drop: float = 0.25
     ri = F.relu(F.linear(R.mean(dim=1), lin_r.weight, lin_r.bias))
     di = F.relu(F.linear(D.permute(0, 2, 1).reshape(B, -1), lin_d.weight, lin_d.bias))   # channel-major flatten
     x = torch.cat((ri, di, Ar.mean(dim=1), Ad.mean(dim=1)), dim=1)
-    y, hid = lstm_state_encoder(mod.state_encoder.rnn, x, hidden, masks[:, 0])
+    y, hid = lstm_state_encoder(mod.state_encoder.rnn, x, hidden, masks[:, 0], starts)
     return F.linear(y, mod.linear.weight, mod.linear.bias), hid
 
 
-def lo_tail(mod, rgb_gmean, depth_feat, hidden, masks, sub_goal):
+def lo_tail(mod, rgb_gmean, depth_feat, hidden, masks, sub_goal, starts=None):
     """rgb_gmean [B,2048], depth_feat [B,16,128] -> (actions [B,2], stop [B,1], hidden)."""
     B = rgb_gmean.shape[0]
     fc_d = mod.depth_encoder.visual_fc._modules["1"]
@@ -115,6 +124,6 @@ def lo_tail(mod, rgb_gmean, depth_feat, hidden, masks, sub_goal):
     re = F.relu(F.linear(rgb_gmean, mod.rgb_encoder.fc.weight, mod.rgb_encoder.fc.bias))
     se = F.embedding(sub_goal.long().view(-1), mod.sub_task_embedding.weight, padding_idx=4)
     x = torch.cat([de, re, se], dim=1)
-    y, hid = lstm_state_encoder(mod.state_encoder.rnn, x, hidden, masks[:, 0])
+    y, hid = lstm_state_encoder(mod.state_encoder.rnn, x, hidden, masks[:, 0], starts)
     return (F.linear(y, mod.linear.weight, mod.linear.bias),
             F.linear(y, mod.stop_linear.weight, mod.stop_linear.bias), hid)

@@ -122,3 +122,29 @@ def test_train_mode_forward_backward_on_gpu(cpu_case):
     with torch.no_grad():
         logits2, _ = hi((obs, inp["hidden_hi"].to(dev), None, inp["masks"].to(dev)))
     assert float((logits2 - logits.detach()).abs().max()) > 1e-3
+
+
+def test_segment_starts_and_precomputed_segments():
+    """trainer.DaggerUpdater computes the LSTM segment boundaries once on the host (they key its CUDA graphs) and hands
+    them to the tail: same boundaries as RNNStateEncoder.seq_forward (rnn_state_encoder.py:95-110), same results."""
+    from robovln_b200 import torch_tail, trainer
+
+    m = torch.ones(10)
+    m[0] = 0.0
+    m[4] = 0.0
+    m[9] = 0.0
+    assert torch_tail.segment_starts(m, 1) == [0, 4, 9]
+    assert torch_tail.segment_starts(torch.ones(6), 1) == [0]
+    m2 = torch.ones(8)          # T = 4, N = 2: a reset of either environment cuts the sequence
+    m2[5] = 0.0                 # t = 2, env 1
+    assert torch_tail.segment_starts(m2, 2) == [0, 2]
+    g = torch.Generator().manual_seed(3)
+    rnn = torch.nn.LSTM(6, 5)
+    x = torch.randn((10, 6), generator=g)
+    h = torch.randn((2, 1, 5), generator=g)
+    y0, h0 = torch_tail.lstm_state_encoder(rnn, x, h, m)
+    y1, h1 = torch_tail.lstm_state_encoder(rnn, x, h, m, starts=[0, 4, 9])
+    assert torch.equal(y0, y1) and torch.equal(h0, h1)
+    hh = (torch.ones(2, requires_grad=True) * 2, (torch.ones(1, requires_grad=True) * 3,))
+    out = trainer.repackage_hidden(hh)
+    assert not out[0].requires_grad and not out[1][0].requires_grad
