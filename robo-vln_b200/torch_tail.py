@@ -37,15 +37,26 @@ def sinusoid_table(L: int, d: int, device) -> torch.Tensor:
     return out
 
 
-def visual_ling_attn(m, ins: torch.Tensor, vis: torch.Tensor, p_drop: float, training: bool, h: int = 4):
-    """m = module.image_cm_encoder; ins [B,L,768], vis [B,16,256] -> [B,L,256]."""
-    B, L, _ = ins.shape
+def ins_projection(m, ins: torch.Tensor) -> torch.Tensor:
+    """relu(ins_fc(ins)) -- the part of the query side of Visual_Ling_Attn.forward (transformer.py:266-268) that draws no
+    random numbers.  hi_tail computes it ONCE on the un-expanded instruction rows ([1, L, 768] when the trajectory shares one
+    instruction) and for both modalities; every call then applies its own dropout mask and LayerNorm to the expanded rows,
+    exactly as the reference does on its B-times repeated copy (the weight gradient is the same sum, taken in two stages)."""
+    return F.relu(F.linear(ins, m.ins_fc.weight, m.ins_fc.bias))
+
+
+def visual_ling_attn(m, ins: torch.Tensor, vis: torch.Tensor, p_drop: float, training: bool, h: int = 4, q_lin=None):
+    """m = module.image_cm_encoder; ins [B,L,768] (or q_lin = ins_projection(...) [1|B,L,256]), vis [B,16,256] -> [B,L,256]."""
+    B = vis.shape[0]
+    L = (ins if q_lin is None else q_lin).shape[1]
     d = m.vis_fc.weight.shape[0]
     drop = lambda t: F.dropout(t, p_drop, training)  # noqa: E731
     ln0 = (m.layer_norm.weight, m.layer_norm.bias)
     V = F.layer_norm(drop(F.relu(F.linear(vis, m.vis_fc.weight, m.vis_fc.bias))), (d,), *ln0, 1e-5)
-    Q = F.layer_norm(drop(F.relu(F.linear(ins, m.ins_fc.weight, m.ins_fc.bias))), (d,), *ln0, 1e-5)
-    Q = Q + sinusoid_table(L, d, ins.device).unsqueeze(0)
+    if q_lin is None:
+        q_lin = ins_projection(m, ins)
+    Q = F.layer_norm(drop(q_lin.expand(B, -1, -1)), (d,), *ln0, 1e-5)
+    Q = Q + sinusoid_table(L, d, vis.device).unsqueeze(0)
     layer = m.layers._modules["0"]
     a = layer.enc_att.attention
     dk = d // h
@@ -104,9 +115,9 @@ def hi_tail(mod, rgb_feat, depth_feat, bert, hidden, masks, p_drop: float = 0.25
     D = torch.cat([depth_feat, _spatial(mod.depth_encoder.spatial_embeddings.weight).unsqueeze(0).expand(B, -1, -1)], 2)
     Kr = F.linear(R, mod.rgb_kv.weight[:, :, 0], mod.rgb_kv.bias)          # Conv1d(k=1) == per-cell linear
     Kd = F.linear(D, mod.depth_kv.weight[:, :, 0], mod.depth_kv.bias)
-    emb = bert.expand(B, -1, -1)
-    Ar = visual_ling_attn(mod.image_cm_encoder, emb, Kr, p_drop, training)
-    Ad = visual_ling_attn(mod.image_cm_encoder, emb, Kd, p_drop, training)
+    q_lin = ins_projection(mod.image_cm_encoder, bert)      # [1|B, L, 256], shared by the two calls
+    Ar = visual_ling_attn(mod.image_cm_encoder, None, Kr, p_drop, training, q_lin=q_lin)
+    Ad = visual_ling_attn(mod.image_cm_encoder, None, Kd, p_drop, training, q_lin=q_lin)
     lin_r = mod.rgb_linear._modules["2"]
     lin_d = mod.depth_linear._modules["1"]
     ri = F.relu(F.linear(R.mean(dim=1), lin_r.weight, lin_r.bias))
