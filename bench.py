@@ -339,7 +339,19 @@ def run_b200(args):
     gemm_fl = sum(o["flops"] for o in ops if o["flops"] > 0)
     n_gemm = sum(1 for o in ops if o["flops"] > 0)
     all_ms = sum(o["ms"] for o in ops)
-    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # Three ways to put the tcgen05 kernels' algorithmic FLOPs of one step against the measured sustained peak:
+    #  * in the step (the line's `achieved`): FLOPs of all tcgen05 launches of a step / the step's duration -- CUDA events
+    #    over the timed region of this line, the launches spread over three concurrent streams of one graph;
+    #  * serialised: the same launches replayed one by one on a single stream with an event after each (launch gaps
+    #    and the kernels' cold starts are inside those durations; since round 2 the persistent grids are deliberately
+    #    SMALLER than the GPU -- gemm_tc_make_plan: a kernel leaves SMs to the other two streams -- so a kernel timed
+    #    alone under-uses the GPU by construction);
+    #  * per occupied SM: the serialised durations weighted by the share of the SMs each launch occupies.
+    n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    serial = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    occ_ms = sum(o["ms"] * (min(o.get("ctas", 0) or n_sms, n_sms) / n_sms) for o in ops if o["flops"] > 0)
+    per_sm = gemm_fl / (occ_ms * 1e-3) / 1e12 if occ_ms > 0 else 0.0
+    achieved = gemm_fl / (ms_step * 1e-3) / 1e12
     traffic = None
     traffic_src = None
     for tp in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
@@ -354,12 +366,19 @@ def run_b200(args):
     roofline = {
         "bound": "tensor", "kernel": "tcgen05 kernels (gemm_tc_kernel implicit GEMM + fused cross-modal block), %d launches/step" % n_gemm,
         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+        "method": "algorithmic FLOPs of the step's tcgen05 launches / step duration (CUDA events over the timed region; the "
+                  "launches run on three concurrent streams of one graph, so per-launch durations are not observable in the step)",
         "peak_source": "%s, sustained bf16 (kernel timed inside the step)" % peaks["source"], "traffic": traffic,
         "traffic_note": "average DRAM bytes per tensor-core launch (ncu, profiles/%s); 'achieved' is FLOP/s "
                         "(tensor-bound kernel), average FLOPs per launch = flops_per_step / launches" % traffic_src,
-        "flops_per_step": gemm_fl, "ms_per_step_in_kernel": gemm_ms, "kernel_share_of_step": gemm_ms / all_ms if all_ms else None,
+        "flops_per_step": gemm_fl,
+        "serialised_single_stream": {"achieved": serial, "frac": serial / peaks["bf16_tflops"], "ms_in_kernels": gemm_ms,
+                                     "kernel_share_of_serialised_step": gemm_ms / all_ms if all_ms else None,
+                                     "serialised_step_ms": all_ms,
+                                     "note": "event after every launch of a one-stream replay; grids are sized for the concurrent step"},
+        "per_occupied_sm": {"achieved": per_sm, "frac": per_sm / peaks["bf16_tflops"],
+                            "note": "serialised durations x (CTAs of the launch / %d SMs): what the kernels reach on the SMs they hold" % n_sms},
         "step_frac_of_tensor_peak": value / world * GFLOP_PER_OBS * 1e9 / (peaks["bf16_tflops"] * 1e12),
-        "single_stream_step_ms": all_ms,
     }
     if args.profile_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)

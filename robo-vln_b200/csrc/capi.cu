@@ -159,8 +159,8 @@ int hcm_profile_policy(hcm_engine* e, const float* rgb, const float* depth, cons
     std::string js = "[";
     for (size_t i = 0; i < t.size(); ++i) {
       char buf[512];
-      snprintf(buf, sizeof(buf), "%s{\"name\":\"%s\",\"ms\":%.6f,\"flops\":%.1f}", i ? "," : "", t[i].name.c_str(),
-               t[i].ms, t[i].flops);
+      snprintf(buf, sizeof(buf), "%s{\"name\":\"%s\",\"ms\":%.6f,\"flops\":%.1f,\"ctas\":%d}", i ? "," : "", t[i].name.c_str(),
+               t[i].ms, t[i].flops, t[i].ctas);
       js += buf;
     }
     js += "]";

@@ -88,6 +88,7 @@ GemmTcPlan* Engine::add_gemm(Stage& st, const ConvGemm& g, int force_bn) {
   // algorithmic K (the window-mode stem multiplies 7 x 64 padded columns for 7 x 7 x 3 real taps)
   const double K = g.window ? 147.0 : static_cast<double>(g.KH) * g.KW * g.Cin;
   op.flops = 2.0 * static_cast<double>(g.M()) * g.Cout * K;
+  op.ctas = plan->grid;
   op.name = "gemm_tc<" + std::to_string(plan->BN) + "> M=" + std::to_string(g.M()) + " N=" + std::to_string(g.Cout) +
             " K=" + std::to_string(static_cast<long long>(K)) + (g.plain() ? " plain" : (" conv" + std::to_string(g.KH) +
             "x" + std::to_string(g.KW) + "s" + std::to_string(g.stride))) + " tiles=" +
@@ -568,6 +569,7 @@ void Engine::plan_cross_modal(Stage& stq, Stage& st, const h16* bert, const h16*
     // algorithmic FLOPs of what it replaces: attention (QK^T, PV), fc_o, fc1, fc2 for 2*B*L query rows
     op.flops = 2.0 * static_cast<double>(MX) * (2.0 * 16 * 256 + 256.0 * 256 + 2.0 * 1024 * 256);
     op.name = "vla_block<tcgen05> envs=" + std::to_string(B) + " L=" + std::to_string(L) + " tiles=" + std::to_string(2 * B);
+    op.ctas = std::min(2 * B, device_sm_count());
     st.push_back(std::move(op));
     if (&st == &st_hi_tail_) vla_tokens_ = keep_tokens ? Y : nullptr;   // in production the token-level output never leaves the SM
     return;
@@ -1107,7 +1109,7 @@ std::vector<OpTiming> Engine::profile_policy(cudaStream_t s) {
     for (const auto& op : st) {
       op(s);
       RVB_CUDA(cudaEventRecord(prof_events_[ei++], s));
-      out.push_back({op.name, 0.0, op.flops});
+      out.push_back({op.name, 0.0, op.flops, op.ctas});
     }
   };
   policy_sg_ = sg;

@@ -43,6 +43,7 @@ struct Op {
   std::function<int(cudaStream_t)> fn;
   std::string name;     // filled for the profile listing
   double flops = 0.0;   // algorithmic FLOPs (2*M*N*K) for tensor-core ops, 0 otherwise
+  int ctas = 0;         // persistent grid of a tensor-core op (CTAs = SMs it occupies), 0 when not recorded
   Op() = default;
   template <class F, class = typename std::enable_if<!std::is_same<typename std::decay<F>::type, Op>::value>::type>
   Op(F&& f) : fn(std::forward<F>(f)) {}
@@ -54,6 +55,7 @@ struct OpTiming {
   std::string name;
   double ms = 0.0;
   double flops = 0.0;
+  int ctas = 0;
 };
 
 class Engine {
