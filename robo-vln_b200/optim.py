@@ -87,6 +87,10 @@ class FusedAdam(torch.optim.Optimizer):
                                               group["lr"], b1, b2, group["eps"], group["weight_decay"], int(self.decoupled),
                                               step_size, bc2_sqrt, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                            "rvb_fused_adam", lib)
+            # the kernel wrote the parameters (and the moments) behind torch's back: bump their version counters so that
+            # everything keyed on (data_ptr, _version) -- the engine's packed-tail refresh (runtime._tail_sig_now), autograd's
+            # saved-tensor checks -- sees the update, exactly as after an in-place torch op
+            torch.autograd.graph.increment_version([t for quad in live for t in (quad[0], quad[2], quad[3])])
         return loss
 
 

@@ -114,3 +114,37 @@ def test_update_matches_reference_arithmetic(graph):
     if graph:
         assert not upd.graph_errors, upd.graph_errors
         assert sum(g is not None for g in upd._graphs.values()) == 2      # one graph per model, reused across the three calls
+
+
+def test_fused_optimizer_step_is_seen_by_the_inference_engine():
+    """FusedAdam writes the parameters through raw pointers; the engine re-packs its 16-bit tail copies when the
+    (data_ptr, _version) signature of the tail changes -- the optimizer must therefore bump the version counters.
+    Inference right after an update (no eval()/train() toggle, no notify call) has to run on the NEW weights."""
+    import robovln_b200 as R
+
+    pol = _policy(21)
+    opt_hi = R.optim.FusedAdamW([p for p in pol.high_level.parameters() if p.requires_grad], lr=5e-2, weight_decay=0.0)
+    opt_lo = R.optim.FusedAdam([p for p in pol.low_level.parameters() if p.requires_grad], lr=5e-2, weight_decay=0.0)
+    upd = R.trainer.DaggerUpdater(pol.high_level, pol.low_level, opt_hi, opt_lo, graph=True)
+    b = _batch(7)
+
+    def infer():
+        with torch.no_grad():
+            obs = {k: v for k, v in b["obs"].items() if k != "vln_oracle_action_sensor"}
+            return pol.high_level((obs, b["h_hi"], b["prev"], b["masks"]))[0].clone()
+
+    pol.high_level.eval()
+    before = infer()
+    pol.high_level.train()
+    v0 = pol.high_level.linear.weight._version
+    upd.update(dict(b["obs"]), b["prev"], b["masks"], b["corrected"], b["ostop"], b["h_hi"], b["h_lo"], None)
+    assert pol.high_level.linear.weight._version > v0
+    after_engine = infer()                       # train mode + no_grad -> engine inference path, packed tail weights
+    assert float((after_engine - before).abs().max()) > 1e-2, "the engine still runs the tail weights of before the update"
+    # and it agrees with the torch tail evaluated on the updated parameters (dropout off in _policy)
+    rt = pol.high_level.runtime()
+    feats = rt.encode(b["obs"]["rgb"], b["obs"]["depth"], b["obs"]["instruction"], n_envs=1)
+    from robovln_b200 import torch_tail
+    with torch.no_grad():
+        want = torch_tail.hi_tail(pol.high_level, feats["rgb_feat"], feats["depth_feat"], feats["bert"], b["h_hi"], b["masks"], 0.0)[0]
+    assert float((after_engine - want).abs().max()) < 2e-2
