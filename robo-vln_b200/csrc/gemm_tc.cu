@@ -1378,7 +1378,19 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
   // trades kernel latency for SM time: the step is bound by the SM time of its three concurrent streams, not by
   // the length of any one chain
   const long long slots = sms / best_ctas;
-  const long long rounds = (units + slots - 1) / slots + (ln ? 0 : g.extra_rounds);
+  long long rounds = (units + slots - 1) / slots;
+  if (!ln && g.extra_rounds > 0) {
+    // ROBOVLN_GRID_MIN = n keeps the plain grid where the extra round would leave fewer than n CTAs.  Measured: even
+    // the launches of a few dozen tiles are better off with the extra round (3.645 ms/step at 0, 3.663 at 24 and 48,
+    // 3.69 at 72, 3.73 at 100), so the default is 0
+    static int min_grid = -1;
+    if (min_grid < 0) {
+      const char* e = std::getenv("ROBOVLN_GRID_MIN");
+      min_grid = e != nullptr ? std::atoi(e) : 0;
+    }
+    const long long r2 = rounds + g.extra_rounds;
+    if ((units + r2 - 1) / r2 * best_ctas >= min_grid) rounds = r2;
+  }
   plan->grid = static_cast<int>((units + rounds - 1) / rounds) * best_ctas;
   if (ln) plan->grid = std::min(p.m_tiles, sms / p.n_tiles) * p.n_tiles;   // whole clusters / whole row blocks of n_tiles CTAs
   plan->valid = true;
