@@ -310,6 +310,12 @@ RVB_DEVICE uint32_t pack_h2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// max(x, 0) folded into the conversion (F2FP.RELU): one instruction for ReLU + round + pack
+RVB_DEVICE uint32_t pack_h2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 RVB_DEVICE float2 unpack_h2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
@@ -317,11 +323,20 @@ RVB_DEVICE float2 unpack_h2(uint32_t u) {
 RVB_DEVICE h16 to_h16(float x) { return __float2bfloat16_rn(x); }
 RVB_DEVICE float from_h16(h16 x) { return __bfloat162float(x); }
 #else
-// fp16: saturate to the largest finite value instead of overflowing to inf
+// fp16: saturate to the largest finite value instead of overflowing to inf -- cvt.satfinite does it inside the
+// conversion (F2FP.SATFINITE.F16.F32.PACK_AB: one instruction for clamp + round + pack; a min/max pair per element in
+// front of every 16-bit store was a third of the instructions of the GEMM's bias-only epilogue).  NaN stays NaN.
 RVB_DEVICE float sat_h(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }
 RVB_DEVICE uint32_t pack_h2(float lo, float hi) {
-  __half2 v = __floats2half2_rn(sat_h(lo), sat_h(hi));
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// max(x, 0) folded into the conversion as well (F2FP.SATFINITE.RELU)
+RVB_DEVICE uint32_t pack_h2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 RVB_DEVICE float2 unpack_h2(uint32_t u) {
   __half2 v = *reinterpret_cast<__half2*>(&u);

@@ -118,7 +118,8 @@ RVB_DEVICE void epilogue_math(float (&f)[32], const GemmTcParams& p, int n, cons
 // shared memory carved out the L1 holds nothing, so the per-thread bias loads of epilogue_math are L2 round trips on
 // the epilogue's critical path: measured (tools/gemm_timeline.py + ROBOVLN_EPI_DEBUG=2) 3.8k of the 7.7k epilogue cycles
 // of a 128 x 256 bias-only tile.  The lane-distributed copy is fetched once per tile BEFORE the accumulator is waited for.
-RVB_DEVICE void epilogue_math_b(float (&f)[32], const GemmTcParams& p, int n, const h16* res_row, float bias_lane) {
+RVB_DEVICE void epilogue_math_b(float (&f)[32], const GemmTcParams& p, int n, const h16* res_row, float bias_lane,
+                                bool relu_in_pack = false) {   // relu_in_pack: the caller's 16-bit pack applies the ReLU (F2FP.RELU)
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bias_lane, j);
   if (res_row != nullptr) {
@@ -135,8 +136,10 @@ RVB_DEVICE void epilogue_math_b(float (&f)[32], const GemmTcParams& p, int n, co
     }
   }
   if (p.act == ACT_RELU) {
+    if (!relu_in_pack) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
   } else if (p.act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
@@ -560,12 +563,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               t = unpack_h2(r4.z); f[4] += t.x; f[5] += t.y;
               t = unpack_h2(r4.w); f[6] += t.x; f[7] += t.y;
             }
-            if (p.act == ACT_RELU) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
-            }
             uint4 q;
-            q.x = pack_h2(f[0], f[1]); q.y = pack_h2(f[2], f[3]); q.z = pack_h2(f[4], f[5]); q.w = pack_h2(f[6], f[7]);
+            if (p.act == ACT_RELU) {
+              q.x = pack_h2_relu(f[0], f[1]); q.y = pack_h2_relu(f[2], f[3]); q.z = pack_h2_relu(f[4], f[5]); q.w = pack_h2_relu(f[6], f[7]);
+            } else {
+              q.x = pack_h2(f[0], f[1]); q.y = pack_h2(f[2], f[3]); q.z = pack_h2(f[4], f[5]); q.w = pack_h2(f[6], f[7]);
+            }
             *reinterpret_cast<uint4*>(my_row + ((j8 ^ sw) << 4)) = q;
           }
           fence_proxy_async();
@@ -839,16 +842,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int s_ = 0; s_ < BSLOTS; ++s_)
                   if (s_ == (ch - group) + half) bsel = bl[s_];      // slot 2 * ((ch - group) / 2) + half
-                epilogue_math_b(f, p, n + half * 32, p.res_tma ? nullptr : res_row, bsel);
+                epilogue_math_b(f, p, n + half * 32, p.res_tma ? nullptr : res_row, bsel, true);
               }
+              if (p.act == ACT_RELU) {   // ReLU, saturation, rounding and packing in one F2FP per pair
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 q;
-                q.x = pack_h2(f[8 * j], f[8 * j + 1]);
-                q.y = pack_h2(f[8 * j + 2], f[8 * j + 3]);
-                q.z = pack_h2(f[8 * j + 4], f[8 * j + 5]);
-                q.w = pack_h2(f[8 * j + 6], f[8 * j + 7]);
-                *reinterpret_cast<uint4*>(my_row + (((half * 4 + j) ^ sw) << 4)) = q;
+                for (int j = 0; j < 4; ++j) {
+                  uint4 q;
+                  q.x = pack_h2_relu(f[8 * j], f[8 * j + 1]);
+                  q.y = pack_h2_relu(f[8 * j + 2], f[8 * j + 3]);
+                  q.z = pack_h2_relu(f[8 * j + 4], f[8 * j + 5]);
+                  q.w = pack_h2_relu(f[8 * j + 6], f[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(my_row + (((half * 4 + j) ^ sw) << 4)) = q;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 q;
+                  q.x = pack_h2(f[8 * j], f[8 * j + 1]);
+                  q.y = pack_h2(f[8 * j + 2], f[8 * j + 3]);
+                  q.z = pack_h2(f[8 * j + 4], f[8 * j + 5]);
+                  q.w = pack_h2(f[8 * j + 6], f[8 * j + 7]);
+                  *reinterpret_cast<uint4*>(my_row + (((half * 4 + j) ^ sw) << 4)) = q;
+                }
               }
             }
           }

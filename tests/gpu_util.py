@@ -32,7 +32,7 @@ def dtype_name(t: torch.Tensor) -> str:
 
 
 def conv_gemm(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_rows=0, act=0, out_f32=False,
-              force_bn=0, impl=0, ldc=None, out=None):
+              force_bn=0, impl=0, ldc=None, out=None, sync=True):
     """x: [NB,H,W,Cin] h16 (contiguous), w: [Cout, KH*KW*Cin] h16 -> out [M, Cout]."""
     dt = dtype_name(x)
     NB, H, W, Cin = x.shape
@@ -48,7 +48,8 @@ def conv_gemm(x, w, *, KH=1, KW=1, stride=1, pad=0, bias=None, res=None, res_row
                                0 if res is None else res.shape[-1], res_rows, act, P(out), ldc, int(out_f32), force_bn,
                                impl, 0, 0, stream())
     check(rc, "rvb_conv_gemm", dt)
-    torch.cuda.synchronize()
+    if sync:
+        torch.cuda.synchronize()
     return out
 
 
