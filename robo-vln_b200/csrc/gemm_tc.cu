@@ -252,50 +252,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             img = mt * p.nb;
           }
         }
-        // k-block rotation: tiles that share an operand (same mu -> same A rows, same nt -> same weights) start
-        // their K walk at different blocks, so that concurrently running CTAs do not ask L2 for the same lines at
-        // the same moment.  The sum over k blocks is order independent (fp32 accumulation; the order is a function
-        // of the tile index, hence deterministic).
-        const int krot = p.krot ? (mu * 5 + nt * 3) % p.num_kb : 0;
-        for (int kseq = 0; kseq < p.num_kb; ++kseq) {
-          int kb = kseq + krot;
-          if (kb >= p.num_kb) kb -= p.num_kb;
+        // The K walk (filter tap (r, s) x 64-channel block) is kept in running counters: this loop is ONE thread, every
+        // instruction of it is issued at dependent-chain latency, and the two integer divisions per k block it used to
+        // do (kb / cblocks, tap / KW) made a k block cost ~640 cycles to issue -- more than its 128 MMA cycles at
+        // BN = 64, so the narrow convs of the trunk fronts were bound by their own producer.
+        int tap = 0, cb = 0, r = 0, sx = 0, tapcol = 0;
+        const int hbase = h0 * p.stride - p.pad;
+        const int ncol = nt * BN + ((CTAS == 2) ? static_cast<int>(cta_rank) * (BN / 2) : 0);
+        const int mrow = mt * BLOCK_M;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
+          const int ccol = cb * BLOCK_K;
           if (CTAS == 2) {
             // both CTAs' bytes are credited to the LEADER's full barrier, which the leader arms
             const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_bytes + C::B_STAGE_BYTES));
-            if (p.plain) {
-              tma_load_4d_2sm(sa, &tmA, full_leader, cb * BLOCK_K, mt * BLOCK_M, 0, 0);
-            } else {
-              const int r = tap / p.KW;
-              const int s = tap - r * p.KW;
-              tma_load_4d_2sm(sa, &tmA, full_leader, cb * BLOCK_K, s - p.pad, h0 * p.stride + r - p.pad, img);
-            }
-            tma_load_2d_2sm(sb, &tmB, full_leader, tap * p.Cin + cb * BLOCK_K,
-                            nt * BN + static_cast<int>(cta_rank) * (BN / 2));
-            if (++stage == nstages) {
-              stage = 0;
-              phase ^= 1;
-            }
-            continue;
-          }
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + (p.b_res ? 0u : static_cast<uint32_t>(C::B_STAGE_BYTES)));
-          if (p.plain) {
-            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, mt * BLOCK_M, 0, 0);
-          } else if (p.window2) {
-            tma_load_4d(sa, &tmA, &full_bar[stage], 0, 0, h0 + tap, img);   // row pair h0 + tap = filter rows 2 tap, 2 tap + 1
+            if (p.plain) tma_load_4d_2sm(sa, &tmA, full_leader, ccol, mrow, 0, 0);
+            else tma_load_4d_2sm(sa, &tmA, full_leader, ccol, sx - p.pad, hbase + r, img);
+            tma_load_2d_2sm(sb, &tmB, full_leader, tapcol + ccol, ncol);
           } else {
-            const int r = tap / p.KW;
-            const int s = tap - r * p.KW;
-            tma_load_4d(sa, &tmA, &full_bar[stage], cb * BLOCK_K, s - p.pad, h0 * p.stride + r - p.pad, img);
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + (p.b_res ? 0u : static_cast<uint32_t>(C::B_STAGE_BYTES)));
+            if (p.plain) tma_load_4d(sa, &tmA, &full_bar[stage], ccol, mrow, 0, 0);
+            else if (p.window2) tma_load_4d(sa, &tmA, &full_bar[stage], 0, 0, h0 + tap, img);   // row pair h0 + tap = filter rows 2 tap, 2 tap + 1
+            else tma_load_4d(sa, &tmA, &full_bar[stage], ccol, sx - p.pad, hbase + r, img);
+            if (!p.b_res) tma_load_2d(sb, &tmB, &full_bar[stage], tapcol + ccol, ncol);
           }
-          if (!p.b_res) tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + cb * BLOCK_K, nt * BN);
-          if (tile == unit && kseq == 0) GT_STAMP(2);
+          if (tile == unit && kb == 0) GT_STAMP(2);
+          if (++cb == p.cblocks) {      // next filter tap
+            cb = 0;
+            ++tap;
+            tapcol += p.Cin;
+            if (++sx == p.KW) {
+              sx = 0;
+              ++r;
+            }
+          }
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -1210,12 +1203,6 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
       dbg = e ? std::atoi(e) : 0;
     }
     p.dbg = dbg;
-    static int krot = -1;
-    if (krot < 0) {
-      const char* e = std::getenv("ROBOVLN_GEMM_KROT");
-      krot = (e != nullptr) ? std::atoi(e) : 0;
-    }
-    p.krot = (krot != 0 && g.window == 0) ? 1 : 0;
   }
 
   const uint32_t ones[4] = {1, 1, 1, 1};
@@ -1370,10 +1357,7 @@ void gemm_tc_make_plan(const ConvGemm& g, GemmTcPlan* plan, int force_bn) {
     const int a_stages_left = (SMEM_STAGE_BUDGET - b_total) / A_STAGE_BYTES;
     p.b_res = (bres_env && best_ctas == 1 && p.n_tiles == 1 && !p.res_tma && !ln && !gn && p.m_tiles > 1 && b_total <= SMEM_STAGE_BUDGET &&
                a_stages_left >= 3) ? 1 : 0;
-    if (p.b_res) {
-      p.nstages = std::min(max_stages, a_stages_left);   // the barrier arrays hold Cfg::STAGES = max_stages entries
-      p.krot = 0;   // the MMA issuer indexes the resident blocks by k block: the producer must walk them in order
-    }
+    if (p.b_res) p.nstages = std::min(max_stages, a_stages_left);   // the barrier arrays hold Cfg::STAGES = max_stages entries
     RVB_CHECK(p.nstages >= 2, "gemm: too few pipeline stages");
   }
   if (p.res_tma) {

@@ -176,7 +176,6 @@ struct GemmTcParams {
   int ln_xchg;       // 1: statistics exchanged through global memory (ln_ws / ln_cnt), independent CTAs
   void* ln_ws;
   int* ln_cnt;
-  int krot;          // 1: per-tile rotation of the k-block walk (L2 hot-spot avoidance)
   int nstages;       // pipeline stages in use (fewer when the residual slices take their place)
   int b_res;         // 1: single N tile whose weights stay in shared memory for the whole launch (the ring carries A only)
   long long* times;  // diagnostics (ROBOVLN_GEMM_TIMES): [CTA][16] SM-clock stamps of the first tile's phases; null in production
