@@ -240,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       for (int tile = unit; tile < total_tiles; tile += num_units) {
-        const int mu = tile / p.n_tiles;
+        const int mu = (p.n_tiles == 1) ? tile : tile / p.n_tiles;   // no division on the single-N-tile launches (one k block per tile there)
         const int nt = tile - mu * p.n_tiles;
         const int mt = mu * CTAS + static_cast<int>(cta_rank);   // may be one past the end for the peer: OOB -> zeros
         int img = 0, h0 = 0;
@@ -305,6 +305,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // descriptors of slot 0; a slot's descriptor is that plus its byte offset >> 4 (the address field holds 14 bits)
+      const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem_a));
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_b));
       if (CTAS == 1 && p.b_res && unit < total_tiles) mbar_wait(&rbar_base[0], 0);   // resident weights have landed
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -314,8 +317,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (tile == unit && kb == 0) GT_STAMP(4);
-          const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (p.b_res ? kb : stage) * C::B_STAGE_BYTES));
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (A_STAGE_BYTES >> 4));
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((p.b_res ? kb : stage) * (C::B_STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 elements = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
@@ -383,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int gn_par = 0;
     if (p.res_tma && lane == 0 && chunk_exists(unit, group)) issue_res(unit, group);
     for (int tile = unit; tile < total_tiles; tile += num_units) {
-      const int mu = tile / p.n_tiles;
+      const int mu = (p.n_tiles == 1) ? tile : tile / p.n_tiles;
       const int nt = tile - mu * p.n_tiles;
       const int mt = mu * CTAS + static_cast<int>(cta_rank);
       const long long m = static_cast<long long>(mt) * p.tile_rows + row_in_tile;
