@@ -187,7 +187,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // stages hold eight 4 KiB residual slices (32 rows x 128 B, one per epilogue warp)
   uint8_t* res_slices = smem_b + nstages * C::B_STAGE_BYTES;
 
-  const int warp = threadIdx.x >> 5;
+  // the warp index through a shuffle: provably warp-uniform for the compiler, so that the role branches below are
+  // uniform branches and the single-lane TMA / MMA issue loops can keep their operands in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -228,15 +230,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // The whole warp walks the loop (convergent code: coordinates live in uniform registers); lane 0 issues.  With the
+    // loop inside `if (lane == 0)` every TMA instruction was wrapped in an elect / R2UR.BROADCAST waterfall and a k block
+    // took ~480 cycles to issue.
+    {
+      const bool issuer = (lane == 0);
       int stage = 0;
       uint32_t phase = 0;
       if (CTAS == 1 && p.b_res && unit < total_tiles) {   // the whole weight matrix of this (single) N tile, once
-        mbar_arrive_expect_tx(&rbar_base[0], static_cast<uint32_t>(p.num_kb) * C::B_STAGE_BYTES);
+        if (issuer) mbar_arrive_expect_tx(&rbar_base[0], static_cast<uint32_t>(p.num_kb) * C::B_STAGE_BYTES);
+        int tapc = 0, cbr = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          tma_load_2d(smem_b + kb * C::B_STAGE_BYTES, &tmB, &rbar_base[0], tap * p.Cin + cb * BLOCK_K, 0);
+          if (issuer) tma_load_2d(smem_b + kb * C::B_STAGE_BYTES, &tmB, &rbar_base[0], tapc + cbr * BLOCK_K, 0);
+          if (++cbr == p.cblocks) {
+            cbr = 0;
+            tapc += p.Cin;
+          }
         }
       }
       for (int tile = unit; tile < total_tiles; tile += num_units) {
@@ -268,18 +277,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (CTAS == 2) {
             // both CTAs' bytes are credited to the LEADER's full barrier, which the leader arms
             const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_bytes + C::B_STAGE_BYTES));
-            if (p.plain) tma_load_4d_2sm(sa, &tmA, full_leader, ccol, mrow, 0, 0);
-            else tma_load_4d_2sm(sa, &tmA, full_leader, ccol, sx - p.pad, hbase + r, img);
-            tma_load_2d_2sm(sb, &tmB, full_leader, tapcol + ccol, ncol);
-          } else {
+            if (issuer) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (p.a_bytes + C::B_STAGE_BYTES));
+              if (p.plain) tma_load_4d_2sm(sa, &tmA, full_leader, ccol, mrow, 0, 0);
+              else tma_load_4d_2sm(sa, &tmA, full_leader, ccol, sx - p.pad, hbase + r, img);
+              tma_load_2d_2sm(sb, &tmB, full_leader, tapcol + ccol, ncol);
+            }
+          } else if (issuer) {
             mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + (p.b_res ? 0u : static_cast<uint32_t>(C::B_STAGE_BYTES)));
             if (p.plain) tma_load_4d(sa, &tmA, &full_bar[stage], ccol, mrow, 0, 0);
             else if (p.window2) tma_load_4d(sa, &tmA, &full_bar[stage], 0, 0, h0 + tap, img);   // row pair h0 + tap = filter rows 2 tap, 2 tap + 1
             else tma_load_4d(sa, &tmA, &full_bar[stage], ccol, sx - p.pad, hbase + r, img);
             if (!p.b_res) tma_load_2d(sb, &tmB, &full_bar[stage], tapcol + ccol, ncol);
           }
-          if (tile == unit && kb == 0) GT_STAMP(2);
+          if (issuer && tile == unit && kb == 0) GT_STAMP(2);
           if (++cb == p.cblocks) {      // next filter tap
             cb = 0;
             ++tap;
@@ -294,12 +305,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             phase ^= 1;
           }
         }
-        if (tile == unit) GT_STAMP(3);
+        if (issuer && tile == unit) GT_STAMP(3);
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0 && cta_rank == 0) {   // in a pair only the leader issues MMAs
+    if (cta_rank == 0) {   // in a pair only the leader issues MMAs; the warp walks the loop convergently, lane 0 issues
+      const bool issuer = (lane == 0);
       constexpr uint32_t idesc = umma_idesc_h16(BLOCK_M * CTAS, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -316,31 +328,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (tile == unit && kb == 0) GT_STAMP(4);
+          if (issuer && tile == unit && kb == 0) GT_STAMP(4);
           const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (A_STAGE_BYTES >> 4));
           const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((p.b_res ? kb : stage) * (C::B_STAGE_BYTES >> 4));
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 elements = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
-            if (CTAS == 2)
-              umma_f16kind_2sm(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                               static_cast<uint32_t>((kb | k) != 0));
-            else
-              umma_f16kind(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                           static_cast<uint32_t>((kb | k) != 0));
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advance 16 elements = 32 B along K inside the 128B swizzle atom: +2 in the >>4 address field
+              if (CTAS == 2)
+                umma_f16kind_2sm(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                 static_cast<uint32_t>((kb | k) != 0));
+              else
+                umma_f16kind(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                             static_cast<uint32_t>((kb | k) != 0));
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+            if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
           }
-          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator complete -> epilogue warps (of both CTAs)
-        if (CTAS == 2) umma_commit_2sm(&tfull_bar[acc]);
-        else umma_commit(&tfull_bar[acc]);
-        if (tile == unit) GT_STAMP(5);
+        if (issuer) {
+          if (CTAS == 2) umma_commit_2sm(&tfull_bar[acc]);
+          else umma_commit(&tfull_bar[acc]);
+        }
+        if (issuer && tile == unit) GT_STAMP(5);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
