@@ -236,7 +236,8 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
   float2* s_ln = reinterpret_cast<float2*>(smem + VB_OFF_MISC + 512);       // [2][128]
   float* s_par = reinterpret_cast<float*>(smem + VB_OFF_PAR);               // bo | ln1g | ln1b | b2 | ln2g | ln2b | b1
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform: the role branches are uniform branches
+  const int lane = threadIdx.x & 31;
   const int env = blockIdx.x, mod = blockIdx.y;
   const int cell_row0 = (mod * p.B + env) * 16;          // first of this tile's 16 visual-cell rows in kvx
   const int q_row0 = p.q_shared ? 0 : env * p.L;
@@ -268,27 +269,28 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    {   // the whole warp walks this block convergently (operands in uniform registers); lane 0 issues
+      const bool issuer = (lane == 0);
       // resident operands: Q0 tile (4 K blocks) and the 4 per-head V tiles
-      mbar_arrive_expect_tx(&one[0], 4 * VB_SUB + 4 * 2048);
-      for (int kb = 0; kb < 4; ++kb) tma_load_2d(bufA + kb * VB_SUB, &tmQ0, &one[0], kb * 64, q_row0);
-      for (int h = 0; h < 4; ++h) tma_load_2d(sV + h * 2048, &tmV, &one[0], 1032 + h * 64, cell_row0);
+      if (issuer) mbar_arrive_expect_tx(&one[0], 4 * VB_SUB + 4 * 2048);
+      for (int kb = 0; kb < 4; ++kb) if (issuer) tma_load_2d(bufA + kb * VB_SUB, &tmQ0, &one[0], kb * 64, q_row0);
+      for (int h = 0; h < 4; ++h) if (issuer) tma_load_2d(sV + h * 2048, &tmV, &one[0], 1032 + h * 64, cell_row0);
       int slot = 0;
       uint32_t phase = 0;
       auto next = [&]() { if (++slot == VB_NS) { slot = 0; phase ^= 1; } };
       // S: K' blocks [64 (key, head) rows x 64 k]
       for (int kb = 0; kb < 4; ++kb) {
         mbar_wait(&empty_bar[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[slot], 8192);
-        tma_load_3d(ring + slot * VB_SLOT, &tmKp, &full_bar[slot], kb * 64, 0, cell_row0);
+        if (issuer) mbar_arrive_expect_tx(&full_bar[slot], 8192);
+        if (issuer) tma_load_3d(ring + slot * VB_SLOT, &tmKp, &full_bar[slot], kb * 64, 0, cell_row0);
         next();
       }
       // fc_o: Wo [256 x 256] as (k block, n half) units of [128 x 64]
       for (int kb = 0; kb < 4; ++kb)
         for (int nh = 0; nh < 2; ++nh) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[slot], VB_SLOT);
-          tma_load_2d(ring + slot * VB_SLOT, &tmWo, &full_bar[slot], ((kb + rk) & 3) * 64, ((nh + rc) & 1) * 128);
+          if (issuer) mbar_arrive_expect_tx(&full_bar[slot], VB_SLOT);
+          if (issuer) tma_load_2d(ring + slot * VB_SLOT, &tmWo, &full_bar[slot], ((kb + rk) & 3) * 64, ((nh + rc) & 1) * 128);
           next();
         }
       // FFN in MMA issue order
@@ -297,18 +299,21 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
         ffn_step(step, is_fc2, c);
         for (int u = 0; u < 4; ++u) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[slot], VB_SLOT);
+          if (issuer) mbar_arrive_expect_tx(&full_bar[slot], VB_SLOT);
           const int cc = (c + rc) & 7;       // the hidden chunk this CTA processes at sequence position c
-          if (!is_fc2) tma_load_2d(ring + slot * VB_SLOT, &tmW1, &full_bar[slot], ((u + rk) & 3) * 64, cc * 128);    // W1[cc*128.., k block]
-          else tma_load_2d(ring + slot * VB_SLOT, &tmW2, &full_bar[slot], cc * 128 + (((u >> 1) + rk) & 1) * 64,
-                           (((u & 1) + (rk >> 1)) & 1) * 128);                                                        // W2[n half, k = cc*128 + kb2*64]
+          if (issuer) {
+            if (!is_fc2) tma_load_2d(ring + slot * VB_SLOT, &tmW1, &full_bar[slot], ((u + rk) & 3) * 64, cc * 128);    // W1[cc*128.., k block]
+            else tma_load_2d(ring + slot * VB_SLOT, &tmW2, &full_bar[slot], cc * 128 + (((u >> 1) + rk) & 1) * 64,
+                             (((u & 1) + (rk >> 1)) & 1) * 128);                                                        // W2[n half, k = cc*128 + kb2*64]
+          }
           next();
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {   // the whole warp walks this block convergently (operands in uniform registers); lane 0 issues
+      const bool issuer = (lane == 0);
       int slot = 0;
       uint32_t phase = 0;
       auto next = [&]() { if (++slot == VB_NS) { slot = 0; phase ^= 1; } };
@@ -320,47 +325,47 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
         const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + slot * VB_SLOT));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16kind(tmem_base + d_col, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+          if (issuer) umma_f16kind(tmem_base + d_col, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
                        static_cast<uint32_t>(!(first && k == 0)));
-        umma_commit(&empty_bar[slot]);
+        if (issuer) umma_commit(&empty_bar[slot]);
         next();
       };
       constexpr uint32_t idesc64 = umma_idesc_h16(128, 64);
       constexpr uint32_t idesc128 = umma_idesc_h16(128, 128);
-      VB_STAMP(0);
+      if (issuer) VB_STAMP(0);
       mbar_wait(&one[0], 0);
       tc_fence_after();
-      VB_STAMP(1);
+      if (issuer) VB_STAMP(1);
       // ---- S[128, 64] = Q0 . K'^T
       for (int kb = 0; kb < 4; ++kb) unit(bufA + kb * VB_SUB, TM_H, idesc64, kb == 0);
-      umma_commit(&one[1]);
-      VB_STAMP(2);
+      if (issuer) umma_commit(&one[1]);
+      if (issuer) VB_STAMP(2);
       // ---- O_h[128, 64] = P_h . V_h   (V MN-major: [key, dim] rows of 128 B)
       mbar_wait(&one[2], 0);
       tc_fence_after();
-      VB_STAMP(3);
+      if (issuer) VB_STAMP(3);
       {
         constexpr uint32_t idesc_mn = umma_idesc_h16(128, 64) | (1u << 16);
         const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
         for (int h = 0; h < 4; ++h)
-          umma_f16kind(tmem_base + TM_Y + h * 64, pdesc + static_cast<uint64_t>(h * 2), umma_desc_sw128(smem_u32(sV + h * 2048)),
+          if (issuer) umma_f16kind(tmem_base + TM_Y + h * 64, pdesc + static_cast<uint64_t>(h * 2), umma_desc_sw128(smem_u32(sV + h * 2048)),
                        idesc_mn, 0u);
-        umma_commit(&one[3]);
+        if (issuer) umma_commit(&one[3]);
       }
       // ---- fc_o: A[128, 256] = ctx . Wo^T
       mbar_wait(&one[4], 0);
       tc_fence_after();
-      VB_STAMP(4);
+      if (issuer) VB_STAMP(4);
       for (int kb = 0; kb < 4; ++kb)
         for (int nh = 0; nh < 2; ++nh) unit(bufB + ((kb + rk) & 3) * VB_SUB, TM_H + ((nh + rc) & 1) * 128, idesc128, kb == 0);
-      umma_commit(&one[5]);
-      VB_STAMP(5);
+      if (issuer) umma_commit(&one[5]);
+      if (issuer) VB_STAMP(5);
       // ---- FFN
       mbar_wait(&one[6], 0);
       tc_fence_after();
-      VB_STAMP(6);
+      if (issuer) VB_STAMP(6);
       for (int step = 0; step < 16; ++step) {
-        VB_STAMP(8 + step);
+        if (issuer) VB_STAMP(8 + step);
         int is_fc2, c;
         ffn_step(step, is_fc2, c);
         const int b = c & 1;
@@ -370,18 +375,18 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
             tc_fence_after();
           }
           for (int kb = 0; kb < 4; ++kb) unit(bufB + ((kb + rk) & 3) * VB_SUB, TM_H + b * 128, idesc128, kb == 0);
-          umma_commit(&hfull[b]);
+          if (issuer) umma_commit(&hfull[b]);
         } else {
           mbar_wait(&sfull[b], static_cast<uint32_t>((c >> 1) & 1));
           tc_fence_after();
           for (int u = 0; u < 4; ++u)
             unit(bufA + b * 2 * VB_SUB + (((u >> 1) + rk) & 1) * VB_SUB, TM_Y + (((u & 1) + (rk >> 1)) & 1) * 128, idesc128,
                  c == 0 && (u >> 1) == 0);
-          umma_commit(&sempty[b]);
+          if (issuer) umma_commit(&sempty[b]);
         }
       }
-      umma_commit(&one[7]);
-      VB_STAMP(7);
+      if (issuer) umma_commit(&one[7]);
+      if (issuer) VB_STAMP(7);
     }
   } else {
     // =============================== epilogue (warps 2..9) ===============================
@@ -617,7 +622,8 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
   float2* s_ln = reinterpret_cast<float2*>(smem + VB_OFF_MISC + 512);
   float* s_par = reinterpret_cast<float*>(smem + VB_OFF_PAR);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform: the role branches are uniform branches
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();               // 0 = RGB tile (leader), 1 = depth tile
   const int env = static_cast<int>(blockIdx.x >> 1), mod = static_cast<int>(rank);
   const int cell_row0 = (mod * p.B + env) * 16;
@@ -644,10 +650,11 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
 
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ===============================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(in_bar, 4 * VB_SUB + 4 * 2048);
-      for (int kb = 0; kb < 4; ++kb) tma_load_2d(bufA + kb * VB_SUB, &tmQ0, in_bar, kb * 64, q_row0);
-      for (int h = 0; h < 4; ++h) tma_load_2d(sV + h * 2048, &tmV, in_bar, 1032 + h * 64, cell_row0);
+    {   // the whole warp walks this block convergently (operands in uniform registers); lane 0 issues
+      const bool issuer = (lane == 0);
+      if (issuer) mbar_arrive_expect_tx(in_bar, 4 * VB_SUB + 4 * 2048);
+      for (int kb = 0; kb < 4; ++kb) if (issuer) tma_load_2d(bufA + kb * VB_SUB, &tmQ0, in_bar, kb * 64, q_row0);
+      for (int h = 0; h < 4; ++h) if (issuer) tma_load_2d(sV + h * 2048, &tmV, in_bar, 1032 + h * 64, cell_row0);
       int slot = 0;
       uint32_t phase = 0;
       auto next = [&]() { if (++slot == VP_NS) { slot = 0; phase ^= 1; } };
@@ -655,17 +662,17 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
       // halves are credited to the leader's full barrier, which the leader arms
       auto begin_unit = [&](uint32_t bytes_per_cta) -> uint32_t {
         mbar_wait(&empty_bar[slot], phase ^ 1);
-        if (rank == 0) mbar_arrive_expect_tx(&full_bar[slot], 2 * bytes_per_cta);
+        if (rank == 0) if (issuer) mbar_arrive_expect_tx(&full_bar[slot], 2 * bytes_per_cta);
         return leader_addr(&full_bar[slot]);
       };
       for (int kb = 0; kb < 4; ++kb) {                      // S: this tile's K' block [64 (key, head) x 64 k]
         const uint32_t fb = begin_unit(8192);
-        tma_load_3d_2sm(ring + slot * VB_SLOT, &tmKp, fb, kb * 64, 0, cell_row0);
+        if (issuer) tma_load_3d_2sm(ring + slot * VB_SLOT, &tmKp, fb, kb * 64, 0, cell_row0);
         next();
       }
       for (int kb = 0; kb < 4; ++kb) {                      // fc_o: Wo rows [rank*128, +128), k block kb
         const uint32_t fb = begin_unit(VB_SLOT);
-        tma_load_2d_2sm(ring + slot * VB_SLOT, &tmWo, fb, kb * 64, static_cast<int>(rank) * 128);
+        if (issuer) tma_load_2d_2sm(ring + slot * VB_SLOT, &tmWo, fb, kb * 64, static_cast<int>(rank) * 128);
         next();
       }
       for (int step = 0; step < 8; ++step) {                // FFN in MMA issue order: fc1(0), {fc1(c+1), fc2(c)}, fc2(3)
@@ -673,17 +680,20 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
         const int c = (step == 0) ? 0 : (step == 7 ? 3 : ((step & 1) ? (step + 1) >> 1 : (step >> 1) - 1));
         for (int kb = 0; kb < 4; ++kb) {
           const uint32_t fb = begin_unit(VB_SLOT);
-          if (!is_fc2) tma_load_2d_2sm(ring + slot * VB_SLOT, &tmW1, fb, kb * 64, c * 256 + static_cast<int>(rank) * 128);
-          else tma_load_2d_2sm(ring + slot * VB_SLOT, &tmW2, fb, c * 256 + kb * 64, static_cast<int>(rank) * 128);
+          if (issuer) {
+            if (!is_fc2) tma_load_2d_2sm(ring + slot * VB_SLOT, &tmW1, fb, kb * 64, c * 256 + static_cast<int>(rank) * 128);
+            else tma_load_2d_2sm(ring + slot * VB_SLOT, &tmW2, fb, c * 256 + kb * 64, static_cast<int>(rank) * 128);
+          }
           next();
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader) ===============================
-    if (lane == 0) {
+    {   // the whole warp walks this block convergently (operands in uniform registers); lane 0 issues
+      const bool issuer = (lane == 0);
       mbar_wait(in_bar, 0);                                  // this CTA's Q0 / V have landed
-      mbar_arrive_cluster(leader_addr(in_both));
+      if (issuer) mbar_arrive_cluster(leader_addr(in_both));
       if (rank == 0) {
         int slot = 0;
         uint32_t phase = 0;
@@ -695,42 +705,42 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
           const uint64_t bdesc = umma_desc_sw128(smem_u32(ring + slot * VB_SLOT));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16kind_2sm(tmem_base + d_col, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+            if (issuer) umma_f16kind_2sm(tmem_base + d_col, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
                              static_cast<uint32_t>(!(first && k == 0)));
-          umma_commit_2sm(&empty_bar[slot]);
+          if (issuer) umma_commit_2sm(&empty_bar[slot]);
           next();
         };
         constexpr uint32_t idesc_s = umma_idesc_h16(256, 128);
         constexpr uint32_t idesc_w = umma_idesc_h16(256, 256);
-        VB_STAMP(0);
+        if (issuer) VB_STAMP(0);
         mbar_wait(in_both, 0);
         tc_fence_after();
-        VB_STAMP(1);
+        if (issuer) VB_STAMP(1);
         for (int kb = 0; kb < 4; ++kb) unit(bufA + kb * VB_SUB, 0, idesc_s, kb == 0);          // S -> columns [0, 128)
-        umma_commit_2sm(s_done);
-        VB_STAMP(2);
+        if (issuer) umma_commit_2sm(s_done);
+        if (issuer) VB_STAMP(2);
         mbar_wait(p_ready, 0);
         tc_fence_after();
-        VB_STAMP(3);
+        if (issuer) VB_STAMP(3);
         {
           constexpr uint32_t idesc_mn = umma_idesc_h16(256, 128) | (1u << 16);
           const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
           for (int h = 0; h < 4; ++h)                                                            // O_h -> columns [h*128, +128)
-            umma_f16kind_2sm(tmem_base + h * 128, pdesc + static_cast<uint64_t>(h * 2), umma_desc_sw128(smem_u32(sV + h * 2048)),
+            if (issuer) umma_f16kind_2sm(tmem_base + h * 128, pdesc + static_cast<uint64_t>(h * 2), umma_desc_sw128(smem_u32(sV + h * 2048)),
                              idesc_mn, 0u);
-          umma_commit_2sm(o_done);
+          if (issuer) umma_commit_2sm(o_done);
         }
         mbar_wait(ctx_ready, 0);
         tc_fence_after();
-        VB_STAMP(4);
+        if (issuer) VB_STAMP(4);
         for (int kb = 0; kb < 4; ++kb) unit(bufB + kb * VB_SUB, TM_H, idesc_w, kb == 0);        // fc_o -> columns [256, 512)
-        umma_commit_2sm(fco_done);
-        VB_STAMP(5);
+        if (issuer) umma_commit_2sm(fco_done);
+        if (issuer) VB_STAMP(5);
         mbar_wait(x_ready, 0);
         tc_fence_after();
-        VB_STAMP(6);
+        if (issuer) VB_STAMP(6);
         for (int step = 0; step < 8; ++step) {
-          VB_STAMP(8 + step);
+          if (issuer) VB_STAMP(8 + step);
           const int is_fc2 = (step == 7) ? 1 : (step == 0 ? 0 : ((step & 1) ? 0 : 1));
           const int c = (step == 0) ? 0 : (step == 7 ? 3 : ((step & 1) ? (step + 1) >> 1 : (step >> 1) - 1));
           if (!is_fc2) {
@@ -739,16 +749,16 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
               tc_fence_after();
             }
             for (int kb = 0; kb < 4; ++kb) unit(bufB + kb * VB_SUB, TM_H, idesc_w, kb == 0);
-            umma_commit_2sm(hfull);
+            if (issuer) umma_commit_2sm(hfull);
           } else {
             mbar_wait(sfull, static_cast<uint32_t>(c & 1));
             tc_fence_after();
             for (int kb = 0; kb < 4; ++kb) unit(bufA + kb * VB_SUB, TM_Y, idesc_w, c == 0 && kb == 0);
-            umma_commit_2sm(sempty);
+            if (issuer) umma_commit_2sm(sempty);
           }
         }
-        umma_commit_2sm(y_done);
-        VB_STAMP(7);
+        if (issuer) umma_commit_2sm(y_done);
+        if (issuer) VB_STAMP(7);
       }
     }
   } else {
