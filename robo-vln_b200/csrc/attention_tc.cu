@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(AT_THREADS) bert_attn_tc_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap tmKV,
                                                                    h16* __restrict__ ctx, int L, int LP, int heads) {
   extern __shared__ uint8_t at_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = at_raw + ((1024u - (smem_u32(at_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;
   uint8_t* sV = smem + 2 * 16384;

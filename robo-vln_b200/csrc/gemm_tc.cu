@@ -170,7 +170,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   if (threadIdx.x == 0) GT_STAMP(0);
   __shared__ float gn_x[GN ? 2 * 8 * 16 : 1];   // GroupNorm: (sum, sumsq) x 8 groups per epilogue warp, double-buffered
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic ON the __shared__ array: rounding the address through an integer made every
+  // later access a generic LD.E / ST.E instead of LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   // resident-B mode: [nstages A buffers][num_kb B blocks]; otherwise [STAGES A buffers][STAGES B buffers]
   uint8_t* smem_b = smem + (p.b_res ? nstages : STAGES) * A_STAGE_BYTES;

@@ -217,7 +217,7 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmWo,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const VlaBlockParams p) {
   extern __shared__ uint8_t vb_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vb_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = vb_raw + ((1024u - (smem_u32(vb_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* bufA = smem + VB_OFF_A;
   uint8_t* bufB = smem + VB_OFF_B;
   uint8_t* sP = smem + VB_OFF_P;
@@ -595,7 +595,7 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmWo,
                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const VlaBlockParams p) {
   extern __shared__ uint8_t vb_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(vb_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = vb_raw + ((1024u - (smem_u32(vb_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* bufA = smem + VB_OFF_A;
   uint8_t* bufB = smem + VB_OFF_B;
   uint8_t* sP = smem + VB_OFF_P;
