@@ -472,7 +472,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // sums over the group's columns, a segmented warp shuffle over the sample's rows and, for 64-pixel
         // samples, one exchange between the two warps that share the sample.  Fixed order: bit-reproducible.
         const int cpg = p.gn_cpg, hw = p.gn_hw;
-        const int ngrp = 64 / cpg;                       // groups per chunk: 8, 4, 2 or 1
         const float inv_cnt = 1.0f / static_cast<float>(hw * cpg);
         const int pair_bar = 3 + group * 2 + (quad >> 1);
 #pragma unroll 1
@@ -494,25 +493,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld_32x32(taddr + c0 + 32, v1);
           }
           tmem_ld_wait();
-          // per-thread sums per group (ngrp <= 8), then over the sample's rows
+          // Per-thread sums over fixed 8-column UNITS (static register indices: two instructions per element), folded
+          // into groups of cpg = 8 / 16 / 32 / 64 columns afterwards: after the fold, slot u holds the totals of the
+          // group that contains unit u, so the normalisation below indexes its mean / rstd statically as well.  (Selecting
+          // the group of every column at run time cost ~20 predicated instructions per element.)
           float gs[8], gq[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.0f;
+          for (int u = 0; u < 8; ++u) gs[u] = gq[u] = 0.0f;
 #pragma unroll
           for (int j = 0; j < 64; ++j) {
             const float x = __uint_as_float(v[j]);
-            const int g = (cpg == 8) ? (j >> 3) : (cpg == 16) ? (j >> 4) : (cpg == 32) ? (j >> 5) : 0;
-#pragma unroll
-            for (int gg = 0; gg < 8; ++gg)
-              if (gg == g) { gs[gg] += x; gq[gg] = fmaf(x, x, gq[gg]); }
+            gs[j >> 3] += x;
+            gq[j >> 3] = fmaf(x, x, gq[j >> 3]);
           }
-          const int seg = hw < 32 ? hw : 32;
+          if (cpg >= 16) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g < ngrp) {
+            for (int u = 0; u < 8; u += 2) { gs[u] += gs[u + 1]; gq[u] += gq[u + 1]; }
+          }
+          if (cpg >= 32) {
+#pragma unroll
+            for (int u = 0; u < 8; u += 4) { gs[u] += gs[u + 2]; gq[u] += gq[u + 2]; }
+          }
+          if (cpg >= 64) { gs[0] += gs[4]; gq[0] += gq[4]; }
+          // group totals over the sample's rows: only the leading slot of every group is reduced
+          const int seg = hw < 32 ? hw : 32;
+          const int ustep = cpg >> 3;   // 1, 2, 4 or 8 slots per group
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if ((u & (ustep - 1)) == 0) {
               for (int o = 1; o < seg; o <<= 1) {
-                gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o);
-                gq[g] += __shfl_xor_sync(0xffffffffu, gq[g], o);
+                gs[u] += __shfl_xor_sync(0xffffffffu, gs[u], o);
+                gq[u] += __shfl_xor_sync(0xffffffffu, gq[u], o);
               }
             }
           }
@@ -521,24 +532,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* other = gn_x + ((gn_par * 8 + ((warp - 2) ^ 1)) * 16);
             if (lane == 0) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) { mine[2 * g] = gs[g]; mine[2 * g + 1] = gq[g]; }
+              for (int u = 0; u < 8; ++u) { mine[2 * u] = gs[u]; mine[2 * u + 1] = gq[u]; }
             }
             named_bar_sync(pair_bar, 64);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int u = 0; u < 8; ++u) {
               // fold in quad order so that both warps compute bit-identical totals
-              const float a = (quad & 1) ? other[2 * g] : gs[g], b = (quad & 1) ? gs[g] : other[2 * g];
-              const float c = (quad & 1) ? other[2 * g + 1] : gq[g], d = (quad & 1) ? gq[g] : other[2 * g + 1];
-              gs[g] = a + b;
-              gq[g] = c + d;
+              const float a = (quad & 1) ? other[2 * u] : gs[u], b = (quad & 1) ? gs[u] : other[2 * u];
+              const float c = (quad & 1) ? other[2 * u + 1] : gq[u], d = (quad & 1) ? gq[u] : other[2 * u + 1];
+              gs[u] = a + b;
+              gq[u] = c + d;
             }
             gn_par ^= 1;
           }
+          // every slot takes the totals of its group's leading slot
+          if (cpg >= 64) { gs[4] = gs[0]; gq[4] = gq[0]; }
+          if (cpg >= 32) {
+#pragma unroll
+            for (int u = 0; u < 8; u += 4) { gs[u + 2] = gs[u]; gq[u + 2] = gq[u]; }
+          }
+          if (cpg >= 16) {
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) { gs[u + 1] = gs[u]; gq[u + 1] = gq[u]; }
+          }
           float gmean[8], grstd[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            gmean[g] = gs[g] * inv_cnt;
-            grstd[g] = rsqrtf(fmaxf(gq[g] * inv_cnt - gmean[g] * gmean[g], 0.0f) + 1e-5f);
+          for (int u = 0; u < 8; ++u) {
+            gmean[u] = gs[u] * inv_cnt;
+            grstd[u] = rsqrtf(fmaxf(gq[u] * inv_cnt - gmean[u] * gmean[u], 0.0f) + 1e-5f);
           }
           if (store_pending) {
             if (p.plain) {
@@ -559,15 +580,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + n + j));
               const float gam[4] = {g4.x, g4.y, g4.z, g4.w}, bet[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int jj = j + t;
-                const int g = (cpg == 8) ? (jj >> 3) : (cpg == 16) ? (jj >> 4) : (cpg == 32) ? (jj >> 5) : 0;
-                float mean = gmean[0], rstd = grstd[0];
-#pragma unroll
-                for (int gg = 1; gg < 8; ++gg)
-                  if (gg == g) { mean = gmean[gg]; rstd = grstd[gg]; }
-                f[e + t] = (__uint_as_float(v[jj]) - mean) * rstd * gam[t] + bet[t];
-              }
+              for (int t = 0; t < 4; ++t)
+                f[e + t] = (__uint_as_float(v[j + t]) - gmean[j8]) * grstd[j8] * gam[t] + bet[t];
             }
             if (res_row != nullptr) {
               const uint4 r4 = rres[j8];
