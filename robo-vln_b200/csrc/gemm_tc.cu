@@ -372,6 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row_in_tile = quad * 32 + lane;
     const bool leader = (quad == 2 && lane == 0);  // first thread of the group (warps 2 and 6)
     uint8_t* stage_buf = smem_c + group * 16384;
+    // BN = 64, 16-bit output, no residual: a tile is ONE 64-column chunk, which would leave the second warp group idle.
+    // The two groups take alternate TILES instead (group g owns the tiles accumulated in TMEM buffer g): both staging
+    // buffers and both sets of four warps work, and the epilogue of tile t + 1 overlaps that of tile t.
+    const bool alt_tiles = !LN && !GN && BN == 64 && !p.out_f32 && p.tma_store && p.res == nullptr;
+    const int cgroup = alt_tiles ? 0 : group;   // chunk-column group
     uint8_t* my_row = stage_buf + row_in_tile * 128;
     const int sw = row_in_tile & 7;
     // columns per chunk: one 128-byte row segment of the output type
@@ -439,9 +444,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 
       // plain epilogue: this warp's bias values for the whole tile, lane-distributed -- 32-column slot s of the warp's
-      // columns lives in bl[s] (16-bit output: chunk group + 2i = slots 2i, 2i + 1; fp32 output: chunk group + 2i = slot i)
-      constexpr int BSLOTS = (!LN && !GN) ? (BN / 64 < 2 ? 2 : BN / 64) : 1;
-      float bl[BSLOTS];
+      // columns lives in bl<s> (16-bit output: chunk group + 2i = slots 2i, 2i + 1; fp32 output: chunk group + 2i = slot i)
+      // (scalars, selected with ternaries below: as an indexed array they were put in local memory and fetched with LDL)
+      float bl0 = 0.0f, bl1 = 0.0f, bl2 = 0.0f, bl3 = 0.0f;
       uint4 rcur[4];
       const bool res_pre = !LN && !GN && p.out_f32 && p.tma_store && res_row != nullptr;
       auto load_res = [&](int ch_, uint4 (&dst)[4]) {   // fp32 output: residual of one 32-column chunk of this thread's row
@@ -451,13 +456,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           dst[j] = (ch_ < BN / 32 && nn < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + nn) + j) : make_uint4(0, 0, 0, 0);
       };
       if constexpr (!LN && !GN) {
-#pragma unroll
-        for (int s_ = 0; s_ < BSLOTS; ++s_) {
-          // slot -> first column: 16-bit: chunk (group + 2*(s_/2)) * 64 + (s_%2) * 32; fp32: chunk (group + 2*s_) * 32
-          const int col = p.out_f32 ? (group + 2 * s_) * 32 : (group + 2 * (s_ >> 1)) * 64 + (s_ & 1) * 32;
+        auto slot_bias = [&](int s_) {
+          // slot -> first column: 16-bit: chunk (cgroup + 2*(s_/2)) * 64 + (s_%2) * 32; fp32: chunk (cgroup + 2*s_) * 32
+          const int col = p.out_f32 ? (cgroup + 2 * s_) * 32 : (cgroup + 2 * (s_ >> 1)) * 64 + (s_ & 1) * 32;
           const int nn = n0 + col + lane;
-          bl[s_] = (p.bias != nullptr && col < BN && nn < p.N) ? __ldg(p.bias + nn) : 0.0f;
-        }
+          return (p.bias != nullptr && col < BN && nn < p.N) ? __ldg(p.bias + nn) : 0.0f;
+        };
+        bl0 = slot_bias(0);
+        bl1 = slot_bias(1);
+        if (BN >= 192) { bl2 = slot_bias(2); bl3 = slot_bias(3); }
         if (res_pre) load_res(group, rcur);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -777,7 +784,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (!LN && !GN && p.tma_store) {
 #pragma unroll 1
-        for (int ch = group; ch < n_chunks; ch += 2) {
+        for (int ch = (alt_tiles && acc != group) ? n_chunks : cgroup; ch < n_chunks; ch += 2) {
           const int c0 = ch * chunk_cols;
           const int n = n0 + c0;
           if (n >= p.N) break;  // uniform across the group
@@ -814,10 +821,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
             }
             {
-              float bsel = 0.0f;
-#pragma unroll
-              for (int s_ = 0; s_ < BSLOTS; ++s_)
-                if (s_ == ((ch - group) >> 1)) bsel = bl[s_];
+              const int bi = (ch - cgroup) >> 1;
+              const float bsel = (bi == 0) ? bl0 : (bi == 1) ? bl1 : (bi == 2) ? bl2 : bl3;
               epilogue_math_b(f, p, n, res_pre ? nullptr : res_row, bsel);
             }
 #pragma unroll
@@ -866,10 +871,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
               if (!(p.dbg & 2)) {
-                float bsel = 0.0f;
-#pragma unroll
-                for (int s_ = 0; s_ < BSLOTS; ++s_)
-                  if (s_ == (ch - group) + half) bsel = bl[s_];      // slot 2 * ((ch - group) / 2) + half
+                const int bi = (ch - cgroup) + half;      // slot 2 * ((ch - cgroup) / 2) + half
+                const float bsel = (bi == 0) ? bl0 : (bi == 1) ? bl1 : (bi == 2) ? bl2 : bl3;
                 epilogue_math_b(f, p, n + half * 32, p.res_tma ? nullptr : res_row, bsel, true);
               }
               if (p.act == ACT_RELU) {   // ReLU, saturation, rounding and packing in one F2FP per pair
