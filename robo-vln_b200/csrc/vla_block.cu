@@ -552,7 +552,11 @@ vla_block_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc4[k & 3] += x[k];
       }
-      for (; r < p.L; ++r) acc4[r & 3] += from_h16(*reinterpret_cast<const h16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
+      // tail: r is a multiple of 8 here, so row r + k has k = (r + k) & 7 and goes to accumulator k & 3 -- static indices
+      // (indexing acc4 with the run-time row number had put the four accumulators in local memory)
+#pragma unroll
+      for (int k = 0; k < 7; ++k)
+        if (r + k < p.L) acc4[k & 3] += from_h16(*reinterpret_cast<const h16*>(colp + (r + k) * 128 + ((chunk ^ k) << 4)));
       const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       p.out[static_cast<long long>(env) * p.out_pitch + mod * 256 + et] = to_h16(acc / static_cast<float>(p.L));
       if (et == 0) VB_STAMP(56);
@@ -925,7 +929,11 @@ vla_pair_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc4[k & 3] += x[k];
       }
-      for (; r < p.L; ++r) acc4[r & 3] += from_h16(*reinterpret_cast<const h16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
+      // tail: r is a multiple of 8 here, so row r + k has k = (r + k) & 7 and goes to accumulator k & 3 -- static indices
+      // (indexing acc4 with the run-time row number had put the four accumulators in local memory)
+#pragma unroll
+      for (int k = 0; k < 7; ++k)
+        if (r + k < p.L) acc4[k & 3] += from_h16(*reinterpret_cast<const h16*>(colp + (r + k) * 128 + ((chunk ^ k) << 4)));
       const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       p.out[static_cast<long long>(env) * p.out_pitch + mod * 256 + et] = to_h16(acc / static_cast<float>(p.L));
       if (et == 0) VB_STAMP(56);
