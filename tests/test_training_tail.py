@@ -148,3 +148,21 @@ def test_segment_starts_and_precomputed_segments():
     hh = (torch.ones(2, requires_grad=True) * 2, (torch.ones(1, requires_grad=True) * 3,))
     out = trainer.repackage_hidden(hh)
     assert not out[0].requires_grad and not out[1][0].requires_grad
+
+
+def test_dagger_updater_mirrors_update_agent_signature(golden_dir):
+    """trainer.DaggerUpdater.update takes the arguments of the reference's _update_agent in the same order and returns
+    the same 4-tuple (fixture: oracle/make_golden_api.py, read with ast from the unmodified reference source)."""
+    import inspect
+    import json
+    import os
+
+    from robovln_b200 import trainer
+
+    api = json.load(open(os.path.join(golden_dir, "update_agent_api.json")))
+    params = [p for p in inspect.signature(trainer.DaggerUpdater.update).parameters if p != "self"]
+    assert params == api["args"]
+    assert api["returns"] == ["loss", "high_recurrent_hidden_states", "low_recurrent_hidden_states", "detached_state_low"]
+    assert api["loss_tuple_len"] == 4
+    src = inspect.getsource(trainer.DaggerUpdater.update)
+    assert "return loss, hi_hidden, lo_hidden, detached_state_low" in src
