@@ -41,7 +41,7 @@ RVB_DEVICE void mma_h16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t 
 
 // LKT = number of 16-key tiles (keys padded to 16*LKT)
 template <int LKT>
-__global__ void __launch_bounds__(256) bert_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ ctx, int L,
+__global__ void __launch_bounds__(256, (LKT <= 5) ? 4 : 1) bert_attn_kernel(const h16* __restrict__ qkv, h16* __restrict__ ctx, int L,
                                                         int heads) {
   RVB_PDL_PROLOGUE();
   constexpr int LP = LKT * 16;
